@@ -1,0 +1,223 @@
+"""CPU oracle — TEST INFRASTRUCTURE ONLY.
+
+ctypes front-end of ``oracle/liboracle.so`` (``pbn_oracle.cpp``), the plain C++
+restatement of the reference's KDE/CKDE log-likelihood path.  Only ``tests/``,
+``__graft_entry__.smoke()`` and the CPU-baseline legs of ``bench.py`` may import this
+package; ``pybnesian_b200`` never does.
+
+All matrices are passed column-major (``order='F'``), null rows already removed —
+the layout ``DataFrame::to_eigen`` hands to the reference's kernels
+(/root/reference/pybnesian/dataset/dataset.hpp:236-338).
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+
+_c_i64 = ctypes.c_int64
+_c_int = ctypes.c_int
+_c_dp = ctypes.POINTER(ctypes.c_double)
+_c_vp = ctypes.c_void_p
+
+
+def build(force=False):
+    """Compile liboracle.so (and oracle/_ref when the reference tree is present)."""
+    src = os.path.join(_HERE, "pbn_oracle.cpp")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "liboracle.so"])
+    if os.path.isdir("/root/reference/pybnesian/kde/opencl_kernels") and os.path.isdir(os.path.join(_HERE, "ref_shim")):
+        subprocess.check_call(["make", "-C", _HERE, "ref"])
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        _lib = ctypes.CDLL(_LIB_PATH)
+        _lib.orc_num_threads.restype = _c_int
+    return _lib
+
+
+def _dtype_code(a):
+    if a.dtype == np.float64:
+        return 0
+    if a.dtype == np.float32:
+        return 1
+    raise ValueError("oracle: only float64 / float32 data")
+
+
+def _fmat(a):
+    a = np.asarray(a)
+    if a.ndim == 1:
+        a = a.reshape(-1, 1)
+    return np.asfortranarray(a)
+
+
+def _dptr(a):
+    return a.ctypes.data_as(_c_dp)
+
+
+def num_threads():
+    return lib().orc_num_threads()
+
+
+def cov(X):
+    X = _fmat(X)
+    n, d = X.shape
+    out = np.empty((d, d), order="F")
+    lib().orc_cov(_c_vp(X.ctypes.data), _c_i64(n), _c_int(d), _c_int(_dtype_code(X)), _dptr(out))
+    return out
+
+
+class SingularCovariance(ValueError):
+    pass
+
+
+def bandwidth(X, rule="normal_reference"):
+    """NormalReferenceRule / ScottsBandwidth bandwidth matrix (d x d float64)."""
+    X = _fmat(X)
+    n, d = X.shape
+    H = np.empty((d, d), order="F")
+    st = lib().orc_bandwidth(_c_vp(X.ctypes.data), _c_i64(n), _c_int(d), _c_int(_dtype_code(X)),
+                             _c_int(0 if rule == "normal_reference" else 1), _dptr(H))
+    if st:
+        raise SingularCovariance("status %d" % st)
+    return H
+
+
+def kde_prepare(H, N):
+    H = np.asfortranarray(np.asarray(H, dtype=np.float64))
+    d = H.shape[0]
+    L = np.empty((d, d), order="F")
+    ln = ctypes.c_double()
+    st = lib().orc_kde_prepare(_dptr(H), _c_int(d), _c_i64(N), _dptr(L), ctypes.byref(ln))
+    if st:
+        raise SingularCovariance("bandwidth not positive definite")
+    return L, ln.value
+
+
+def _logl_call(fn, train, test, H):
+    train, test = _fmat(train), _fmat(test)
+    assert train.dtype == test.dtype and train.shape[1] == test.shape[1]
+    N, d = train.shape
+    m = test.shape[0]
+    H = np.asfortranarray(np.asarray(H, dtype=np.float64))
+    out = np.empty(m)
+    s = ctypes.c_double()
+    fn(_c_vp(train.ctypes.data), _c_i64(N), _c_vp(test.ctypes.data), _c_i64(m), _c_int(d),
+       _c_int(_dtype_code(train)), _dptr(H), _dptr(out), ctypes.byref(s))
+    return out, s.value
+
+
+def kde_logl(train, test, H):
+    """(logl[m], slogl) of a KDE with bandwidth H, reference arithmetic in the data's dtype."""
+    return _logl_call(lib().orc_kde_logl, train, test, H)
+
+
+def ckde_logl(train, test, Hjoint):
+    """(logl[m], slogl) of CKDE(col 0 | cols 1..): joint - marginal with H[1:,1:]."""
+    return _logl_call(lib().orc_ckde_logl, train, test, Hjoint)
+
+
+def kde_logl_ld(train, test, H):
+    """Long-double direct evaluation (independent cross-check of the restatement)."""
+    train, test = _fmat(train), _fmat(test)
+    N, d = train.shape
+    m = test.shape[0]
+    H = np.asfortranarray(np.asarray(H, dtype=np.float64))
+    out = np.empty(m)
+    st = lib().orc_kde_logl_ld(_c_vp(train.ctypes.data), _c_i64(N), _c_vp(test.ctypes.data), _c_i64(m), _c_int(d),
+                               _c_int(_dtype_code(train)), _dptr(H), _dptr(out))
+    if st:
+        raise SingularCovariance("bandwidth not positive definite")
+    return out
+
+
+def ucv_score_unconstrained(X, H):
+    X = _fmat(X)
+    N, d = X.shape
+    H = np.asfortranarray(np.asarray(H, dtype=np.float64).reshape(d, d))
+    out = ctypes.c_double()
+    lib().orc_ucv_score_unconstrained(_c_vp(X.ctypes.data), _c_i64(N), _c_int(d), _c_int(_dtype_code(X)), _dptr(H),
+                                      ctypes.byref(out))
+    return out.value
+
+
+def ucv_score_diagonal(X, hdiag):
+    X = _fmat(X)
+    N, d = X.shape
+    h = np.ascontiguousarray(np.asarray(hdiag, dtype=np.float64))
+    out = ctypes.c_double()
+    lib().orc_ucv_score_diagonal(_c_vp(X.ctypes.data), _c_i64(N), _c_int(d), _c_int(_dtype_code(X)), _dptr(h),
+                                 ctypes.byref(out))
+    return out.value
+
+
+def cv_indices(valid_rows, k, seed):
+    """Shuffled indices + fold limits (CrossValidationProperties)."""
+    idx = np.ascontiguousarray(np.asarray(valid_rows, dtype=np.int32)).copy()
+    limits = np.empty(k + 1, dtype=np.int32)
+    lib().orc_cv_indices(idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), _c_i64(idx.size), _c_int(k),
+                         ctypes.c_uint32(seed), limits.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)))
+    return idx, limits
+
+
+def holdout_indices(valid_rows, test_ratio, seed):
+    idx = np.ascontiguousarray(np.asarray(valid_rows, dtype=np.int32)).copy()
+    ntr = ctypes.c_int32()
+    lib().orc_holdout_indices(idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), _c_i64(idx.size),
+                              ctypes.c_double(test_ratio), ctypes.c_uint32(seed), ctypes.byref(ntr))
+    return idx[:ntr.value], idx[ntr.value:]
+
+
+def _colptrs(cols):
+    arr = (ctypes.c_void_p * len(cols))(*[c.ctypes.data for c in cols])
+    return arr
+
+
+def lg_fit(y, parents):
+    """MLE of a LinearGaussianCPD: (beta[p+1], variance)."""
+    cols = [np.ascontiguousarray(y)] + [np.ascontiguousarray(p) for p in parents]
+    p = len(cols) - 1
+    beta = np.empty(p + 1)
+    var = ctypes.c_double()
+    lib().orc_lg_fit(_colptrs(cols), _c_i64(cols[0].size), _c_int(p), _c_int(_dtype_code(cols[0])), _dptr(beta),
+                     ctypes.byref(var))
+    return beta, var.value
+
+
+def lg_logl(y, parents, beta, variance):
+    cols = [np.ascontiguousarray(y)] + [np.ascontiguousarray(p) for p in parents]
+    p = len(cols) - 1
+    m = cols[0].size
+    beta = np.ascontiguousarray(np.asarray(beta, dtype=np.float64))
+    out = np.empty(m)
+    s = ctypes.c_double()
+    lib().orc_lg_logl(_colptrs(cols), _c_i64(m), _c_int(p), _c_int(_dtype_code(cols[0])), _dptr(beta),
+                      ctypes.c_double(variance), _dptr(out), ctypes.byref(s))
+    return out, s.value
+
+
+def cv_score(X, indices, limits, factor="ckde", rule="normal_reference"):
+    """CVLikelihood.local_score for column 0 given columns 1.. (X: all rows, column-major)."""
+    X = _fmat(X)
+    n, d = X.shape
+    indices = np.ascontiguousarray(indices, dtype=np.int32)
+    limits = np.ascontiguousarray(limits, dtype=np.int32)
+    out = ctypes.c_double()
+    st = lib().orc_cv_score(_c_vp(X.ctypes.data), _c_i64(n), _c_int(d), _c_int(_dtype_code(X)),
+                            indices.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                            limits.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), _c_int(limits.size - 1),
+                            _c_int(0 if factor == "ckde" else 1), _c_int(0 if rule == "normal_reference" else 1),
+                            ctypes.byref(out))
+    if st:
+        raise SingularCovariance("status %d" % st)
+    return out.value
