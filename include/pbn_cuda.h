@@ -1,0 +1,130 @@
+/* pbn_cuda.h — C ABI of libpbn_cuda.so: the B200 (sm_100a) device layer that replaces
+ * PyBNesian's OpenCL layer for the KDE / CKDE log-likelihood hot path.
+ *
+ * Every entry point cites the reference interface it stands in for (paths relative to
+ * /root/reference/pybnesian/).  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Conventions
+ *   - every function returns PBN_OK (0) or a PBN_ERR_* code; pbn_last_error() gives the
+ *     message of the last failure on the calling thread.
+ *   - dtype: PBN_F64 / PBN_F32 (the Arrow column type; all columns of a table agree,
+ *     dataset/dataset.cpp:253-271).
+ *   - host matrices (bandwidths, covariances) are column-major double, d x d.
+ *   - a "row range" is two half-open segments [b0,e0) ++ [b1,e1) of table rows: a
+ *     cross-validation training set is exactly that on a table stored in shuffled order
+ *     (dataset/crossvalidation_adaptator.cpp:5-31); pass b1 == e1 for a single segment.
+ *   - tables hold null-free columns: dropping rows with nulls is done by the caller,
+ *     as DataFrame::to_eigen does for the reference (dataset/dataset.hpp:236-338).
+ */
+#ifndef PBN_CUDA_H
+#define PBN_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PBN_OK 0
+#define PBN_ERR_CUDA 1        /* a CUDA runtime call failed  -> RuntimeError (opencl_config.hpp:19-27) */
+#define PBN_ERR_ARG 2         /* invalid argument            -> ValueError */
+#define PBN_ERR_SINGULAR 3    /* SingularCovarianceData      (util/exceptions.hpp, NormalReferenceRule.hpp:37-60) */
+#define PBN_ERR_UNSUPPORTED 4
+
+#define PBN_F64 0
+#define PBN_F32 1
+
+#define PBN_BW_NORMAL_REFERENCE 0 /* kde/NormalReferenceRule.hpp:109-134 */
+#define PBN_BW_SCOTT 1            /* kde/ScottsBandwidth.hpp:91-117 */
+
+#define PBN_MAX_DIM 32
+
+typedef struct pbn_ctx pbn_ctx;     /* one GPU: device id, stream, scratch memory          */
+typedef struct pbn_table pbn_table; /* resident column store (uploaded once, kept in HBM)  */
+typedef struct pbn_kde pbn_kde;     /* fitted KDE or CKDE: whitened training rows on device */
+
+typedef struct pbn_rows {
+    int64_t b0, e0, b1, e1;
+} pbn_rows;
+
+const char* pbn_last_error(void);
+const char* pbn_version(void);
+int pbn_device_count(int* out);
+
+/* Replaces opencl::OpenCLConfig::get() (opencl/opencl_config.cpp:149-220): one context
+ * per GPU instead of a process-wide platform-0/device-0 singleton. */
+int pbn_ctx_create(int device, pbn_ctx** out);
+int pbn_ctx_destroy(pbn_ctx* ctx);
+/* Use an externally owned cudaStream_t (e.g. torch's current stream); NULL restores the own stream. */
+int pbn_ctx_set_stream(pbn_ctx* ctx, void* cuda_stream);
+void* pbn_ctx_stream(pbn_ctx* ctx);
+int pbn_ctx_synchronize(pbn_ctx* ctx);
+int pbn_ctx_sm_count(pbn_ctx* ctx);
+/* Counters since context creation: kernel launches issued by this library, host->device
+ * and device->host bytes it copied. */
+int pbn_ctx_counters(pbn_ctx* ctx, int64_t* launches, int64_t* h2d_bytes, int64_t* d2h_bytes);
+
+/* Replaces OpenCLConfig::copy_to_buffer (opencl/opencl_config.hpp:226-239) applied to
+ * DataFrame::to_eigen output: uploads `ncols` dense host columns of `nrows` values once;
+ * the table stays resident until freed. */
+int pbn_table_upload(pbn_ctx* ctx, const void* const* col_ptrs, int ncols, int64_t nrows, int dtype,
+                     pbn_table** out);
+/* Same, from pageable or pinned host memory already laid out column-major (one block). */
+int pbn_table_free(pbn_table* tbl);
+int64_t pbn_table_rows(const pbn_table* tbl);
+int pbn_table_cols(const pbn_table* tbl);
+/* Replaces OpenCLConfig::read_from_buffer (opencl_config.hpp:241-250) for KDE pickling
+ * (kde/KDE.hpp:642-666): copies rows of one column back to the host. */
+int pbn_table_download(pbn_ctx* ctx, const pbn_table* tbl, int col, pbn_rows rows, void* out);
+
+/* Sample mean and unbiased covariance of the selected columns over a row range
+ * (DataFrame::cov, dataset/dataset.hpp:341-396), computed on the device (two passes,
+ * fp64 accumulation) and returned to the host. */
+int pbn_table_moments(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, pbn_rows rows,
+                      double* mean_out, double* cov_out);
+
+/* NormalReferenceRule / ScottsBandwidth ::bandwidth (kde/NormalReferenceRule.hpp:37-60,109-134;
+ * kde/ScottsBandwidth.hpp:33-56,91-117).  Fails with PBN_ERR_SINGULAR when rows <= d or the
+ * covariance is not positive definite (util/basic_eigen_ops.hpp:136-147). */
+int pbn_bandwidth(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, pbn_rows rows, int rule,
+                  double* H_out);
+/* diag_bandwidth of the same selectors (NormalReferenceRule.hpp:72-106; ScottsBandwidth.hpp:66-89). */
+int pbn_diag_bandwidth(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, pbn_rows rows, int rule,
+                       double* h_out);
+
+/* KDE::fit<>(bandwidth, buffer, type, N) / KDE::_fit (kde/KDE.hpp:451-511): Cholesky of H,
+ * lognorm constant, training rows made resident (whitened with the Cholesky factor).
+ * `cols[0..d)` are table columns in the KDE's variable order. */
+int pbn_kde_fit(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, pbn_rows rows, const double* H,
+                pbn_kde** out);
+/* CKDE::_fit (factors/continuous/CKDE.hpp:182-200): cols[0] = variable, cols[1..d) = evidence,
+ * H = joint bandwidth; the marginal uses H[1:,1:] on the same rows.  d == 1 is a plain KDE. */
+int pbn_ckde_fit(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, pbn_rows rows, const double* H,
+                 pbn_kde** out);
+int pbn_kde_free(pbn_kde* kde);
+int64_t pbn_kde_num_instances(const pbn_kde* kde);
+double pbn_kde_lognorm(const pbn_kde* kde); /* joint lognorm (kde/KDE.hpp:476-477) */
+
+/* KDE::logl / slogl (kde/KDE.hpp:513-640) and CKDE::logl / slogl
+ * (factors/continuous/CKDE.hpp:202-287) for a fitted model: one fused launch over
+ * train x test tiles.  `cols` index the test table in the same variable order as fit.
+ * out_logl (host, rows.count doubles) and out_slogl (host, 1 double) may each be NULL. */
+int pbn_kde_logl(pbn_ctx* ctx, const pbn_kde* kde, const pbn_table* test, const int* cols, pbn_rows rows,
+                 double* out_logl, double* out_slogl);
+/* Asynchronous form for benchmarking / pipelining: result stays on the device
+ * (d_out_logl: rows.count doubles or NULL; d_out_slogl: 1 double or NULL), no host sync. */
+int pbn_kde_logl_device(pbn_ctx* ctx, const pbn_kde* kde, const pbn_table* test, const int* cols, pbn_rows rows,
+                        double* d_out_logl, double* d_out_slogl);
+/* Number of test rows of the last logl call on this context that needed the shifted
+ * (max-subtracted) re-evaluation because their unshifted kernel sum underflowed. */
+int pbn_ctx_last_fallback_rows(pbn_ctx* ctx, int64_t* out);
+
+/* Device scratch for callers that keep results on the GPU (e.g. bench.py). */
+int pbn_device_alloc(pbn_ctx* ctx, int64_t bytes, void** out);
+int pbn_device_free(pbn_ctx* ctx, void* ptr);
+int pbn_device_read(pbn_ctx* ctx, const void* dptr, int64_t bytes, void* host_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PBN_CUDA_H */

@@ -1,0 +1,12 @@
+"""pybnesian_b200 — B200-native (sm_100a) implementation of PyBNesian's KDE / CKDE
+log-likelihood hot path behind the reference's Python API.
+
+Same class names as `pybnesian` for the path: KDE, CKDE, CKDEType, BandwidthSelector,
+NormalReferenceRule, ScottsBandwidth, SingularCovarianceData, ...
+"""
+from ._lib import SingularCovarianceData, Context, default_context, LIB_PATH
+from .dataset import DataFrame
+from .kde import BandwidthSelector, NormalReferenceRule, ScottsBandwidth, KDE
+from .factors import Factor, FactorType, CKDE, CKDEType
+
+__version__ = "0.1.0"

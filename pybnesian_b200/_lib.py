@@ -1,0 +1,150 @@
+"""ctypes binding of libpbn_cuda.so (C ABI in include/pbn_cuda.h).
+
+There is no CPU fallback: if the CUDA library is missing or no sm_100 GPU is usable,
+the first compute call raises (RuntimeError), it never silently computes elsewhere.
+"""
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpbn_cuda.so")
+
+PBN_OK, PBN_ERR_CUDA, PBN_ERR_ARG, PBN_ERR_SINGULAR, PBN_ERR_UNSUPPORTED = 0, 1, 2, 3, 4
+PBN_F64, PBN_F32 = 0, 1
+BW_NORMAL_REFERENCE, BW_SCOTT = 0, 1
+
+EXPORTS = [
+    "pbn_last_error", "pbn_version", "pbn_device_count", "pbn_ctx_create", "pbn_ctx_destroy", "pbn_ctx_set_stream",
+    "pbn_ctx_stream", "pbn_ctx_synchronize", "pbn_ctx_sm_count", "pbn_ctx_counters", "pbn_table_upload",
+    "pbn_table_free", "pbn_table_rows", "pbn_table_cols", "pbn_table_download", "pbn_table_moments", "pbn_bandwidth",
+    "pbn_diag_bandwidth", "pbn_kde_fit", "pbn_ckde_fit", "pbn_kde_free", "pbn_kde_num_instances", "pbn_kde_lognorm",
+    "pbn_kde_logl", "pbn_kde_logl_device", "pbn_ctx_last_fallback_rows", "pbn_device_alloc", "pbn_device_free",
+    "pbn_device_read",
+]
+
+
+class SingularCovarianceData(ValueError):
+    """Mirror of pybnesian.SingularCovarianceData (pybindings_kde.cpp:114), a ValueError."""
+
+
+class Rows(ctypes.Structure):
+    _fields_ = [("b0", ctypes.c_int64), ("e0", ctypes.c_int64), ("b1", ctypes.c_int64), ("e1", ctypes.c_int64)]
+
+    @staticmethod
+    def single(begin, end):
+        return Rows(begin, end, 0, 0)
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "pybnesian_b200: CUDA extension %s is not built. Run `python -c 'import __graft_entry__ as g; "
+                "g.build()'` (or `make -C pybnesian_b200/csrc`). There is no CPU fallback." % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        vp, i64, ci, dp = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.POINTER(ctypes.c_double)
+        ip = ctypes.POINTER(ctypes.c_int)
+        L.pbn_last_error.restype = ctypes.c_char_p
+        L.pbn_version.restype = ctypes.c_char_p
+        L.pbn_device_count.argtypes = [ip]
+        L.pbn_ctx_create.argtypes = [ci, ctypes.POINTER(vp)]
+        L.pbn_ctx_destroy.argtypes = [vp]
+        L.pbn_ctx_set_stream.argtypes = [vp, vp]
+        L.pbn_ctx_stream.argtypes = [vp]
+        L.pbn_ctx_stream.restype = vp
+        L.pbn_ctx_synchronize.argtypes = [vp]
+        L.pbn_ctx_sm_count.argtypes = [vp]
+        L.pbn_ctx_counters.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(i64)]
+        L.pbn_table_upload.argtypes = [vp, ctypes.POINTER(vp), ci, i64, ci, ctypes.POINTER(vp)]
+        L.pbn_table_free.argtypes = [vp]
+        L.pbn_table_rows.argtypes = [vp]
+        L.pbn_table_rows.restype = i64
+        L.pbn_table_cols.argtypes = [vp]
+        L.pbn_table_download.argtypes = [vp, vp, ci, Rows, vp]
+        L.pbn_table_moments.argtypes = [vp, vp, ip, ci, Rows, dp, dp]
+        L.pbn_bandwidth.argtypes = [vp, vp, ip, ci, Rows, ci, dp]
+        L.pbn_diag_bandwidth.argtypes = [vp, vp, ip, ci, Rows, ci, dp]
+        L.pbn_kde_fit.argtypes = [vp, vp, ip, ci, Rows, dp, ctypes.POINTER(vp)]
+        L.pbn_ckde_fit.argtypes = [vp, vp, ip, ci, Rows, dp, ctypes.POINTER(vp)]
+        L.pbn_kde_free.argtypes = [vp]
+        L.pbn_kde_num_instances.argtypes = [vp]
+        L.pbn_kde_num_instances.restype = i64
+        L.pbn_kde_lognorm.argtypes = [vp]
+        L.pbn_kde_lognorm.restype = ctypes.c_double
+        L.pbn_kde_logl.argtypes = [vp, vp, vp, ip, Rows, dp, dp]
+        L.pbn_kde_logl_device.argtypes = [vp, vp, vp, ip, Rows, vp, vp]
+        L.pbn_ctx_last_fallback_rows.argtypes = [vp, ctypes.POINTER(i64)]
+        L.pbn_device_alloc.argtypes = [vp, i64, ctypes.POINTER(vp)]
+        L.pbn_device_free.argtypes = [vp, vp]
+        L.pbn_device_read.argtypes = [vp, vp, i64, vp]
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc == PBN_OK:
+        return
+    msg = lib().pbn_last_error().decode("utf-8", "replace")
+    if rc == PBN_ERR_SINGULAR:
+        raise SingularCovarianceData(msg)
+    if rc in (PBN_ERR_ARG, PBN_ERR_UNSUPPORTED):
+        raise ValueError(msg)
+    raise RuntimeError(msg)
+
+
+class Context:
+    """One GPU (pbn_ctx).  The default context uses device PBN_CUDA_DEVICE, else LOCAL_RANK, else 0."""
+
+    def __init__(self, device=0):
+        self.handle = ctypes.c_void_p()
+        check(lib().pbn_ctx_create(int(device), ctypes.byref(self.handle)))
+        self.device = int(device)
+
+    def synchronize(self):
+        check(lib().pbn_ctx_synchronize(self.handle))
+
+    def set_stream(self, cuda_stream_ptr):
+        check(lib().pbn_ctx_set_stream(self.handle, ctypes.c_void_p(cuda_stream_ptr or 0)))
+
+    @property
+    def stream(self):
+        return lib().pbn_ctx_stream(self.handle)
+
+    @property
+    def sm_count(self):
+        return lib().pbn_ctx_sm_count(self.handle)
+
+    def counters(self):
+        a, b, c = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        check(lib().pbn_ctx_counters(self.handle, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return {"launches": a.value, "h2d_bytes": b.value, "d2h_bytes": c.value}
+
+    def last_fallback_rows(self):
+        v = ctypes.c_int64()
+        check(lib().pbn_ctx_last_fallback_rows(self.handle, ctypes.byref(v)))
+        return v.value
+
+
+_default_ctx = None
+
+
+def default_context():
+    global _default_ctx
+    if _default_ctx is None:
+        dev = int(os.environ.get("PBN_CUDA_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+        _default_ctx = Context(dev)
+    return _default_ctx
+
+
+def int_array(values):
+    return (ctypes.c_int * len(values))(*[int(v) for v in values])

@@ -1,0 +1,294 @@
+// pair_kernel.cuh — the train x test Gaussian-kernel-sum kernel (sm_100a).
+//
+// Replaces, in one fused launch, what the reference does with 4 kernel launches per
+// test row plus a 5-pass column log-sum-exp per 64 test rows:
+//   kde/KDE.hpp:123-212, 592-640 (MultivariateKDE::execute_logl_mat, KDE::_logl_impl),
+//   kde/opencl_kernels/KDE.cl.src:123-233 (substract, solve, square, logl_values_*),
+//   opencl/opencl_config.hpp:517-536 (logsumexp_cols_offset).
+// No N x m matrix is ever written: every (train, test) pair lives in registers.
+//
+// Inputs are *whitened* rows (see whiten_kernel in runtime.cu):  y = c * L^-1 (x - mu)
+// with c chosen so that the exponent is already in table / log2 units:
+//   f64:  t = -sum_c (yt_c - yi_c)^2  ==  256 * log2(e) * (-1/2 s)   (s = Mahalanobis^2)
+//         exp(-s/2) = 2^(t/256) = 2^k * T[j] * P(g),  n = rint(t), k = n>>8, j = n&255,
+//         g = t - n in [-1/2, 1/2], P a degree-4 polynomial (max rel. err 3.4e-16).
+//         Cost: 3 DADD + 4 DFMA + 1 DFMA (accumulate) on the FP64 pipe.
+//   f32:  t = -sum_c (..)^2 == log2(e) * (-1/2 s);  exp(-s/2) = ex2.approx(t) (1 MUFU).
+// Sums are accumulated unshifted (every term <= 1); rows whose sum is too small for
+// that to be accurate are re-run with a per-row shift by the caller (runtime.cu).
+//
+// Work decomposition ("stream-K"): a unit is (test tile of TB rows) x (train tile of
+// TILE points); units of all jobs of a launch are numbered consecutively, test-tile
+// major, and every CTA takes the same number of consecutive units.  A test tile that is
+// covered by several CTAs gets one partial-sum slot per CTA; finalize_kernel adds the
+// slots in a fixed order, so results are deterministic.
+//
+// Train tiles are staged in shared memory with 1-D TMA bulk copies
+// (cp.async.bulk.shared::cluster.global + mbarrier complete_tx), double buffered.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pbn {
+
+struct PairJob {
+    const void* train;     // whitened train rows, AoS [n_train (padded alloc)][D]
+    const void* test;      // whitened test rows, AoS [m][D]
+    double* part;          // partial sums: [n_acc][slots][m_pad]
+    const double* shift;   // per test row additive shift of the exponent (kernel units), may be null
+    long long n_train;
+    long long m;
+    long long m_pad;       // row stride of one slot
+    long long unit_begin;  // first unit id of this job in the launch
+    int n_train_tiles;
+    int n_test_tiles;
+    int slots;
+    int pad_;
+};
+
+constexpr int kThreads = 256;
+constexpr int kStages = 2;
+
+template <typename T> struct PairCfg;
+template <> struct PairCfg<double> { static constexpr int R = 2; static constexpr int TILE = 512; };
+template <> struct PairCfg<float>  { static constexpr int R = 4; static constexpr int TILE = 1024; };
+
+// exp2 table for the f64 path: T[j] = 2^(j/256)
+constexpr int kExpTabBits = 8;
+constexpr int kExpTab = 1 << kExpTabBits;
+// P(g) = exp(g * ln2/256) by Taylor to degree 4 (|g| <= 1/2): c_i = (ln2/256)^i / i!
+static __constant__ double c_exp2_poly[5] = {1.0, 2.7076061740622863e-03, 3.6655655969101058e-06,
+                                             3.3083026805413709e-09, 2.2393951908751570e-12};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// exp(-s/2) from the f64 kernel exponent t (= 256*log2e*(-s/2), t <= 0 up to shift).
+__device__ __forceinline__ double exp2_tab(double t, const double* __restrict__ tab, double& scaled_tab) {
+    const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
+    double tm = t + MAGIC;
+    int n = __double2loint(tm);
+    double nd = tm - MAGIC;
+    double g = t - nd;
+    double p = fma(c_exp2_poly[4], g, c_exp2_poly[3]);
+    p = fma(p, g, c_exp2_poly[2]);
+    p = fma(p, g, c_exp2_poly[1]);
+    p = fma(p, g, 1.0);
+    int j = n & (kExpTab - 1);
+    int k = n >> kExpTabBits;
+    // t < -1021*256 (or not a sane negative number): force the smallest normal scale.
+    // hi word of a negative double grows (as unsigned) with its magnitude.
+    unsigned hi = static_cast<unsigned>(__double2hiint(t));
+    const unsigned HI_LIM = 0xC10FE800u;  // hi word of -(1021*256) = -261376.0
+    k = (hi > HI_LIM) ? -1022 : k;
+    k = (k > 1000) ? 1000 : k;  // positive exponents only arise from shifted re-runs; keep finite
+    double tj = tab[j];
+    scaled_tab = __hiloint2double(__double2hiint(tj) + (k << 20), __double2loint(tj));
+    return p;
+}
+
+template <typename T, int D, bool CKDE>
+__global__ void __launch_bounds__(kThreads, (sizeof(T) == 8) ? 2 : 2)
+pair_kernel(const PairJob* __restrict__ jobs, int n_jobs, long long total_units, long long upb,
+            const double* __restrict__ exp_tab_g) {
+    constexpr int R = PairCfg<T>::R;
+    constexpr int TILE = PairCfg<T>::TILE;
+    constexpr int TB = kThreads * R;  // test rows per tile
+    constexpr uint32_t TILE_BYTES = TILE * D * sizeof(T);
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T* tile_buf = reinterpret_cast<T*>(smem_raw);  // [kStages][TILE*D]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + kStages * TILE_BYTES);
+    double* tab = reinterpret_cast<double*>(smem_raw + kStages * TILE_BYTES + 64);
+
+    const int tid = threadIdx.x;
+    const long long u0 = static_cast<long long>(blockIdx.x) * upb;
+    long long u1 = u0 + upb;
+    if (u1 > total_units) u1 = total_units;
+    if (u0 >= u1) return;
+
+    if (sizeof(T) == 8) {
+        for (int i = tid; i < kExpTab; i += kThreads) tab[i] = exp_tab_g[i];
+    }
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&full_bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // locate the job of the first unit (jobs are sorted by unit_begin)
+    int jlo = 0, jhi = n_jobs - 1;
+    while (jlo < jhi) {
+        int mid = (jlo + jhi + 1) >> 1;
+        if (jobs[mid].unit_begin <= u0) jlo = mid; else jhi = mid - 1;
+    }
+
+    // producer state (thread 0): next unit to load
+    int pj = jlo;
+    long long pu = u0;
+    auto issue_load = [&](int stage) {
+        // advance pj to the job containing pu
+        while (pj + 1 < n_jobs && jobs[pj + 1].unit_begin <= pu) ++pj;
+        const PairJob& jb = jobs[pj];
+        long long local = pu - jb.unit_begin;
+        int nt = static_cast<int>(local % jb.n_train_tiles);
+        long long start = static_cast<long long>(nt) * TILE;
+        long long cnt = jb.n_train - start;
+        if (cnt > TILE) cnt = TILE;
+        uint32_t bytes = static_cast<uint32_t>(((cnt * D * sizeof(T)) + 15) & ~15ull);
+        const T* src = reinterpret_cast<const T*>(jb.train) + start * D;
+        mbar_expect_tx(&full_bar[stage], bytes);
+        tma_bulk_g2s(tile_buf + static_cast<size_t>(stage) * TILE * D, src, bytes, &full_bar[stage]);
+        ++pu;
+    };
+    if (tid == 0) {
+        for (int s = 0; s < kStages && pu < u1; ++s) issue_load(s);
+    }
+
+    int cj = jlo;
+    T yt[R][D];
+    T shiftv[R];
+    double sum_j[R], sum_m[R];
+    float facc_j[R], facc_m[R];
+    long long cur_tt = -1;
+    int cur_job = -1;
+
+    auto flush = [&]() {
+        if (cur_job < 0) return;
+        const PairJob& jb = jobs[cur_job];
+        long long ustart = jb.unit_begin + cur_tt * jb.n_train_tiles;
+        int slot = static_cast<int>(blockIdx.x - ustart / upb);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            long long row = cur_tt * TB + r * kThreads + tid;
+            if (row < jb.m) {
+                jb.part[static_cast<long long>(slot) * jb.m_pad + row] = sum_j[r];
+                if (CKDE) jb.part[(static_cast<long long>(jb.slots) + slot) * jb.m_pad + row] = sum_m[r];
+            }
+        }
+    };
+
+    for (long long u = u0; u < u1; ++u) {
+        const int stage = static_cast<int>((u - u0) % kStages);
+        const uint32_t parity = static_cast<uint32_t>(((u - u0) / kStages) & 1);
+        while (cj + 1 < n_jobs && jobs[cj + 1].unit_begin <= u) ++cj;
+        const PairJob& jb = jobs[cj];
+        const long long local = u - jb.unit_begin;
+        const long long tt = local / jb.n_train_tiles;
+        const int nt = static_cast<int>(local - tt * jb.n_train_tiles);
+        if (cj != cur_job || tt != cur_tt) {
+            flush();
+            cur_job = cj;
+            cur_tt = tt;
+            const T* tp = reinterpret_cast<const T*>(jb.test);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                long long row = tt * TB + r * kThreads + tid;
+                bool ok = row < jb.m;
+#pragma unroll
+                for (int c = 0; c < D; ++c) yt[r][c] = ok ? tp[row * D + c] : T(0);
+                shiftv[r] = (ok && jb.shift) ? static_cast<T>(jb.shift[row]) : T(0);
+                sum_j[r] = 0.0;
+                sum_m[r] = 0.0;
+            }
+        }
+        long long cnt_ll = jb.n_train - static_cast<long long>(nt) * TILE;
+        const int cnt = cnt_ll > TILE ? TILE : static_cast<int>(cnt_ll);
+
+        mbar_wait(&full_bar[stage], parity);
+        const T* __restrict__ tp = tile_buf + static_cast<size_t>(stage) * TILE * D;
+
+        if (sizeof(T) == 8) {
+#pragma unroll 2
+            for (int i = 0; i < cnt; ++i) {
+                double p[D];
+#pragma unroll
+                for (int c = 0; c < D; ++c) p[c] = static_cast<double>(tp[i * D + c]);
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    double acc = static_cast<double>(shiftv[r]);
+#pragma unroll
+                    for (int c = 0; c < D; ++c) {
+                        double dl = static_cast<double>(yt[r][c]) - p[c];
+                        acc = fma(-dl, dl, acc);
+                        if (CKDE && c == D - 2) {
+                            double st;
+                            double pm = exp2_tab(acc, tab, st);
+                            sum_m[r] = fma(st, pm, sum_m[r]);
+                        }
+                    }
+                    double st;
+                    double pj2 = exp2_tab(acc, tab, st);
+                    sum_j[r] = fma(st, pj2, sum_j[r]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r) { facc_j[r] = 0.f; facc_m[r] = 0.f; }
+#pragma unroll 4
+            for (int i = 0; i < cnt; ++i) {
+                float p[D];
+#pragma unroll
+                for (int c = 0; c < D; ++c) p[c] = static_cast<float>(tp[i * D + c]);
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    float acc = static_cast<float>(shiftv[r]);
+#pragma unroll
+                    for (int c = 0; c < D; ++c) {
+                        float dl = static_cast<float>(yt[r][c]) - p[c];
+                        acc = fmaf(-dl, dl, acc);
+                        if (CKDE && c == D - 2) {
+                            float e;
+                            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(acc));
+                            facc_m[r] += e;
+                        }
+                    }
+                    float e;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(acc));
+                    facc_j[r] += e;
+                }
+            }
+            // per-tile float sums are folded into double accumulators (keeps the
+            // summation error at the level of one tile, ~sqrt(TILE) ulp)
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                sum_j[r] += static_cast<double>(facc_j[r]);
+                if (CKDE) sum_m[r] += static_cast<double>(facc_m[r]);
+            }
+        }
+
+        __syncthreads();  // everyone is done with this stage
+        if (tid == 0 && pu < u1) issue_load(stage);
+    }
+    flush();
+}
+
+// Generic-D fallback (D > 8): one test row per thread, runtime D <= 32, same unit scheme.
+constexpr int kMaxGenericD = 32;
+
+}  // namespace pbn

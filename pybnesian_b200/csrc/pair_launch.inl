@@ -1,0 +1,40 @@
+// pair_launch.inl — instantiates pair_kernel<PBN_T, D, CKDE> for D = 1..8 and provides
+// the launcher for one element type.  Included by pair_f64.cu / pair_f32.cu with
+// PBN_T and PBN_LAUNCH_NAME defined (one translation unit per type so they build in parallel).
+#include "pair_kernel.cuh"
+
+namespace pbn {
+
+template <int D, bool CKDE>
+static cudaError_t launch_one(const PairJob* jobs, int n_jobs, long long total_units, long long upb, int grid,
+                              const double* tab, cudaStream_t stream) {
+    constexpr size_t smem = kStages * PairCfg<PBN_T>::TILE * D * sizeof(PBN_T) + 64 + kExpTab * sizeof(double);
+    static bool configured = false;  // per instantiation; attribute is per device function
+    auto kern = pair_kernel<PBN_T, D, CKDE>;
+    if (!configured || true) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    kern<<<grid, kThreads, smem, stream>>>(jobs, n_jobs, total_units, upb, tab);
+    return cudaGetLastError();
+}
+
+cudaError_t PBN_LAUNCH_NAME(int D, bool ckde, const PairJob* jobs, int n_jobs, long long total_units, long long upb,
+                            int grid, const double* tab, cudaStream_t stream) {
+#define PBN_CASE(d)                                                                                          \
+    case d:                                                                                                  \
+        return ckde ? launch_one<(d < 2 ? 2 : d), true>(jobs, n_jobs, total_units, upb, grid, tab, stream)   \
+                    : launch_one<d, false>(jobs, n_jobs, total_units, upb, grid, tab, stream);
+    switch (D) {
+        PBN_CASE(1) PBN_CASE(2) PBN_CASE(3) PBN_CASE(4) PBN_CASE(5) PBN_CASE(6) PBN_CASE(7) PBN_CASE(8)
+        default:
+            return cudaErrorInvalidValue;
+    }
+#undef PBN_CASE
+}
+
+int PBN_TILE_NAME() { return PairCfg<PBN_T>::TILE; }
+int PBN_TB_NAME() { return kThreads * PairCfg<PBN_T>::R; }
+
+}  // namespace pbn

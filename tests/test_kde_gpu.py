@@ -1,0 +1,243 @@
+"""GPU parity tests for KDE / CKDE logl & slogl through the C ABI (via the Python mirror of
+the reference API).  Shapes follow the reference's tests/factors/continuous/KDE_test.py and
+CKDE_test.py; the checker is the CPU oracle (oracle/), with SciPy as an independent check.
+
+Tolerances (BASELINE.json north_star): 1e-10 relative in float64, 1e-4 in float32.
+"""
+import numpy as np
+import pandas as pd
+import pytest
+from scipy.stats import gaussian_kde
+
+import oracle
+import util_data
+
+pytestmark = pytest.mark.gpu
+
+RTOL64 = 1e-10
+RTOL32 = 1e-4
+
+VARSETS = [["a"], ["b", "a"], ["c", "a", "b"], ["d", "a", "b", "c"]]
+
+
+@pytest.fixture(scope="module")
+def pbn():
+    import pybnesian_b200 as pbn
+    return pbn
+
+
+def relerr(got, want, floor=1e-300):
+    return np.max(np.abs(got - want) / np.maximum(np.abs(want), floor))
+
+
+def relerr32(got, want):
+    """float32 bar: 1e-4 relative, measured against max(|logl|, 1): a log-likelihood that
+    happens to be ~0 has no meaningful relative error in single precision (the reference's
+    own tests use atol=5e-4 for float32, KDE_test.py:189)."""
+    return relerr(got, want, floor=1.0)
+
+
+@pytest.mark.parametrize("variables", VARSETS)
+@pytest.mark.parametrize("n_train", [10, 500, 10000])
+def test_kde_logl_f64_vs_oracle(pbn, variables, n_train):
+    df = util_data.generate_normal_data(n_train, seed=0)
+    test = util_data.generate_normal_data(50, seed=1)
+    if n_train <= len(variables):
+        pytest.skip("not enough instances")
+    k = pbn.KDE(variables)
+    k.fit(df)
+    X, T = df[variables].to_numpy(), test[variables].to_numpy()
+    H = oracle.bandwidth(X)
+    assert relerr(k.bandwidth, H) < 1e-12
+    want, want_s = oracle.kde_logl(X, T, H)
+    got = k.logl(test)
+    assert relerr(got, want) < RTOL64
+    assert abs(k.slogl(test) - want_s) <= RTOL64 * abs(want_s)
+    sk = gaussian_kde(X.T, bw_method=lambda s: np.power(4 / (s.d + 2), 1 / (s.d + 4)) * s.scotts_factor())
+    assert np.allclose(got, sk.logpdf(T.T), rtol=1e-9, atol=0)
+
+
+@pytest.mark.parametrize("variables", VARSETS)
+@pytest.mark.parametrize("n_train", [500, 10000])
+def test_kde_logl_f32_vs_oracle(pbn, variables, n_train):
+    df = util_data.generate_normal_data(n_train, seed=0).astype("float32")
+    test = util_data.generate_normal_data(50, seed=1).astype("float32")
+    k = pbn.KDE(variables)
+    k.fit(df)
+    X, T = df[variables].to_numpy(), test[variables].to_numpy()
+    H = oracle.bandwidth(X)
+    assert relerr(k.bandwidth, H) < 1e-5
+    want, want_s = oracle.kde_logl(X, T, H)
+    got = k.logl(test)
+    assert relerr32(got, want) < RTOL32
+    assert abs(k.slogl(test) - want_s) <= RTOL32 * abs(want_s)
+
+
+@pytest.mark.parametrize("rule", ["normal_reference", "scott"])
+def test_bandwidth_rules(pbn, rule):
+    df = util_data.generate_normal_data(1000, seed=0)
+    sel = pbn.NormalReferenceRule() if rule == "normal_reference" else pbn.ScottsBandwidth()
+    for variables in VARSETS:
+        H = sel.bandwidth(df, variables)
+        assert relerr(H, oracle.bandwidth(df[variables].to_numpy(), rule)) < 1e-12
+
+
+@pytest.mark.parametrize("evidence", [[], ["a"], ["a", "b"], ["a", "b", "c"]])
+@pytest.mark.parametrize("n_train", [10, 10000])
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_ckde_logl_vs_oracle(pbn, evidence, n_train, dtype):
+    variables = ["d"] + evidence
+    if n_train <= len(variables):
+        pytest.skip("not enough instances")
+    df = util_data.generate_normal_data(n_train, seed=0).astype(dtype)
+    test = util_data.generate_normal_data(50, seed=1).astype(dtype)
+    cpd = pbn.CKDE("d", evidence)
+    cpd.fit(df)
+    X, T = df[variables].to_numpy(), test[variables].to_numpy()
+    H = oracle.bandwidth(X)
+    want, want_s = oracle.ckde_logl(X, T, H)
+    got = cpd.logl(test)
+    tol = RTOL64 if dtype == "float64" else RTOL32
+    err = relerr(got, want) if dtype == "float64" else relerr32(got, want)
+    assert err < tol
+    assert abs(cpd.slogl(test) - want_s) <= tol * abs(want_s)
+    if evidence:
+        assert relerr(cpd.kde_marg().bandwidth, H[1:, 1:]) < (1e-12 if dtype == "float64" else 1e-5)
+
+
+def test_nulls_give_nan_in_place(pbn):
+    df = util_data.generate_normal_data(2000, seed=0)
+    test = util_data.generate_normal_data(300, seed=1)
+    rng = np.random.default_rng(3)
+    test_null = test.copy()
+    for col in ["a", "b"]:
+        test_null.loc[rng.choice(300, 40, replace=False), col] = np.nan
+    variables = ["c", "a", "b"]
+    k = pbn.KDE(variables)
+    k.fit(df)
+    got = k.logl(test_null)
+    isnull = test_null[variables].isna().any(axis=1).to_numpy()
+    assert np.all(np.isnan(got[isnull])) and not np.any(np.isnan(got[~isnull]))
+    full = k.logl(test)
+    assert relerr(got[~isnull], full[~isnull]) < 1e-13
+    assert abs(k.slogl(test_null) - np.nansum(got)) < 1e-9
+    # training data with nulls: rows dropped (KDE::_fit contains_null branch)
+    df_null = df.copy()
+    df_null.loc[rng.choice(2000, 100, replace=False), "a"] = np.nan
+    k2 = pbn.KDE(variables)
+    k2.fit(df_null)
+    keep = ~df_null[variables].isna().any(axis=1).to_numpy()
+    assert k2.num_instances() == keep.sum()
+    X = df_null[variables].to_numpy()[keep]
+    want, _ = oracle.kde_logl(X, test[variables].to_numpy(), oracle.bandwidth(X))
+    assert relerr(k2.logl(test), want) < RTOL64
+
+
+def test_type_mismatch_and_errors(pbn):
+    df = util_data.generate_normal_data(500, seed=0)
+    dff = df.astype("float32")
+    k = pbn.KDE(["a"])
+    with pytest.raises(ValueError, match="KDE factor not fitted"):
+        k.logl(df)
+    k.fit(df)
+    for fn in (k.logl, k.slogl):
+        with pytest.raises(ValueError, match="Data type of training and test datasets is different."):
+            fn(dff)
+    with pytest.raises(ValueError, match="Cannot create a KDE model with 0 variables"):
+        pbn.KDE([])
+    with pytest.raises(pbn.SingularCovarianceData):
+        pbn.KDE(["a", "b", "c"]).fit(df.iloc[:3])
+    dup = df.copy()
+    dup["b"] = 2 * dup["a"]
+    with pytest.raises(pbn.SingularCovarianceData, match="not positive-definite"):
+        pbn.KDE(["a", "b"]).fit(dup)
+
+
+def test_variable_order_invariance_and_set_bandwidth(pbn):
+    df = util_data.generate_normal_data(3000, seed=0)
+    test = util_data.generate_normal_data(200, seed=1)
+    k1 = pbn.KDE(["a", "b", "c"]); k1.fit(df)
+    k2 = pbn.KDE(["c", "a", "b"]); k2.fit(df)
+    assert relerr(k1.logl(test), k2.logl(test)) < 1e-11
+    k = pbn.KDE(["a"]); k.fit(df)
+    k.bandwidth = [[1.0]]
+    want, _ = oracle.kde_logl(df[["a"]].to_numpy(), test[["a"]].to_numpy(), np.array([[1.0]]))
+    assert relerr(k.logl(test), want) < RTOL64
+
+
+def test_python_bandwidth_selector(pbn):
+    class Halved(pbn.BandwidthSelector):
+        def bandwidth(self, df, variables):
+            return 0.5 * pbn.NormalReferenceRule().bandwidth(df, variables)
+
+    df = util_data.generate_normal_data(2000, seed=0)
+    test = util_data.generate_normal_data(100, seed=1)
+    k = pbn.KDE(["a", "b"], Halved()); k.fit(df)
+    X = df[["a", "b"]].to_numpy()
+    want, _ = oracle.kde_logl(X, test[["a", "b"]].to_numpy(), 0.5 * oracle.bandwidth(X))
+    assert relerr(k.logl(test), want) < RTOL64
+
+
+def test_far_test_points_use_shifted_path(pbn):
+    """Test rows tens of bandwidths away from every training point: the unshifted kernel sum
+    underflows and the rows are re-evaluated with a max shift (what the reference's
+    logsumexp_cols_offset does for every row)."""
+    df = util_data.generate_normal_data(4000, seed=0)
+    test = util_data.generate_normal_data(64, seed=1)
+    test.loc[:7, "a"] += 40.0
+    test.loc[8:11, "b"] -= 300.0
+    for dtype, tol in (("float64", RTOL64), ("float32", RTOL32)):
+        tr, te = df.astype(dtype), test.astype(dtype)
+        for variables in (["a"], ["a", "b"], ["c", "a", "b"]):
+            k = pbn.KDE(variables); k.fit(tr)
+            X = tr[variables].to_numpy()
+            want, _ = oracle.kde_logl(X, te[variables].to_numpy(), oracle.bandwidth(X))
+            got = k.logl(te)
+            assert np.all(np.isfinite(got))
+            assert (relerr(got, want) if dtype == "float64" else relerr32(got, want)) < tol
+            assert pbn.default_context().last_fallback_rows() > 0
+        cpd = pbn.CKDE("b", ["a", "c"]); cpd.fit(tr)
+        X = tr[["b", "a", "c"]].to_numpy()
+        want, _ = oracle.ckde_logl(X, te[["b", "a", "c"]].to_numpy(), oracle.bandwidth(X))
+        got = cpd.logl(te)
+        assert (relerr(got, want) if dtype == "float64" else relerr32(got, want)) < tol
+
+
+@pytest.mark.parametrize("d", [5, 8, 9, 12])
+def test_higher_dimensions(pbn, d):
+    tr = util_data.iid_normal(3000, d, seed=0)
+    te = util_data.iid_normal(100, d, seed=1)
+    variables = list(tr.columns)
+    k = pbn.KDE(variables); k.fit(tr)
+    X = tr.to_numpy()
+    want, _ = oracle.kde_logl(X, te.to_numpy(), oracle.bandwidth(X))
+    assert relerr(k.logl(te), want) < RTOL64
+    cpd = pbn.CKDE(variables[0], variables[1:]); cpd.fit(tr)
+    want, _ = oracle.ckde_logl(X, te.to_numpy(), oracle.bandwidth(X))
+    assert relerr(cpd.logl(te), want) < 1e-9
+
+
+def test_config1_shape(pbn):
+    """BASELINE.json configs[0]: KDE(['a','b']) fit + logl, 10k train / 10k test, float64."""
+    tr = util_data.generate_normal_data(10000, seed=0)
+    te = util_data.generate_normal_data(10000, seed=1)
+    k = pbn.KDE(["a", "b"]); k.fit(tr)
+    X = tr[["a", "b"]].to_numpy()
+    want, want_s = oracle.kde_logl(X, te[["a", "b"]].to_numpy(), oracle.bandwidth(X))
+    assert relerr(k.logl(te), want) < RTOL64
+    assert abs(k.slogl(te) - want_s) < RTOL64 * abs(want_s)
+
+
+def test_multi_tile_ragged_sizes(pbn):
+    """Sizes that are not multiples of the train / test tiles and need several CTAs per test tile."""
+    for n, m in [(513, 1), (1025, 511), (5000, 1537), (20011, 2049)]:
+        tr = util_data.generate_normal_data(n, seed=2)
+        te = util_data.generate_normal_data(m, seed=3)
+        for dtype, tol in (("float64", RTOL64), ("float32", RTOL32)):
+            cpd = pbn.CKDE("c", ["a", "b"]); cpd.fit(tr.astype(dtype))
+            X = tr[["c", "a", "b"]].to_numpy().astype(dtype)
+            T = te[["c", "a", "b"]].to_numpy().astype(dtype)
+            sub = slice(0, min(m, 200))
+            want, _ = oracle.ckde_logl(X, T[sub], oracle.bandwidth(X))
+            got = cpd.logl(te.astype(dtype))[sub]
+            assert (relerr(got, want) if dtype == "float64" else relerr32(got, want)) < tol
