@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the KDE/CKDE log-likelihood hot path on B200.
+
+Metric (BASELINE.json): KDE/CKDE logl kernel-pair evals/s (train x test; a CKDE with parents
+counts joint + marginal = 2 per train x test pair).
+
+Workload at every N: BASELINE.json configs[1] — CKDE('d' | 'a','b','c'), float64,
+1M training rows (util_test.generate_normal_data recipe, seed 0) and 1M test rows (seed 1)
+PER GPU; a "step" is one `slogl` pass (2e12 pair-evals per GPU).  Multi-GPU: test rows are
+sharded (weak scaling: 1M test rows per rank, a different seed per rank), the fitted training
+set is replicated, and the only collective is an NCCL all-reduce of the per-rank
+log-likelihood scalar.
+
+  value     whole-job pair-evals/s with train and test tables resident in HBM
+  e2e       same metric through the public API (`CKDE.slogl(record_batch)`) with HOST test
+            buffers: H2D upload of the test columns and D2H of the result inside the timed region
+  roofline  the pair kernel alone (CUDA events around the launch, recorded inside
+            libpbn_cuda on the launching stream) against the FP64 FMA roofline of SURVEY.md §8(d)
+  cpu_baseline  the CPU oracle (port of the reference arithmetic; the reference itself cannot be
+            built here) on a bounded sample of the same workload, all host threads
+
+`--impl reference` times only that CPU arm.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+METRIC = "KDE/CKDE logl kernel-pair evals/s (train x test)"
+UNIT = "pair-evals/s"
+VARIABLES = ["d", "a", "b", "c"]  # CKDE('d' | a, b, c)
+
+
+def gen(size, seed, dtype=np.float64):
+    import util_data
+    return util_data.generate_normal_data(size, seed=seed).astype(dtype)
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, power, reasons = [], None, [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": mx, "reasons": ["no samples"]}
+        load = [s for s in sm if s > 0.5 * max(sm)] or sm
+        return {"sm_mhz": float(np.median(load)), "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+def cpu_arm(n_train, sample_rows, steps, warmup):
+    """Times the CPU oracle (reference arithmetic, OpenMP over test rows) on `sample_rows`
+    test rows against the full training set.  Returns (pair-evals/s, threads, ms/step, check)."""
+    import oracle
+    tr = gen(n_train, 0)[VARIABLES].to_numpy()
+    te = gen(max(sample_rows, 1), 1)[VARIABLES].to_numpy()
+    H = oracle.bandwidth(tr)
+    for _ in range(warmup):
+        oracle.ckde_logl(tr, te[: max(8, sample_rows // 16)], H)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        _, s = oracle.ckde_logl(tr, te, H)
+        times.append(time.perf_counter() - t0)
+    t = float(np.mean(times))
+    return 2.0 * n_train * sample_rows / t, oracle.num_threads(), 1e3 * t, s
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, args.steps)
+    # ~1e8 pair-evals/s on 8 cores: 192 rows x 1M x 2 = 3.8e8 pair-evals ~ 4 s per step
+    rows = args.cpu_rows or 192
+    val, threads, ms, _ = cpu_arm(args.n_train, rows, steps, min(args.warmup, 1))
+    sample = "%d of %d test rows per step against all %d training rows" % (rows, args.n_test, args.n_train)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "note": "oracle/ port of the reference arithmetic; the reference's OpenCL path cannot be "
+                                 "built in this image (no CL/cl.h, no ICD, no NLopt/Boost)"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(args):
+    return {"workload": "configs[1]: CKDE('d'|'a','b','c') slogl, float64, %d train x %d test rows per GPU, "
+                        "NormalReferenceRule bandwidth, generate_normal_data seeds 0/1" % (args.n_train, args.n_test),
+            "n_train": args.n_train, "n_test_per_gpu": args.n_test, "d_joint": 4, "d_marginal": 3,
+            "parallelism": "test rows sharded over %d GPU(s), training set replicated" % args.gpus,
+            "l2": "flushed between timed steps (256 MiB memset); train set (32 MB) is L2 resident by design"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n-train", type=int, default=1_000_000)
+    ap.add_argument("--n-test", type=int, default=1_000_000)
+    ap.add_argument("--cpu-rows", type=int, default=0, help="test rows of the CPU-baseline sample")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import pyarrow as pa
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA GPU (B200); there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    os.environ["PBN_CUDA_DEVICE"] = str(local_rank)
+
+    import pybnesian_b200 as pbn
+    from pybnesian_b200 import _lib
+    import ctypes
+
+    ctx = pbn.default_context()
+    stream = torch.cuda.Stream()  # a non-default stream shared by torch and the library
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)  # the library launches on torch's current stream: torch events see it
+
+    steps, warmup = args.steps, max(args.warmup, 3)
+    n_train, n_test = args.n_train, args.n_test
+    train_df = gen(n_train, 0)
+    test_df = gen(n_test, 1 + rank)  # each rank scores its own shard of test rows
+    train = pbn.DataFrame(train_df)
+    test = pbn.DataFrame(test_df)
+
+    cpd = pbn.CKDE("d", ["a", "b", "c"])
+    cpd.fit(train)                       # bandwidth, Cholesky, whitened training rows resident in HBM
+    test_tbl, test_cols, _ = test.device_table(VARIABLES)   # test columns resident in HBM
+    out = torch.zeros(1, dtype=torch.float64, device="cuda")
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    L = _lib.lib()
+
+    def step():
+        _lib.check(L.pbn_kde_logl_device(ctx.handle, cpd._handle.handle, test_tbl.handle, _lib.int_array(test_cols),
+                                         test_tbl.rows(), None, ctypes.c_void_p(out.data_ptr())))
+        if world > 1:
+            dist.all_reduce(out)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step()
+    barrier()
+    ctx.set_timing(True)
+    ctx.pair_kernel_time(reset=True)
+    c0 = ctx.counters()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    wall0 = time.perf_counter()
+    for a, b in ev:
+        flush.zero_()
+        a.record(stream)
+        step()
+        b.record(stream)
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    c1 = ctx.counters()
+    ctx.set_timing(False)
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(sum(step_ms))
+    kern_ms, kern_launches, kern_pairs = ctx.pair_kernel_time(reset=True)
+    slogl_total = float(out.item())
+
+    tmax = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms = float(tmax.item())
+    pairs_per_step_per_gpu = 2.0 * n_train * n_test
+    value = pairs_per_step_per_gpu * world * steps / (total_ms * 1e-3)
+
+    # ---- e2e: public API with host buffers (pinned), H2D + D2H inside the timed region ----
+    pinned = {c: torch.from_numpy(test_df[c].to_numpy()).pin_memory() for c in VARIABLES}
+    host_rb = pa.RecordBatch.from_arrays([pa.array(pinned[c].numpy()) for c in VARIABLES], names=VARIABLES)
+    cpd.slogl(host_rb)  # warm
+    barrier()
+    e0 = ctx.counters()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        s_e2e = cpd.slogl(host_rb)
+    ctx.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e1 = ctx.counters()
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = pairs_per_step_per_gpu * world * args.e2e_steps / float(te.item())
+    e2e = {"value": e2e_value, "unit": UNIT,
+           "h2d_bytes_per_step": (e1["h2d_bytes"] - e0["h2d_bytes"]) // args.e2e_steps,
+           "d2h_bytes_per_step": (e1["d2h_bytes"] - e0["d2h_bytes"]) // args.e2e_steps,
+           "api": "CKDE.slogl(pyarrow.RecordBatch over pinned host buffers)", "steps": args.e2e_steps,
+           "timer": "host wall clock around the blocking API call, max over ranks"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the pair kernel (rank 0's launches) ----
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    f_hz = (clocks.get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0) * 1e6
+    sms, lanes = ctx.sm_count, 64
+    # FP64-pipe instructions per pair-eval I(d) = 2d + 18; CKDE run as two passes
+    # (joint d=4, marginal d=3) => mean (26 + 24)/2 = 25 per pair-eval.
+    i_survey = (2 * 4 + 18 + 2 * 3 + 18) / 2.0
+    # This kernel's own count per pair-eval: fused pass shares the d differences/FMAs, table exp2
+    # costs 3 DADD + 4 DFMA + 1 DFMA(accumulate): (2*4 + 2*8)/2 = 12.
+    i_own = (2 * 4 + 2 * 8) / 2.0
+    achieved = kern_pairs / (kern_ms * 1e-3) if kern_ms > 0 else None
+    peak = sms * lanes * f_hz / i_survey
+    roofline = {
+        "bound": "fp64_fma", "kernel": "pbn::pair_kernel<double,4,CKDE>", "achieved": achieved, "peak": peak,
+        "unit": UNIT, "frac": (achieved / peak) if achieved else None, "traffic": None,
+        "peak_def": "SMs(%d) x 64 FP64 lanes x %.0f MHz (median SM clock sampled in the timed region) / %.1f FP64-pipe "
+                    "instr per pair-eval (SURVEY.md 8d two-pass count; a fused pass may exceed 1.0)" % (sms, f_hz / 1e6, i_survey),
+        "own_count": {"fp64_instr_per_pair_eval": i_own, "peak": sms * lanes * f_hz / i_own,
+                      "frac": (achieved / (sms * lanes * f_hz / i_own)) if achieved else None},
+        "kernel_ms_per_launch": kern_ms / max(kern_launches, 1), "launches_timed": kern_launches,
+        "kernel_share_of_step": kern_ms / (sum(step_ms)) if step_ms else None,
+        "hbm_peak_gbs_measured": peaks.get("hbm_gbs"),
+        "algorithmic_bytes_per_pair_eval": (8.0 * 4 * (n_train + n_test) + 8.0 * n_test) / (2.0 * n_train * n_test),
+    }
+
+    cpu_baseline = None
+    if not args.no_cpu:
+        rows = args.cpu_rows or 768
+        v, threads, ms, _ = cpu_arm(n_train, rows, 1, 1)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": "%d of %d test rows against all %d training rows (%.1f s)" % (rows, n_test, n_train, ms / 1e3)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": workload_config(args),
+        "clocks": clocks, "e2e": e2e, "gpu_launches": c1["launches"] - c0["launches"],
+        "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "check": {"slogl_sum_over_ranks": slogl_total, "slogl_e2e_rank0": s_e2e,
+                  "fallback_rows_last_call": ctx.last_fallback_rows(), "wall_s_timed_loop": wall},
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -64,6 +64,15 @@ int pbn_ctx_sm_count(pbn_ctx* ctx);
  * and device->host bytes it copied. */
 int pbn_ctx_counters(pbn_ctx* ctx, int64_t* launches, int64_t* h2d_bytes, int64_t* d2h_bytes);
 
+/* Device timing of the pair kernel alone: when enabled, CUDA events are recorded on the
+ * context's stream around every pair-kernel launch; pbn_ctx_pair_kernel_time() returns the
+ * accumulated kernel milliseconds, the number of timed launches and the train x test
+ * pair evaluations they processed (a CKDE pair counts 2: joint + marginal). The reference has
+ * no profiling hooks (its queue is created without CL_QUEUE_PROFILING_ENABLE,
+ * opencl/opencl_config.cpp:175). */
+int pbn_ctx_set_timing(pbn_ctx* ctx, int on);
+int pbn_ctx_pair_kernel_time(pbn_ctx* ctx, double* total_ms, int64_t* n_launches, int64_t* pair_evals, int reset);
+
 /* Replaces OpenCLConfig::copy_to_buffer (opencl/opencl_config.hpp:226-239) applied to
  * DataFrame::to_eigen output: uploads `ncols` dense host columns of `nrows` values once;
  * the table stays resident until freed. */

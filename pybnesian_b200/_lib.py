@@ -20,7 +20,7 @@ EXPORTS = [
     "pbn_table_free", "pbn_table_rows", "pbn_table_cols", "pbn_table_download", "pbn_table_moments", "pbn_bandwidth",
     "pbn_diag_bandwidth", "pbn_kde_fit", "pbn_ckde_fit", "pbn_kde_free", "pbn_kde_num_instances", "pbn_kde_lognorm",
     "pbn_kde_logl", "pbn_kde_logl_device", "pbn_ctx_last_fallback_rows", "pbn_device_alloc", "pbn_device_free",
-    "pbn_device_read",
+    "pbn_device_read", "pbn_ctx_set_timing", "pbn_ctx_pair_kernel_time",
 ]
 
 
@@ -87,6 +87,8 @@ def lib():
         L.pbn_device_alloc.argtypes = [vp, i64, ctypes.POINTER(vp)]
         L.pbn_device_free.argtypes = [vp, vp]
         L.pbn_device_read.argtypes = [vp, vp, i64, vp]
+        L.pbn_ctx_set_timing.argtypes = [vp, ci]
+        L.pbn_ctx_pair_kernel_time.argtypes = [vp, dp, ctypes.POINTER(i64), ctypes.POINTER(i64), ci]
         _lib = L
     return _lib
 
@@ -128,6 +130,16 @@ class Context:
         a, b, c = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
         check(lib().pbn_ctx_counters(self.handle, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
         return {"launches": a.value, "h2d_bytes": b.value, "d2h_bytes": c.value}
+
+    def set_timing(self, on):
+        check(lib().pbn_ctx_set_timing(self.handle, 1 if on else 0))
+
+    def pair_kernel_time(self, reset=False):
+        """(total ms, launches, pair evaluations) of the timed pair-kernel launches."""
+        ms, n, pe = ctypes.c_double(), ctypes.c_int64(), ctypes.c_int64()
+        check(lib().pbn_ctx_pair_kernel_time(self.handle, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(pe),
+                                             1 if reset else 0))
+        return ms.value, n.value, pe.value
 
     def last_fallback_rows(self):
         v = ctypes.c_int64()

@@ -35,7 +35,8 @@ struct PairJob {
     const void* train;     // whitened train rows, AoS [n_train (padded alloc)][D]
     const void* test;      // whitened test rows, AoS [m][D]
     double* part;          // partial sums: [n_acc][slots][m_pad]
-    const double* shift;   // per test row additive shift of the exponent (kernel units), may be null
+    const float* bound_train;  // max |whitened coordinate| over the training rows (device scalar)
+    const float* bound_test;   // same over the test rows
     long long n_train;
     long long m;
     long long m_pad;       // row stride of one slot
@@ -50,8 +51,8 @@ constexpr int kThreads = 256;
 constexpr int kStages = 2;
 
 template <typename T> struct PairCfg;
-template <> struct PairCfg<double> { static constexpr int R = 2; static constexpr int TILE = 512; };
-template <> struct PairCfg<float>  { static constexpr int R = 4; static constexpr int TILE = 1024; };
+template <> struct PairCfg<double> { static constexpr int R = 2; static constexpr int TILE = 512; static constexpr int MIN_CTAS = 2; };
+template <> struct PairCfg<float>  { static constexpr int R = 4; static constexpr int TILE = 1024; static constexpr int MIN_CTAS = 2; };
 
 // exp2 table for the f64 path: T[j] = 2^(j/256)
 constexpr int kExpTabBits = 8;
@@ -88,8 +89,15 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
         : "memory");
 }
 
-// exp(-s/2) from the f64 kernel exponent t (= 256*log2e*(-s/2), t <= 0 up to shift).
-__device__ __forceinline__ double exp2_tab(double t, const double* __restrict__ tab, double& scaled_tab) {
+// exp(-s/2) from the f64 kernel exponent t (= 256*log2e*(-s/2), t <= 0):
+//   2^(t/256) = 2^k * T[j] * P(g),  n = rint(t) = 256 k + j,  g = t - n.
+// The table holds T'[j] = T[j] with (j << 12) subtracted from its high word, so that the
+// scaled entry 2^k T[j] is obtained with ONE integer multiply-add: hi' + (n << 12).
+// Returns P(g); `scaled` receives 2^k T[j].  SAFE = false requires t > -2^31 (guaranteed by
+// the caller from the bounding boxes of the whitened rows); SAFE = true accepts any t.
+constexpr int kNMin = -1022 * 256;
+template <bool SAFE>
+__device__ __forceinline__ double exp2_tab(double t, const double* __restrict__ tab, double& scaled) {
     const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
     double tm = t + MAGIC;
     int n = __double2loint(tm);
@@ -99,21 +107,88 @@ __device__ __forceinline__ double exp2_tab(double t, const double* __restrict__ 
     p = fma(p, g, c_exp2_poly[2]);
     p = fma(p, g, c_exp2_poly[1]);
     p = fma(p, g, 1.0);
-    int j = n & (kExpTab - 1);
-    int k = n >> kExpTabBits;
-    // t < -1021*256 (or not a sane negative number): force the smallest normal scale.
-    // hi word of a negative double grows (as unsigned) with its magnitude.
-    unsigned hi = static_cast<unsigned>(__double2hiint(t));
-    const unsigned HI_LIM = 0xC10FE800u;  // hi word of -(1021*256) = -261376.0
-    k = (hi > HI_LIM) ? -1022 : k;
-    k = (k > 1000) ? 1000 : k;  // positive exponents only arise from shifted re-runs; keep finite
-    double tj = tab[j];
-    scaled_tab = __hiloint2double(__double2hiint(tj) + (k << 20), __double2loint(tj));
+    if (SAFE) {
+        // hi word of a negative double grows (as unsigned) with its magnitude;
+        // 0xC10FF000 is the hi word of -(1022*256) = -261632.0
+        unsigned hi = static_cast<unsigned>(__double2hiint(t));
+        n = (hi > 0xC10FF000u) ? kNMin : n;
+    } else {
+        n = max(n, kNMin);
+    }
+    double tj = tab[n & (kExpTab - 1)];
+    scaled = __hiloint2double(__double2hiint(tj) + n * 4096, __double2loint(tj));
     return p;
 }
 
+// One (test tile) x (train tile) unit on the FP64 pipe.
+template <int D, bool CKDE, bool SAFE, int R>
+__device__ __forceinline__ void tile_f64(const double* __restrict__ tp, int cnt, const double (&yt)[R][D],
+                                         const double* __restrict__ tab, double (&sum_j)[R], double (&sum_m)[R]) {
+#pragma unroll 4
+    for (int i = 0; i < cnt; ++i) {
+        double p[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) p[c] = tp[i * D + c];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            double acc = 0.0;
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+                double dl = yt[r][c] - p[c];
+                acc = fma(-dl, dl, acc);
+                if (CKDE && c == D - 2) {
+                    double st;
+                    double pm = exp2_tab<SAFE>(acc, tab, st);
+                    sum_m[r] = fma(st, pm, sum_m[r]);
+                }
+            }
+            double st;
+            double pj = exp2_tab<SAFE>(acc, tab, st);
+            sum_j[r] = fma(st, pj, sum_j[r]);
+        }
+    }
+}
+
+// Same unit on the FP32 FMA pipe + MUFU.EX2; per-tile float sums are folded into the
+// double accumulators by the caller (summation error stays at ~sqrt(TILE) ulp).
+template <int D, bool CKDE, int R>
+__device__ __forceinline__ void tile_f32(const float* __restrict__ tp, int cnt, const float (&yt)[R][D],
+                                         double (&sum_j)[R], double (&sum_m)[R]) {
+    float facc_j[R], facc_m[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) { facc_j[r] = 0.f; facc_m[r] = 0.f; }
+#pragma unroll 4
+    for (int i = 0; i < cnt; ++i) {
+        float p[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) p[c] = tp[i * D + c];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+                float dl = yt[r][c] - p[c];
+                acc = fmaf(-dl, dl, acc);
+                if (CKDE && c == D - 2) {
+                    float e;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(acc));
+                    facc_m[r] += e;
+                }
+            }
+            float e;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(acc));
+            facc_j[r] += e;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        sum_j[r] += static_cast<double>(facc_j[r]);
+        if (CKDE) sum_m[r] += static_cast<double>(facc_m[r]);
+    }
+}
+
 template <typename T, int D, bool CKDE>
-__global__ void __launch_bounds__(kThreads, (sizeof(T) == 8) ? 2 : 2)
+__global__ void __launch_bounds__(kThreads, PairCfg<T>::MIN_CTAS)
 pair_kernel(const PairJob* __restrict__ jobs, int n_jobs, long long total_units, long long upb,
             const double* __restrict__ exp_tab_g) {
     constexpr int R = PairCfg<T>::R;
@@ -152,7 +227,6 @@ pair_kernel(const PairJob* __restrict__ jobs, int n_jobs, long long total_units,
     int pj = jlo;
     long long pu = u0;
     auto issue_load = [&](int stage) {
-        // advance pj to the job containing pu
         while (pj + 1 < n_jobs && jobs[pj + 1].unit_begin <= pu) ++pj;
         const PairJob& jb = jobs[pj];
         long long local = pu - jb.unit_begin;
@@ -172,11 +246,10 @@ pair_kernel(const PairJob* __restrict__ jobs, int n_jobs, long long total_units,
 
     int cj = jlo;
     T yt[R][D];
-    T shiftv[R];
     double sum_j[R], sum_m[R];
-    float facc_j[R], facc_m[R];
     long long cur_tt = -1;
     int cur_job = -1;
+    bool safe = true;
 
     auto flush = [&]() {
         if (cur_job < 0) return;
@@ -212,9 +285,16 @@ pair_kernel(const PairJob* __restrict__ jobs, int n_jobs, long long total_units,
                 bool ok = row < jb.m;
 #pragma unroll
                 for (int c = 0; c < D; ++c) yt[r][c] = ok ? tp[row * D + c] : T(0);
-                shiftv[r] = (ok && jb.shift) ? static_cast<T>(jb.shift[row]) : T(0);
                 sum_j[r] = 0.0;
                 sum_m[r] = 0.0;
+            }
+            if (sizeof(T) == 8) {
+                // |t| <= D * (max|y_train| + max|y_test|)^2 must stay below 2^31 for the
+                // integer-only clamp of the fast exp2 variant
+                float a = jb.bound_train ? *jb.bound_train : INFINITY;
+                float b = jb.bound_test ? *jb.bound_test : INFINITY;
+                float lim = static_cast<float>(D) * (a + b) * (a + b);
+                safe = !(lim < 2.0e9f);
             }
         }
         long long cnt_ll = jb.n_train - static_cast<long long>(nt) * TILE;
@@ -223,63 +303,13 @@ pair_kernel(const PairJob* __restrict__ jobs, int n_jobs, long long total_units,
         mbar_wait(&full_bar[stage], parity);
         const T* __restrict__ tp = tile_buf + static_cast<size_t>(stage) * TILE * D;
 
-        if (sizeof(T) == 8) {
-#pragma unroll 2
-            for (int i = 0; i < cnt; ++i) {
-                double p[D];
-#pragma unroll
-                for (int c = 0; c < D; ++c) p[c] = static_cast<double>(tp[i * D + c]);
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    double acc = static_cast<double>(shiftv[r]);
-#pragma unroll
-                    for (int c = 0; c < D; ++c) {
-                        double dl = static_cast<double>(yt[r][c]) - p[c];
-                        acc = fma(-dl, dl, acc);
-                        if (CKDE && c == D - 2) {
-                            double st;
-                            double pm = exp2_tab(acc, tab, st);
-                            sum_m[r] = fma(st, pm, sum_m[r]);
-                        }
-                    }
-                    double st;
-                    double pj2 = exp2_tab(acc, tab, st);
-                    sum_j[r] = fma(st, pj2, sum_j[r]);
-                }
-            }
+        if constexpr (sizeof(T) == 8) {
+            if (safe)
+                tile_f64<D, CKDE, true, R>(tp, cnt, yt, tab, sum_j, sum_m);
+            else
+                tile_f64<D, CKDE, false, R>(tp, cnt, yt, tab, sum_j, sum_m);
         } else {
-#pragma unroll
-            for (int r = 0; r < R; ++r) { facc_j[r] = 0.f; facc_m[r] = 0.f; }
-#pragma unroll 4
-            for (int i = 0; i < cnt; ++i) {
-                float p[D];
-#pragma unroll
-                for (int c = 0; c < D; ++c) p[c] = static_cast<float>(tp[i * D + c]);
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    float acc = static_cast<float>(shiftv[r]);
-#pragma unroll
-                    for (int c = 0; c < D; ++c) {
-                        float dl = static_cast<float>(yt[r][c]) - p[c];
-                        acc = fmaf(-dl, dl, acc);
-                        if (CKDE && c == D - 2) {
-                            float e;
-                            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(acc));
-                            facc_m[r] += e;
-                        }
-                    }
-                    float e;
-                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(acc));
-                    facc_j[r] += e;
-                }
-            }
-            // per-tile float sums are folded into double accumulators (keeps the
-            // summation error at the level of one tile, ~sqrt(TILE) ulp)
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                sum_j[r] += static_cast<double>(facc_j[r]);
-                if (CKDE) sum_m[r] += static_cast<double>(facc_m[r]);
-            }
+            tile_f32<D, CKDE, R>(tp, cnt, yt, sum_j, sum_m);
         }
 
         __syncthreads();  // everyone is done with this stage

@@ -64,9 +64,15 @@ struct pbn_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
     int sm_count = 0;
-    double* d_exp_tab = nullptr;  // 2^(j/256), j = 0..255
+    double* d_exp_tab = nullptr;  // T'[j] = 2^(j/256) with (j<<12) taken off the high word, j = 0..255
     int64_t launches = 0, h2d = 0, d2h = 0;
     int64_t last_fallback_rows = 0;
+    // optional device timing of the pair kernel (CUDA events on the launching stream)
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;
+    double pair_ms = 0;
+    int64_t pair_launches = 0;
+    int64_t pair_units = 0;  // train x test pairs processed by timed launches (x2 for CKDE)
 };
 
 struct pbn_table {
@@ -85,6 +91,7 @@ struct pbn_kde {
     bool ckde;  // fused joint+marginal (d >= 2, variable stored last)
     int64_t n;
     void* y;  // whitened training rows AoS [n_pad][d]
+    float* d_bound;  // device scalar: max |whitened training coordinate|
     double W[PBN_MAX_DIM * PBN_MAX_DIM];  // row-major lower-triangular whitening matrix (incl. unit scale)
     double mu[PBN_MAX_DIM];
     int perm[PBN_MAX_DIM];  // internal column k = caller column perm[k]
@@ -275,19 +282,26 @@ struct WhitenParams {
 };
 
 template <typename T>
-__global__ void whiten_kernel(const __grid_constant__ WhitenParams P, T* __restrict__ out) {
+__global__ void whiten_kernel(const __grid_constant__ WhitenParams P, T* __restrict__ out, float* __restrict__ bound) {
     int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (r >= P.n) return;
-    int64_t rr = map_row(r, P.b0, P.n0, P.b1);
-    double x[PBN_MAX_DIM];
-    const int d = P.d;
-    for (int c = 0; c < d; ++c) x[c] = static_cast<double>(static_cast<const T*>(P.cols.p[c])[rr]) - P.mu[c];
-    int w = 0;
-    for (int i = 0; i < d; ++i) {
-        double s = 0;
-        for (int k = 0; k <= i; ++k) s = fma(P.W[w++], x[k], s);
-        out[r * d + i] = static_cast<T>(s);
+    float mx = 0.f;
+    if (r < P.n) {
+        int64_t rr = map_row(r, P.b0, P.n0, P.b1);
+        double x[PBN_MAX_DIM];
+        const int d = P.d;
+        for (int c = 0; c < d; ++c) x[c] = static_cast<double>(static_cast<const T*>(P.cols.p[c])[rr]) - P.mu[c];
+        int w = 0;
+        for (int i = 0; i < d; ++i) {
+            double s = 0;
+            for (int k = 0; k <= i; ++k) s = fma(P.W[w++], x[k], s);
+            out[r * d + i] = static_cast<T>(s);
+            float a = fabsf(static_cast<float>(s));
+            mx = (a > mx || a != a) ? (a != a ? INFINITY : a) : mx;  // NaN counts as unbounded
+        }
     }
+    // max |coordinate| of the launch (non-negative floats order like their bit patterns)
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (bound && (threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(reinterpret_cast<int*>(bound), __float_as_int(mx * 1.0001f));
 }
 
 // ------------------------------------------------------------------------------------
@@ -518,7 +532,8 @@ static std::string var_list(const int* cols, int d) {
     return s + "]";
 }
 
-static int whiten_launch(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* tbl, const int* cols, pbn_rows rows, void* out) {
+static int whiten_launch(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* tbl, const int* cols, pbn_rows rows, void* out,
+                         float* bound) {
     WhitenParams P;
     memset(&P, 0, sizeof(P));
     const int d = k->d;
@@ -536,9 +551,9 @@ static int whiten_launch(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* tbl, c
     const int threads = 256;
     int blocks = (int)((P.n + threads - 1) / threads);
     if (k->dtype == PBN_F64)
-        whiten_kernel<double><<<blocks, threads, 0, ctx->stream>>>(P, static_cast<double*>(out));
+        whiten_kernel<double><<<blocks, threads, 0, ctx->stream>>>(P, static_cast<double*>(out), bound);
     else
-        whiten_kernel<float><<<blocks, threads, 0, ctx->stream>>>(P, static_cast<float*>(out));
+        whiten_kernel<float><<<blocks, threads, 0, ctx->stream>>>(P, static_cast<float*>(out), bound);
     ctx->launches++;
     PBN_CUDA_TRY(cudaGetLastError());
     return PBN_OK;
@@ -592,11 +607,13 @@ static int fit_impl(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, 
     if (rc != PBN_OK) { delete k; return rc; }
     int tile = k->dtype == PBN_F64 ? pbn::pair_tile_f64() : pbn::pair_tile_f32();
     int64_t n_pad = ((n + tile - 1) / tile) * tile + 16;
-    cudaError_t e = cudaMallocAsync(&k->y, (size_t)n_pad * d * elem_size(k->dtype), ctx->stream);
+    size_t ybytes = ((size_t)n_pad * d * elem_size(k->dtype) + 255) / 256 * 256;
+    cudaError_t e = cudaMallocAsync(&k->y, ybytes + 256, ctx->stream);
     if (e != cudaSuccess) { delete k; PBN_CUDA_TRY(e); }
-    e = cudaMemsetAsync(k->y, 0, (size_t)n_pad * d * elem_size(k->dtype), ctx->stream);
+    e = cudaMemsetAsync(k->y, 0, ybytes + 256, ctx->stream);
     if (e != cudaSuccess) { cudaFreeAsync(k->y, ctx->stream); delete k; PBN_CUDA_TRY(e); }
-    rc = whiten_launch(ctx, k, tbl, cols, rows, k->y);
+    k->d_bound = reinterpret_cast<float*>(static_cast<char*>(k->y) + ybytes);
+    rc = whiten_launch(ctx, k, tbl, cols, rows, k->y, k->d_bound);
     if (rc != PBN_OK) { cudaFreeAsync(k->y, ctx->stream); delete k; return rc; }
     *out = k;
     return PBN_OK;
@@ -626,8 +643,11 @@ static int logl_impl(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, cons
     const bool fast = d <= 8;
 
     void* ytest = nullptr;
-    PBN_CUDA_TRY(cudaMallocAsync(&ytest, (size_t)m * d * es + 64, st));
-    PBN_TRY(whiten_launch(ctx, k, test, cols, rows, ytest));
+    size_t ytbytes = ((size_t)m * d * es + 255) / 256 * 256;
+    PBN_CUDA_TRY(cudaMallocAsync(&ytest, ytbytes + 256, st));
+    float* bound_test = reinterpret_cast<float*>(static_cast<char*>(ytest) + ytbytes);
+    PBN_CUDA_TRY(cudaMemsetAsync(bound_test, 0, 256, st));
+    PBN_TRY(whiten_launch(ctx, k, test, cols, rows, ytest, bound_test));
 
     double* out = d_out_logl;
     bool own_out = false;
@@ -660,7 +680,8 @@ static int logl_impl(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, cons
         job.train = k->y;
         job.test = ytest;
         job.part = part;
-        job.shift = nullptr;
+        job.bound_train = k->d_bound;
+        job.bound_test = bound_test;
         job.n_train = k->n;
         job.m = m;
         job.m_pad = m_pad;
@@ -671,10 +692,21 @@ static int logl_impl(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, cons
         write_job_kernel<<<1, 1, 0, st>>>(job, d_job, n_flagged);
         ctx->launches++;
         PBN_CUDA_TRY(cudaGetLastError());
+        cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+        if (ctx->timing) {
+            PBN_CUDA_TRY(cudaEventCreate(&ev0));
+            PBN_CUDA_TRY(cudaEventCreate(&ev1));
+            PBN_CUDA_TRY(cudaEventRecord(ev0, st));
+        }
         cudaError_t e = f64 ? pbn::launch_pair_f64(d, k->ckde, d_job, 1, U, upb, grid, ctx->d_exp_tab, st)
                             : pbn::launch_pair_f32(d, k->ckde, d_job, 1, U, upb, grid, ctx->d_exp_tab, st);
         ctx->launches++;
         PBN_CUDA_TRY(e);
+        if (ctx->timing) {
+            PBN_CUDA_TRY(cudaEventRecord(ev1, st));
+            ctx->timed.emplace_back(ev0, ev1);
+            ctx->pair_units += (int64_t)k->n * m * (k->ckde ? 2 : 1);
+        }
         FinalizeParams F;
         F.job = d_job;
         F.upb = upb;
@@ -741,12 +773,11 @@ static int logl_impl(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, cons
     }
 
     double* d_sum = d_out_slogl;
-    bool own_sum = false;
     if (h_out_slogl || d_out_slogl) {
         int sb = (int)std::min<int64_t>((m + 255) / 256, (int64_t)ctx->sm_count * 4);
         double* partial = nullptr;
         PBN_CUDA_TRY(cudaMallocAsync(&partial, (size_t)(sb + 1) * sizeof(double), st));
-        if (!d_sum) { d_sum = partial + sb; own_sum = true; }
+        if (!d_sum) d_sum = partial + sb;
         sum_partial_kernel<<<sb, 256, 0, st>>>(out, m, partial);
         sum_final_kernel<<<1, 256, 0, st>>>(partial, sb, d_sum);
         ctx->launches += 2;
@@ -757,7 +788,6 @@ static int logl_impl(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, cons
         }
         if (h_out_slogl) PBN_CUDA_TRY(cudaStreamSynchronize(st));
         PBN_CUDA_TRY(cudaFreeAsync(partial, st));
-        (void)own_sum;
     }
     if (h_out_logl) {
         PBN_CUDA_TRY(cudaMemcpyAsync(h_out_logl, out, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -807,7 +837,15 @@ int pbn_ctx_create(int device, pbn_ctx** out) {
     PBN_CUDA_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     std::vector<double> tab(pbn::kExpTab);
-    for (int j = 0; j < pbn::kExpTab; ++j) tab[j] = (double)exp2l((long double)j / pbn::kExpTab);
+    for (int j = 0; j < pbn::kExpTab; ++j) {
+        // T'[j]: 2^(j/256) with (j << 12) subtracted from the high word (see exp2_tab)
+        double v = (double)exp2l((long double)j / pbn::kExpTab);
+        uint64_t bits;
+        memcpy(&bits, &v, 8);
+        uint32_t hi = (uint32_t)(bits >> 32) - ((uint32_t)j << 12);
+        bits = ((uint64_t)hi << 32) | (bits & 0xffffffffull);
+        memcpy(&tab[j], &bits, 8);
+    }
     PBN_CUDA_TRY(cudaMalloc(&c->d_exp_tab, tab.size() * sizeof(double)));
     PBN_CUDA_TRY(cudaMemcpy(c->d_exp_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
     // keep freed stream-ordered allocations cached instead of returning them to the OS
@@ -848,6 +886,30 @@ int pbn_ctx_counters(pbn_ctx* ctx, int64_t* launches, int64_t* h2d, int64_t* d2h
     if (launches) *launches = ctx->launches;
     if (h2d) *h2d = ctx->h2d;
     if (d2h) *d2h = ctx->d2h;
+    return PBN_OK;
+}
+int pbn_ctx_set_timing(pbn_ctx* ctx, int on) {
+    if (!ctx) return set_error(PBN_ERR_ARG, "null context");
+    ctx->timing = on != 0;
+    return PBN_OK;
+}
+int pbn_ctx_pair_kernel_time(pbn_ctx* ctx, double* total_ms, int64_t* n_launches, int64_t* pair_evals, int reset) {
+    if (!ctx) return set_error(PBN_ERR_ARG, "null context");
+    DevSetter ds(ctx->device);
+    for (auto& pr : ctx->timed) {
+        PBN_CUDA_TRY(cudaEventSynchronize(pr.second));
+        float ms = 0;
+        PBN_CUDA_TRY(cudaEventElapsedTime(&ms, pr.first, pr.second));
+        ctx->pair_ms += ms;
+        ctx->pair_launches++;
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    ctx->timed.clear();
+    if (total_ms) *total_ms = ctx->pair_ms;
+    if (n_launches) *n_launches = ctx->pair_launches;
+    if (pair_evals) *pair_evals = ctx->pair_units;
+    if (reset) { ctx->pair_ms = 0; ctx->pair_launches = 0; ctx->pair_units = 0; }
     return PBN_OK;
 }
 int pbn_ctx_last_fallback_rows(pbn_ctx* ctx, int64_t* out) {
