@@ -8,7 +8,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpbn_cuda.so")
+# PBN_CUDA_LIB selects an alternative build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("PBN_CUDA_LIB") or os.path.join(_HERE, "libpbn_cuda.so")
 
 PBN_OK, PBN_ERR_CUDA, PBN_ERR_ARG, PBN_ERR_SINGULAR, PBN_ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 PBN_F64, PBN_F32 = 0, 1

@@ -9,10 +9,10 @@
 //
 // Inputs are *whitened* rows (see whiten_kernel in runtime.cu):  y = c * L^-1 (x - mu)
 // with c chosen so that the exponent is already in table / log2 units:
-//   f64:  t = -sum_c (yt_c - yi_c)^2  ==  256 * log2(e) * (-1/2 s)   (s = Mahalanobis^2)
-//         exp(-s/2) = 2^(t/256) = 2^k * T[j] * P(g),  n = rint(t), k = n>>8, j = n&255,
-//         g = t - n in [-1/2, 1/2], P a degree-4 polynomial (max rel. err 3.4e-16).
-//         Cost: 3 DADD + 4 DFMA + 1 DFMA (accumulate) on the FP64 pipe.
+//   f64:  t = -sum_c (yt_c - yi_c)^2  ==  K * log2(e) * (-1/2 s)   (s = Mahalanobis^2, K = 2048)
+//         exp(-s/2) = 2^(t/K) = 2^k * T[j] * P(g),  n = rint(t), k = n>>11, j = n&2047,
+//         g = t - n in [-1/2, 1/2], P a degree-3 polynomial (max rel. err 3.4e-16).
+//         Cost: 3 DADD + 3 DFMA + 1 DFMA (accumulate) on the FP64 pipe.
 //   f32:  t = -sum_c (..)^2 == log2(e) * (-1/2 s);  exp(-s/2) = ex2.approx(t) (1 MUFU).
 // Sums are accumulated unshifted (every term <= 1); rows whose sum is too small for
 // that to be accurate are re-run with a per-row shift by the caller (runtime.cu).
@@ -51,15 +51,46 @@ constexpr int kThreads = 256;
 constexpr int kStages = 2;
 
 template <typename T> struct PairCfg;
-template <> struct PairCfg<double> { static constexpr int R = 2; static constexpr int TILE = 512; static constexpr int MIN_CTAS = 2; };
-template <> struct PairCfg<float>  { static constexpr int R = 4; static constexpr int TILE = 1024; static constexpr int MIN_CTAS = 2; };
+#ifndef PBN_F64_R
+#define PBN_F64_R 2
+#endif
+#ifndef PBN_F64_TILE
+#define PBN_F64_TILE 512
+#endif
+#ifndef PBN_F64_MINCTAS
+#define PBN_F64_MINCTAS 2
+#endif
+#ifndef PBN_F32_R
+#define PBN_F32_R 4
+#endif
+#ifndef PBN_F32_TILE
+#define PBN_F32_TILE 1024
+#endif
+#ifndef PBN_F32_MINCTAS
+#define PBN_F32_MINCTAS 3
+#endif
+#ifndef PBN_EXP_BITS
+#define PBN_EXP_BITS 11
+#endif
+template <> struct PairCfg<double> { static constexpr int R = PBN_F64_R; static constexpr int TILE = PBN_F64_TILE; static constexpr int MIN_CTAS = PBN_F64_MINCTAS; };
+template <> struct PairCfg<float>  { static constexpr int R = PBN_F32_R; static constexpr int TILE = PBN_F32_TILE; static constexpr int MIN_CTAS = PBN_F32_MINCTAS; };
 
-// exp2 table for the f64 path: T[j] = 2^(j/256)
-constexpr int kExpTabBits = 8;
+// exp2 table for the f64 path: T[j] = 2^(j/K), K = 2^PBN_EXP_BITS entries in shared memory
+constexpr int kExpTabBits = PBN_EXP_BITS;
 constexpr int kExpTab = 1 << kExpTabBits;
-// P(g) = exp(g * ln2/256) by Taylor to degree 4 (|g| <= 1/2): c_i = (ln2/256)^i / i!
+// P(g) = exp(g * ln2/K) by Taylor (|g| <= 1/2): c_i = (ln2/K)^i / i!;  K = 256: degree 4,
+// K = 2048: degree 3 (max relative error 3.4e-16 either way, measured against long double).
+#if PBN_EXP_BITS == 8
+constexpr int kExpDeg = 4;
 static __constant__ double c_exp2_poly[5] = {1.0, 2.7076061740622863e-03, 3.6655655969101058e-06,
                                              3.3083026805413709e-09, 2.2393951908751570e-12};
+#elif PBN_EXP_BITS == 11
+constexpr int kExpDeg = 3;
+static __constant__ double c_exp2_poly[5] = {1.0, 3.3845077175778578e-04, 5.7274462451720403e-08,
+                                             6.4615286729323650e-12, 0.0};
+#else
+#error "PBN_EXP_BITS must be 8 or 11"
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -89,13 +120,14 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
         : "memory");
 }
 
-// exp(-s/2) from the f64 kernel exponent t (= 256*log2e*(-s/2), t <= 0):
-//   2^(t/256) = 2^k * T[j] * P(g),  n = rint(t) = 256 k + j,  g = t - n.
-// The table holds T'[j] = T[j] with (j << 12) subtracted from its high word, so that the
-// scaled entry 2^k T[j] is obtained with ONE integer multiply-add: hi' + (n << 12).
+// exp(-s/2) from the f64 kernel exponent t (= K*log2e*(-s/2), t <= 0):
+//   2^(t/K) = 2^k * T[j] * P(g),  n = rint(t) = K k + j,  g = t - n.
+// The table holds T'[j] = T[j] with (j << (20 - log2 K)) subtracted from its high word, so that the
+// scaled entry 2^k T[j] is obtained with ONE integer multiply-add: hi' + n * 2^(20 - log2 K).
 // Returns P(g); `scaled` receives 2^k T[j].  SAFE = false requires t > -2^31 (guaranteed by
 // the caller from the bounding boxes of the whitened rows); SAFE = true accepts any t.
-constexpr int kNMin = -1022 * 256;
+constexpr int kNMin = -1022 * kExpTab;
+constexpr unsigned kHiLim = (PBN_EXP_BITS == 8) ? 0xC10FF000u : 0xC13FF000u;  // -261632.0 / -2093056.0
 template <bool SAFE>
 __device__ __forceinline__ double exp2_tab(double t, const double* __restrict__ tab, double& scaled) {
     const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
@@ -103,20 +135,25 @@ __device__ __forceinline__ double exp2_tab(double t, const double* __restrict__ 
     int n = __double2loint(tm);
     double nd = tm - MAGIC;
     double g = t - nd;
-    double p = fma(c_exp2_poly[4], g, c_exp2_poly[3]);
-    p = fma(p, g, c_exp2_poly[2]);
+    double p;
+    if (kExpDeg == 4) {
+        p = fma(c_exp2_poly[4], g, c_exp2_poly[3]);
+        p = fma(p, g, c_exp2_poly[2]);
+    } else {
+        p = fma(c_exp2_poly[3], g, c_exp2_poly[2]);
+    }
     p = fma(p, g, c_exp2_poly[1]);
     p = fma(p, g, 1.0);
     if (SAFE) {
         // hi word of a negative double grows (as unsigned) with its magnitude;
-        // 0xC10FF000 is the hi word of -(1022*256) = -261632.0
+        // kHiLim is the hi word of -(1022 * K)
         unsigned hi = static_cast<unsigned>(__double2hiint(t));
-        n = (hi > 0xC10FF000u) ? kNMin : n;
+        n = (hi > kHiLim) ? kNMin : n;
     } else {
         n = max(n, kNMin);
     }
     double tj = tab[n & (kExpTab - 1)];
-    scaled = __hiloint2double(__double2hiint(tj) + n * 4096, __double2loint(tj));
+    scaled = __hiloint2double(__double2hiint(tj) + n * (1 << (20 - kExpTabBits)), __double2loint(tj));
     return p;
 }
 

@@ -561,7 +561,7 @@ static int whiten_launch(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* tbl, c
 
 static double unit_scale(int dtype) {  // kernel exponent units per natural-log unit of -s/2
     const double log2e = 1.4426950408889634074;
-    return dtype == PBN_F64 ? 256.0 * log2e : log2e;
+    return dtype == PBN_F64 ? (double)pbn::kExpTab * log2e : log2e;
 }
 
 static int fit_impl(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, pbn_rows rows, const double* H,
@@ -842,7 +842,7 @@ int pbn_ctx_create(int device, pbn_ctx** out) {
         double v = (double)exp2l((long double)j / pbn::kExpTab);
         uint64_t bits;
         memcpy(&bits, &v, 8);
-        uint32_t hi = (uint32_t)(bits >> 32) - ((uint32_t)j << 12);
+        uint32_t hi = (uint32_t)(bits >> 32) - ((uint32_t)j << (20 - pbn::kExpTabBits));
         bits = ((uint64_t)hi << 32) | (bits & 0xffffffffull);
         memcpy(&tab[j], &bits, 8);
     }
