@@ -221,3 +221,73 @@ def cv_score(X, indices, limits, factor="ckde", rule="normal_reference"):
     if st:
         raise SingularCovariance("status %d" % st)
     return out.value
+
+
+# ---------------------------------------------------------------------------------------
+# oracle/_ref: the reference's own OpenCL-C kernels compiled as C++ (ref_shim/), when built.
+# Exists only where /root/reference was present at build time (this container); the
+# prebuilt .so travels to the GPU box.  Used by tests to pin the restatement above.
+# ---------------------------------------------------------------------------------------
+_REF_PATH = os.path.join(_HERE, "_ref", "libref_kernels.so")
+_ref = None
+
+
+def ref_available():
+    return os.path.exists(_REF_PATH)
+
+
+def _reflib():
+    global _ref
+    if _ref is None:
+        _ref = ctypes.CDLL(_REF_PATH)
+    return _ref
+
+
+def ref_kde_logl(train, test, H):
+    """KDE logl/slogl computed by the reference's kernels (host logic restated in ref_driver.cpp)."""
+    train, test = _fmat(train), _fmat(test)
+    N, d = train.shape
+    m = test.shape[0]
+    L, lognorm = kde_prepare(H, N)
+    Lt = np.asfortranarray(L.astype(train.dtype))
+    out = np.empty(m)
+    s = ctypes.c_double()
+    _reflib().ref_kde_logl(_c_vp(train.ctypes.data), _c_int(N), _c_vp(test.ctypes.data), _c_int(m), _c_int(d),
+                           _c_int(_dtype_code(train)), _c_vp(Lt.ctypes.data), ctypes.c_double(lognorm), _dptr(out),
+                           ctypes.byref(s))
+    return out, s.value
+
+
+def ref_ckde_logl(train, test, Hjoint):
+    train, test = _fmat(train), _fmat(test)
+    Hjoint = np.asarray(Hjoint, dtype=np.float64)
+    joint, sj = ref_kde_logl(train, test, Hjoint)
+    if train.shape[1] == 1:
+        return joint, sj
+    marg, _ = ref_kde_logl(train[:, 1:], test[:, 1:], Hjoint[1:, 1:])
+    m = test.shape[0]
+    out = np.empty(m)
+    s = ctypes.c_double()
+    _reflib().ref_ckde_combine(_dptr(np.ascontiguousarray(joint)), _dptr(np.ascontiguousarray(marg)), _c_int(m),
+                               _c_int(_dtype_code(train)), _dptr(out), ctypes.byref(s))
+    return out, s.value
+
+
+def ref_ucv_score_unconstrained(X, H):
+    """UCVScorer::score_unconstrained with the pair sums computed by the reference's kernels
+    (the scalar epilogue restates kde/UCV.cpp:296-304, 357)."""
+    X = _fmat(X)
+    N, d = X.shape
+    T = X.dtype.type
+    Ht = np.asarray(H, dtype=np.float64).reshape(d, d).astype(X.dtype)
+    L = np.linalg.cholesky(Ht.astype(np.float64)).astype(X.dtype)
+    Lt = np.asfortranarray(L)
+    pi_t = float(T(np.pi))
+    lognorm_H = T(-np.sum(np.log(np.diag(Lt).astype(np.float64))) - 0.5 * d * np.log(2 * pi_t))
+    lognorm_2H = float(lognorm_H) - 0.5 * d * np.log(2.0)
+    s2h, sh = ctypes.c_double(), ctypes.c_double()
+    _reflib().ref_ucv_sums(_c_vp(X.ctypes.data), _c_int(N), _c_int(d), _c_int(_dtype_code(X)), _c_vp(Lt.ctypes.data),
+                           ctypes.c_double(lognorm_2H), ctypes.c_double(float(lognorm_H)), ctypes.byref(s2h),
+                           ctypes.byref(sh))
+    s2, s1 = T(s2h.value), T(sh.value)
+    return float(np.exp(lognorm_2H) + float(T(2) * s2 / T(N)) - float(T(4) * s1 / T(N - 1)))
