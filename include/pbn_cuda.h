@@ -42,6 +42,7 @@ extern "C" {
 typedef struct pbn_ctx pbn_ctx;     /* one GPU: device id, stream, scratch memory          */
 typedef struct pbn_table pbn_table; /* resident column store (uploaded once, kept in HBM)  */
 typedef struct pbn_kde pbn_kde;     /* fitted KDE or CKDE: whitened training rows on device */
+typedef struct pbn_ucv pbn_ucv;     /* UCVScorer: training rows + scratch resident on device */
 
 typedef struct pbn_rows {
     int64_t b0, e0, b1, e1;
@@ -127,6 +128,26 @@ int pbn_kde_logl_device(pbn_ctx* ctx, const pbn_kde* kde, const pbn_table* test,
 /* Number of test rows of the last logl call on this context that needed the shifted
  * (max-subtracted) re-evaluation because their unshifted kernel sum underflowed. */
 int pbn_ctx_last_fallback_rows(pbn_ctx* ctx, int64_t* out);
+
+/* kde::UCVScorer (kde/UCV.hpp:12-45): constructed once per (data, variables); every score call
+ * evaluates all N(N-1)/2 pairs in ONE launch (64-bit pair indexing; the reference's 32-bit chunk
+ * offset, UCV.cpp:32,75,136, limits it to N <= 92 682). */
+int pbn_ucv_create(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, pbn_rows rows, pbn_ucv** out);
+int pbn_ucv_free(pbn_ucv* scorer);
+/* UCVScorer::score_unconstrained (H: d x d) / score_diagonal (h: d values, is_diag != 0):
+ * N * UCV(H) = e^{c2} + 2/N sum_{i<j} e^{-s_ij/4 + c2} - 4/(N-1) sum_{i<j} e^{-s_ij/2 + c1}
+ * (kde/UCV.cpp:235-399). */
+int pbn_ucv_score(pbn_ucv* scorer, const double* H_or_hdiag, int is_diag, double* out);
+/* The two pair sums  S2 = sum e^{-s/4},  S1 = sum e^{-s/2}  over slice `part` of `nparts` equal
+ * slices of the tile schedule: the multi-GPU split (each rank one slice, sums all-reduced). */
+int pbn_ucv_pair_sums(pbn_ucv* scorer, const double* H_or_hdiag, int is_diag, int part, int nparts, double* S2,
+                      double* S1);
+int64_t pbn_ucv_pairs(const pbn_ucv* scorer);
+/* UCV::bandwidth / UCV::diag_bandwidth (kde/UCV.cpp:452-525): Nelder-Mead over vech(chol(H))
+ * (or sqrt of the diagonal) from the normal-reference start, ftol_rel = xtol_rel = 1e-4, with the
+ * reference's determinant / score guards.  diagonal != 0 writes d values, else d x d. */
+int pbn_ucv_bandwidth(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, pbn_rows rows, int diagonal,
+                      double* H_out, int* n_evals);
 
 /* Device scratch for callers that keep results on the GPU (e.g. bench.py). */
 int pbn_device_alloc(pbn_ctx* ctx, int64_t bytes, void** out);

@@ -6,7 +6,7 @@ NormalReferenceRule, ScottsBandwidth, SingularCovarianceData, ...
 """
 from ._lib import SingularCovarianceData, Context, default_context, LIB_PATH
 from .dataset import DataFrame
-from .kde import BandwidthSelector, NormalReferenceRule, ScottsBandwidth, KDE
+from .kde import BandwidthSelector, NormalReferenceRule, ScottsBandwidth, UCV, UCVScorer, KDE
 from .factors import Factor, FactorType, CKDE, CKDEType
 
 __version__ = "0.1.0"

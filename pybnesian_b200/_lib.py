@@ -21,7 +21,8 @@ EXPORTS = [
     "pbn_table_free", "pbn_table_rows", "pbn_table_cols", "pbn_table_download", "pbn_table_moments", "pbn_bandwidth",
     "pbn_diag_bandwidth", "pbn_kde_fit", "pbn_ckde_fit", "pbn_kde_free", "pbn_kde_num_instances", "pbn_kde_lognorm",
     "pbn_kde_logl", "pbn_kde_logl_device", "pbn_ctx_last_fallback_rows", "pbn_device_alloc", "pbn_device_free",
-    "pbn_device_read", "pbn_ctx_set_timing", "pbn_ctx_pair_kernel_time",
+    "pbn_device_read", "pbn_ctx_set_timing", "pbn_ctx_pair_kernel_time", "pbn_ucv_create", "pbn_ucv_free",
+    "pbn_ucv_score", "pbn_ucv_pair_sums", "pbn_ucv_pairs", "pbn_ucv_bandwidth",
 ]
 
 
@@ -88,6 +89,13 @@ def lib():
         L.pbn_device_alloc.argtypes = [vp, i64, ctypes.POINTER(vp)]
         L.pbn_device_free.argtypes = [vp, vp]
         L.pbn_device_read.argtypes = [vp, vp, i64, vp]
+        L.pbn_ucv_create.argtypes = [vp, vp, ip, ci, Rows, ctypes.POINTER(vp)]
+        L.pbn_ucv_free.argtypes = [vp]
+        L.pbn_ucv_score.argtypes = [vp, dp, ci, dp]
+        L.pbn_ucv_pair_sums.argtypes = [vp, dp, ci, ci, ci, dp, dp]
+        L.pbn_ucv_pairs.argtypes = [vp]
+        L.pbn_ucv_pairs.restype = i64
+        L.pbn_ucv_bandwidth.argtypes = [vp, vp, ip, ci, Rows, ci, dp, ip]
         L.pbn_ctx_set_timing.argtypes = [vp, ci]
         L.pbn_ctx_pair_kernel_time.argtypes = [vp, dp, ctypes.POINTER(i64), ctypes.POINTER(i64), ci]
         _lib = L

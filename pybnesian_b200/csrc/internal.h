@@ -1,0 +1,135 @@
+// internal.h — shared internals of libpbn_cuda.so (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/pbn_cuda.h"
+#include "pair_kernel.cuh"
+
+int pbn_set_error(int code, const std::string& msg);
+#define set_error pbn_set_error
+
+// ------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------
+#define PBN_CUDA_TRY(expr)                                                                                  \
+    do {                                                                                                    \
+        cudaError_t err__ = (expr);                                                                         \
+        if (err__ != cudaSuccess) {                                                                         \
+            return set_error(PBN_ERR_CUDA, std::string("CUDA error ") + cudaGetErrorName(err__) + " (" +    \
+                                               cudaGetErrorString(err__) + ") at " #expr);                  \
+        }                                                                                                   \
+    } while (0)
+
+#define PBN_TRY(expr)                 \
+    do {                              \
+        int rc__ = (expr);            \
+        if (rc__ != PBN_OK) return rc__; \
+    } while (0)
+
+// ------------------------------------------------------------------------------------
+// objects
+// ------------------------------------------------------------------------------------
+struct pbn_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    int sm_count = 0;
+    double* d_exp_tab = nullptr;  // T'[j] = 2^(j/256) with (j<<12) taken off the high word, j = 0..255
+    int64_t launches = 0, h2d = 0, d2h = 0;
+    int64_t last_fallback_rows = 0;
+    // optional device timing of the pair kernel (CUDA events on the launching stream)
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;
+    double pair_ms = 0;
+    int64_t pair_launches = 0;
+    int64_t pair_units = 0;  // train x test pairs processed by timed launches (x2 for CKDE)
+};
+
+struct pbn_table {
+    pbn_ctx* ctx;
+    int ncols;
+    int64_t nrows;
+    int64_t stride;  // elements between columns
+    int dtype;
+    void* data;  // [ncols][stride]
+};
+
+struct pbn_kde {
+    pbn_ctx* ctx;
+    int d;
+    int dtype;
+    bool ckde;  // fused joint+marginal (d >= 2, variable stored last)
+    int64_t n;
+    void* y;  // whitened training rows AoS [n_pad][d]
+    float* d_bound;  // device scalar: max |whitened training coordinate|
+    double W[PBN_MAX_DIM * PBN_MAX_DIM];  // row-major lower-triangular whitening matrix (incl. unit scale)
+    double mu[PBN_MAX_DIM];
+    int perm[PBN_MAX_DIM];  // internal column k = caller column perm[k]
+    double lognorm_joint;
+    double lognorm_marg;
+};
+
+static inline size_t elem_size(int dtype) { return dtype == PBN_F64 ? 8 : 4; }
+static inline int64_t seg_count(const pbn_rows& r) { return (r.e0 - r.b0) + (r.e1 - r.b1); }
+
+struct DevSetter {
+    int prev = -1;
+    bool ok = true;
+    explicit DevSetter(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) ok = false;
+        if (ok && prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DevSetter() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+
+// ---- host linear algebra (runtime.cu) ----
+bool chol_lower(const double* H, int d, double* L);                  // column-major lower Cholesky
+void tri_inverse_rowmajor(const double* L, int d, double* Winv);     // inverse of lower-tri, row-major
+bool is_psd(const double* cov, int d, int dtype);                    // util/basic_eigen_ops.hpp:136-147
+double unit_scale(int dtype);  // kernel exponent units per natural-log unit of -s/2
+
+struct ColPtrs {
+    const void* p[PBN_MAX_DIM];
+};
+struct Vec32 {
+    double v[PBN_MAX_DIM];
+};
+struct WhitenParams {
+    ColPtrs cols;     // already permuted to internal order
+    double W[PBN_MAX_DIM * (PBN_MAX_DIM + 1) / 2];  // packed lower triangle, row-major
+    double mu[PBN_MAX_DIM];
+    int d;
+    int64_t b0, n0, b1, n;
+};
+
+int check_cols(const pbn_table* tbl, const int* cols, int d);
+int check_rows(const pbn_table* tbl, const pbn_rows& r);
+const void* col_ptr(const pbn_table* t, int c);
+std::string var_list(const int* cols, int d);
+int moments_impl(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, pbn_rows rows, double* mean_out,
+                 double* cov_out);
+// y = W (x - mu) for the rows of a range, AoS output in the table's dtype; `Wfull` row-major d x d lower.
+int whiten_raw_launch(pbn_ctx* ctx, const pbn_table* tbl, const int* cols_internal_order, int d, pbn_rows rows,
+                      const double* Wfull, const double* mu, void* out, float* bound);
+
+namespace pbn {
+cudaError_t launch_pair_f64(int D, bool ckde, const PairJob* jobs, int n_jobs, long long total_units, long long upb,
+                            int grid, const double* tab, cudaStream_t stream);
+cudaError_t launch_pair_f32(int D, bool ckde, const PairJob* jobs, int n_jobs, long long total_units, long long upb,
+                            int grid, const double* tab, cudaStream_t stream);
+int pair_tile_f64();
+int pair_tile_f32();
+int pair_tb_f64();
+int pair_tb_f32();
+}  // namespace pbn

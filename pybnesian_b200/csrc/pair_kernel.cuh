@@ -355,7 +355,17 @@ pair_kernel(const PairJob* __restrict__ jobs, int n_jobs, long long total_units,
     flush();
 }
 
-// Generic-D fallback (D > 8): one test row per thread, runtime D <= 32, same unit scheme.
-constexpr int kMaxGenericD = 32;
+// Job of the UCV pair-sum kernel (ucv_kernel.cu)
+struct UcvJob {
+    const void* y;             // whitened rows AoS [n (padded alloc)][D]
+    long long n;
+    const long long* prefix;   // prefix[tt] = first unit of row tile tt, prefix[n_row_tiles] = total
+    int n_row_tiles;
+    const float* bound;        // max |whitened coordinate|
+    double* partial;           // [grid][2]
+    long long unit_begin, unit_end;  // slice of units handled by this launch (multi-GPU split)
+};
+cudaError_t launch_ucv(int dtype_f64, int D, const UcvJob& job, long long upb, int grid, const double* tab,
+                       cudaStream_t s);
 
 }  // namespace pbn

@@ -15,109 +15,21 @@
 #include <string>
 #include <vector>
 
-#include "../../include/pbn_cuda.h"
-#include "pair_kernel.cuh"
-
-namespace pbn {
-cudaError_t launch_pair_f64(int D, bool ckde, const PairJob* jobs, int n_jobs, long long total_units, long long upb,
-                            int grid, const double* tab, cudaStream_t stream);
-cudaError_t launch_pair_f32(int D, bool ckde, const PairJob* jobs, int n_jobs, long long total_units, long long upb,
-                            int grid, const double* tab, cudaStream_t stream);
-int pair_tile_f64();
-int pair_tile_f32();
-int pair_tb_f64();
-int pair_tb_f32();
-}  // namespace pbn
+#include "internal.h"
 
 using pbn::PairJob;
 
-// ------------------------------------------------------------------------------------
-// error plumbing
-// ------------------------------------------------------------------------------------
 static thread_local std::string g_last_error;
 
-static int set_error(int code, const std::string& msg) {
+int pbn_set_error(int code, const std::string& msg) {
     g_last_error = msg;
     return code;
 }
 
-#define PBN_CUDA_TRY(expr)                                                                                  \
-    do {                                                                                                    \
-        cudaError_t err__ = (expr);                                                                         \
-        if (err__ != cudaSuccess) {                                                                         \
-            return set_error(PBN_ERR_CUDA, std::string("CUDA error ") + cudaGetErrorName(err__) + " (" +    \
-                                               cudaGetErrorString(err__) + ") at " #expr);                  \
-        }                                                                                                   \
-    } while (0)
-
-#define PBN_TRY(expr)                 \
-    do {                              \
-        int rc__ = (expr);            \
-        if (rc__ != PBN_OK) return rc__; \
-    } while (0)
-
-// ------------------------------------------------------------------------------------
-// objects
-// ------------------------------------------------------------------------------------
-struct pbn_ctx {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    cudaStream_t own_stream = nullptr;
-    int sm_count = 0;
-    double* d_exp_tab = nullptr;  // T'[j] = 2^(j/256) with (j<<12) taken off the high word, j = 0..255
-    int64_t launches = 0, h2d = 0, d2h = 0;
-    int64_t last_fallback_rows = 0;
-    // optional device timing of the pair kernel (CUDA events on the launching stream)
-    bool timing = false;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;
-    double pair_ms = 0;
-    int64_t pair_launches = 0;
-    int64_t pair_units = 0;  // train x test pairs processed by timed launches (x2 for CKDE)
-};
-
-struct pbn_table {
-    pbn_ctx* ctx;
-    int ncols;
-    int64_t nrows;
-    int64_t stride;  // elements between columns
-    int dtype;
-    void* data;  // [ncols][stride]
-};
-
-struct pbn_kde {
-    pbn_ctx* ctx;
-    int d;
-    int dtype;
-    bool ckde;  // fused joint+marginal (d >= 2, variable stored last)
-    int64_t n;
-    void* y;  // whitened training rows AoS [n_pad][d]
-    float* d_bound;  // device scalar: max |whitened training coordinate|
-    double W[PBN_MAX_DIM * PBN_MAX_DIM];  // row-major lower-triangular whitening matrix (incl. unit scale)
-    double mu[PBN_MAX_DIM];
-    int perm[PBN_MAX_DIM];  // internal column k = caller column perm[k]
-    double lognorm_joint;
-    double lognorm_marg;
-};
-
-static inline size_t elem_size(int dtype) { return dtype == PBN_F64 ? 8 : 4; }
-static inline int64_t seg_count(const pbn_rows& r) { return (r.e0 - r.b0) + (r.e1 - r.b1); }
-
-struct DevSetter {
-    int prev = -1;
-    bool ok = true;
-    explicit DevSetter(int dev) {
-        if (cudaGetDevice(&prev) != cudaSuccess) ok = false;
-        if (ok && prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
-    }
-    ~DevSetter() {
-        if (prev >= 0) cudaSetDevice(prev);
-    }
-};
-
 // ------------------------------------------------------------------------------------
 // small host linear algebra (d <= 32)
 // ------------------------------------------------------------------------------------
-static bool chol_lower(const double* H, int d, double* L) {  // column-major
+bool chol_lower(const double* H, int d, double* L) {  // column-major
     std::fill(L, L + d * d, 0.0);
     for (int j = 0; j < d; ++j) {
         double s = H[j + j * d];
@@ -135,7 +47,7 @@ static bool chol_lower(const double* H, int d, double* L) {  // column-major
 }
 
 // inverse of a lower-triangular column-major matrix, result row-major lower
-static void tri_inverse_rowmajor(const double* L, int d, double* Winv) {
+void tri_inverse_rowmajor(const double* L, int d, double* Winv) {
     std::fill(Winv, Winv + d * d, 0.0);
     for (int j = 0; j < d; ++j) {
         // solve L x = e_j
@@ -177,7 +89,7 @@ static void jacobi_eigenvalues(std::vector<double> a, int d, std::vector<double>
 }
 
 // util/basic_eigen_ops.hpp:136-147 (eps of the data type)
-static bool is_psd(const double* cov, int d, int dtype) {
+bool is_psd(const double* cov, int d, int dtype) {
     std::vector<double> a(cov, cov + d * d), ev;
     jacobi_eigenvalues(a, d, ev);
     double mx = *std::max_element(ev.begin(), ev.end());
@@ -189,12 +101,6 @@ static bool is_psd(const double* cov, int d, int dtype) {
 // ------------------------------------------------------------------------------------
 // device kernels: moments
 // ------------------------------------------------------------------------------------
-struct ColPtrs {
-    const void* p[PBN_MAX_DIM];
-};
-struct Vec32 {
-    double v[PBN_MAX_DIM];
-};
 
 __device__ __forceinline__ int64_t map_row(int64_t r, int64_t b0, int64_t n0, int64_t b1) {
     return r < n0 ? b0 + r : b1 + (r - n0);
@@ -273,14 +179,6 @@ __global__ void cov_tile_kernel(ColPtrs cols, Vec32 mean, int d, int ntile_side,
 // ------------------------------------------------------------------------------------
 // device kernels: whitening  y = W (x - mu), AoS output
 // ------------------------------------------------------------------------------------
-struct WhitenParams {
-    ColPtrs cols;     // already permuted to internal order
-    double W[PBN_MAX_DIM * (PBN_MAX_DIM + 1) / 2];  // packed lower triangle, row-major
-    double mu[PBN_MAX_DIM];
-    int d;
-    int64_t b0, n0, b1, n;
-};
-
 template <typename T>
 __global__ void whiten_kernel(const __grid_constant__ WhitenParams P, T* __restrict__ out, float* __restrict__ bound) {
     int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -450,23 +348,23 @@ __global__ void write_job_kernel(PairJob j, PairJob* dst, int* zero_counter) {
 // ------------------------------------------------------------------------------------
 // helpers
 // ------------------------------------------------------------------------------------
-static int check_cols(const pbn_table* tbl, const int* cols, int d) {
+int check_cols(const pbn_table* tbl, const int* cols, int d) {
     if (!tbl || !cols) return set_error(PBN_ERR_ARG, "null table / column list");
     if (d < 1 || d > PBN_MAX_DIM) return set_error(PBN_ERR_UNSUPPORTED, "number of variables must be in [1, 32]");
     for (int i = 0; i < d; ++i)
         if (cols[i] < 0 || cols[i] >= tbl->ncols) return set_error(PBN_ERR_ARG, "column index out of range");
     return PBN_OK;
 }
-static int check_rows(const pbn_table* tbl, const pbn_rows& r) {
+int check_rows(const pbn_table* tbl, const pbn_rows& r) {
     if (r.b0 < 0 || r.e0 < r.b0 || r.e0 > tbl->nrows || r.b1 < 0 || r.e1 < r.b1 || r.e1 > tbl->nrows)
         return set_error(PBN_ERR_ARG, "row range out of bounds");
     return PBN_OK;
 }
-static const void* col_ptr(const pbn_table* t, int c) {
+const void* col_ptr(const pbn_table* t, int c) {
     return static_cast<const char*>(t->data) + (size_t)c * t->stride * elem_size(t->dtype);
 }
 
-static int moments_impl(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, pbn_rows rows, double* mean_out,
+int moments_impl(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, pbn_rows rows, double* mean_out,
                         double* cov_out) {
     int64_t n = seg_count(rows);
     if (n <= 0) return set_error(PBN_ERR_ARG, "empty row range");
@@ -526,22 +424,21 @@ static int moments_impl(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int
     return PBN_OK;
 }
 
-static std::string var_list(const int* cols, int d) {
+std::string var_list(const int* cols, int d) {
     std::string s = "[";
     for (int i = 0; i < d; ++i) s += (i ? ", " : "") + std::to_string(cols[i]);
     return s + "]";
 }
 
-static int whiten_launch(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* tbl, const int* cols, pbn_rows rows, void* out,
-                         float* bound) {
+int whiten_raw_launch(pbn_ctx* ctx, const pbn_table* tbl, const int* cols_io, int d, pbn_rows rows, const double* Wfull,
+                      const double* mu, void* out, float* bound) {
     WhitenParams P;
     memset(&P, 0, sizeof(P));
-    const int d = k->d;
-    for (int i = 0; i < d; ++i) P.cols.p[i] = col_ptr(tbl, cols[k->perm[i]]);
+    for (int i = 0; i < d; ++i) P.cols.p[i] = col_ptr(tbl, cols_io[i]);
     int w = 0;
     for (int i = 0; i < d; ++i)
-        for (int j = 0; j <= i; ++j) P.W[w++] = k->W[i * d + j];
-    for (int i = 0; i < d; ++i) P.mu[i] = k->mu[i];
+        for (int j = 0; j <= i; ++j) P.W[w++] = Wfull[i * d + j];
+    for (int i = 0; i < d; ++i) P.mu[i] = mu[i];
     P.d = d;
     P.b0 = rows.b0;
     P.n0 = rows.e0 - rows.b0;
@@ -550,7 +447,7 @@ static int whiten_launch(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* tbl, c
     if (P.n == 0) return PBN_OK;
     const int threads = 256;
     int blocks = (int)((P.n + threads - 1) / threads);
-    if (k->dtype == PBN_F64)
+    if (tbl->dtype == PBN_F64)
         whiten_kernel<double><<<blocks, threads, 0, ctx->stream>>>(P, static_cast<double*>(out), bound);
     else
         whiten_kernel<float><<<blocks, threads, 0, ctx->stream>>>(P, static_cast<float*>(out), bound);
@@ -559,7 +456,14 @@ static int whiten_launch(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* tbl, c
     return PBN_OK;
 }
 
-static double unit_scale(int dtype) {  // kernel exponent units per natural-log unit of -s/2
+static int whiten_launch(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* tbl, const int* cols, pbn_rows rows, void* out,
+                         float* bound) {
+    int pc[PBN_MAX_DIM];
+    for (int i = 0; i < k->d; ++i) pc[i] = cols[k->perm[i]];
+    return whiten_raw_launch(ctx, tbl, pc, k->d, rows, k->W, k->mu, out, bound);
+}
+
+double unit_scale(int dtype) {  // kernel exponent units per natural-log unit of -s/2
     const double log2e = 1.4426950408889634074;
     return dtype == PBN_F64 ? (double)pbn::kExpTab * log2e : log2e;
 }

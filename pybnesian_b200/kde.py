@@ -103,6 +103,99 @@ class ScottsBandwidth(_NativeSelector):
     _name = "ScottsBandwidth"
 
 
+class UCVScorer:
+    """pybnesian.UCVScorer (kde/UCV.hpp:12-45, pybindings_kde.cpp:187-190): N * UCV(H) for a
+    diagonal (`score_diagonal(h)`) or full (`score_unconstrained(H)`) bandwidth."""
+
+    def __init__(self, df, variables):
+        frame = DataFrame.wrap(df)
+        self._variables = list(variables)
+        frame.dtype_code(self._variables, "score UCV")
+        self._tbl, self._cols, _ = frame.device_table(self._variables)
+        self._handle = ctypes.c_void_p()
+        check(lib().pbn_ucv_create(self._tbl.ctx.handle, self._tbl.handle, int_array(self._cols), len(self._cols),
+                                   self._tbl.rows(), ctypes.byref(self._handle)))
+
+    def score_diagonal(self, diagonal_bandwidth):
+        h = np.ascontiguousarray(np.asarray(diagonal_bandwidth, dtype=np.float64).ravel())
+        d = len(self._variables)
+        if h.size != d:
+            raise ValueError("Wrong dimension for bandwidth vector. it should be a %d vector." % d)
+        out = ctypes.c_double()
+        check(lib().pbn_ucv_score(self._handle, _dp(h), 1, ctypes.byref(out)))
+        return out.value
+
+    def score_unconstrained(self, bandwidth):
+        d = len(self._variables)
+        H = np.asarray(bandwidth, dtype=np.float64)
+        if H.shape != (d, d):
+            raise ValueError("Wrong dimension for bandwidth matrix. it should be a %dx%d matrix." % (d, d))
+        H = np.asfortranarray(H)
+        out = ctypes.c_double()
+        check(lib().pbn_ucv_score(self._handle, _dp(H), 0, ctypes.byref(out)))
+        return out.value
+
+    def pair_sums(self, bandwidth, part=0, nparts=1, diagonal=False):
+        """(sum e^{-s/4}, sum e^{-s/2}) over one slice of the pair-tile schedule (multi-GPU split)."""
+        H = np.asfortranarray(np.asarray(bandwidth, dtype=np.float64))
+        s2, s1 = ctypes.c_double(), ctypes.c_double()
+        check(lib().pbn_ucv_pair_sums(self._handle, _dp(H), 1 if diagonal else 0, int(part), int(nparts),
+                                      ctypes.byref(s2), ctypes.byref(s1)))
+        return s2.value, s1.value
+
+    def num_pairs(self):
+        return int(lib().pbn_ucv_pairs(self._handle))
+
+    def __del__(self):
+        try:
+            if self._handle:
+                lib().pbn_ucv_free(self._handle)
+                self._handle = None
+        except Exception:
+            pass
+
+
+class UCV(BandwidthSelector):
+    """pybnesian.UCV (kde/UCV.hpp:47-56, UCV.cpp:452-525): unbiased cross-validation bandwidth,
+    Nelder-Mead from the normal-reference start."""
+
+    last_evaluations = 0
+
+    def _run(self, df, variables, diagonal):
+        variables = list(variables)
+        frame = DataFrame.wrap(df)
+        frame.dtype_code(variables, "fit bandwidth")
+        tbl, cols, _ = frame.device_table(variables)
+        d = len(cols)
+        out = np.empty(d) if diagonal else np.empty((d, d), order="F")
+        n = ctypes.c_int()
+        check(lib().pbn_ucv_bandwidth(tbl.ctx.handle, tbl.handle, int_array(cols), d, tbl.rows(), 1 if diagonal else 0,
+                                      _dp(out), ctypes.byref(n)))
+        self.last_evaluations = n.value
+        return out
+
+    def bandwidth(self, df, variables):
+        if not list(variables):
+            return np.empty((0, 0))
+        return self._run(df, variables, False)
+
+    def diag_bandwidth(self, df, variables):
+        if not list(variables):
+            return np.empty(0)
+        return self._run(df, variables, True)
+
+    def __str__(self):
+        return "UCV"
+
+    __repr__ = __str__
+
+    def __getstate__(self):
+        return ()
+
+    def __setstate__(self, state):
+        pass
+
+
 class _FittedHandle:
     """Owns a pbn_kde (whitened training rows resident on the GPU)."""
 

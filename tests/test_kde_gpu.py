@@ -241,3 +241,29 @@ def test_multi_tile_ragged_sizes(pbn):
             want, _ = oracle.ckde_logl(X, T[sub], oracle.bandwidth(X))
             got = cpd.logl(te.astype(dtype))[sub]
             assert (relerr(got, want) if dtype == "float64" else relerr32(got, want)) < tol
+
+
+GOLD = np.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "kde_golden.npz"))
+
+
+@pytest.mark.parametrize("dt", ["float64", "float32"])
+@pytest.mark.parametrize("variables", VARSETS)
+@pytest.mark.parametrize("N,m", [(500, 50), (10, 50), (300, 70)])
+def test_against_reference_kernel_goldens(pbn, dt, variables, N, m):
+    """CUDA path vs the committed outputs of the reference's own OpenCL-C kernels
+    (tests/golden/make_golden.py), independent of the oracle library."""
+    if N <= len(variables):
+        pytest.skip("not enough instances")
+    tr = util_data.generate_normal_data(N, 0).astype(dt)
+    te = util_data.generate_normal_data(m, 1).astype(dt)
+    key = "%s_%s_%d_%d" % (dt, "".join(variables), N, m)
+    err = relerr if dt == "float64" else relerr32
+    tol = RTOL64 if dt == "float64" else RTOL32
+    k = pbn.KDE(variables); k.fit(tr)
+    assert relerr(k.bandwidth, GOLD["H_" + key]) < (1e-12 if dt == "float64" else 1e-5)
+    assert err(k.logl(te), GOLD["ref_kde_logl_" + key]) < tol
+    assert abs(k.slogl(te) - float(GOLD["ref_kde_slogl_" + key])) <= tol * abs(float(GOLD["ref_kde_slogl_" + key]))
+    cpd = pbn.CKDE(variables[0], variables[1:]); cpd.fit(tr)
+    assert err(cpd.logl(te), GOLD["ref_ckde_logl_" + key]) < tol
+    if dt == "float64":
+        assert np.allclose(k.logl(te), GOLD["scipy_kde_logl_" + key], rtol=1e-9, atol=1e-11)

@@ -193,7 +193,7 @@ def test_cv_score_composition():
 
 
 def test_singular_covariance():
-    X = util_data.generate_normal_data(100, 0)[["a", "b"]].to_numpy()
+    X = util_data.generate_normal_data(100, 0)[["a", "b"]].to_numpy().copy()
     X[:, 1] = 2 * X[:, 0]
     with pytest.raises(oracle.SingularCovariance):
         oracle.bandwidth(X)
