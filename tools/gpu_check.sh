@@ -1,0 +1,18 @@
+#!/bin/bash
+# Runs on the GPU box (under gpurun): GPU tests, the default bench, the ncu launch list and one
+# full ncu capture of the pair kernel.  Outputs under gpurun_out/.
+set -x
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
+nproc > gpurun_out/nproc.txt
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+tail -5 gpurun_out/pytest_gpu.log
+timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
+cat gpurun_out/bench.json
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"
+cat gpurun_out/bench_ref.json
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu --e2e-steps 1 > gpurun_out/ncu_launch.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:pair_kernel -s 1 -c 1 -f -o gpurun_out/prof_pair \
+    python bench.py --steps 1 --warmup 3 --n-test 131072 --no-cpu --e2e-steps 1 > gpurun_out/ncu_full.log 2>&1
+ls -la gpurun_out
