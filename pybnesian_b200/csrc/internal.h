@@ -42,7 +42,7 @@ struct pbn_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
     int sm_count = 0;
-    double* d_exp_tab = nullptr;  // T'[j] = 2^(j/256) with (j<<12) taken off the high word, j = 0..255
+    double* d_exp_tab = nullptr;  // T'[j] = 2^(j/K) with (j << (20 - log2 K)) taken off the high word, j = 0..K-1 (pair_kernel.cuh)
     int64_t launches = 0, h2d = 0, d2h = 0;
     int64_t last_fallback_rows = 0;
     // optional device timing of the pair kernel (CUDA events on the launching stream)
@@ -128,8 +128,8 @@ cudaError_t launch_pair_f64(int D, bool ckde, const PairJob* jobs, int n_jobs, l
                             int grid, const double* tab, cudaStream_t stream);
 cudaError_t launch_pair_f32(int D, bool ckde, const PairJob* jobs, int n_jobs, long long total_units, long long upb,
                             int grid, const double* tab, cudaStream_t stream);
-int pair_tile_f64();
-int pair_tile_f32();
+int pair_tile_f64(int D);
+int pair_tile_f32(int D);
 int pair_tb_f64();
 int pair_tb_f32();
 }  // namespace pbn

@@ -72,25 +72,47 @@ template <typename T> struct PairCfg;
 #ifndef PBN_EXP_BITS
 #define PBN_EXP_BITS 11
 #endif
+#ifndef PBN_EXP_DEG
+#define PBN_EXP_DEG 3
+#endif
+#ifndef PBN_EXP_REP
+#define PBN_EXP_REP 1
+#endif
 template <> struct PairCfg<double> { static constexpr int R = PBN_F64_R; static constexpr int TILE = PBN_F64_TILE; static constexpr int MIN_CTAS = PBN_F64_MINCTAS; };
 template <> struct PairCfg<float>  { static constexpr int R = PBN_F32_R; static constexpr int TILE = PBN_F32_TILE; static constexpr int MIN_CTAS = PBN_F32_MINCTAS; };
 
-// exp2 table for the f64 path: T[j] = 2^(j/K), K = 2^PBN_EXP_BITS entries in shared memory
+// exp2 table of the f64 path: T[j] = 2^(j/K), K = 2^PBN_EXP_BITS, held in shared memory in kExpRep
+// interleaved copies (copy r of entry j at index j*kExpRep + r; a thread reads copy lane mod kExpRep).
+// kExpRep = 16 makes the gather bank-conflict free (2 wavefronts per 8-byte LDS instead of the ~6.6
+// measured for one shared copy), but on B200 it bought nothing: the single-copy kernel reports the
+// shared-memory pipe 98.5% busy (profiles/r1b_ncu_pair_f64_ckde_d4.txt) yet runs at the same speed as
+// the conflict-free variant (profiles/r1c_tuning.md) - the replays hide behind the FP64 pipe, and the
+// extra address arithmetic costs issue slots the DFMA stream needs.  Default: one copy, K = 2048.
 constexpr int kExpTabBits = PBN_EXP_BITS;
 constexpr int kExpTab = 1 << kExpTabBits;
-// P(g) = exp(g * ln2/K) by Taylor (|g| <= 1/2): c_i = (ln2/K)^i / i!;  K = 256: degree 4,
-// K = 2048: degree 3 (max relative error 3.4e-16 either way, measured against long double).
-#if PBN_EXP_BITS == 8
-constexpr int kExpDeg = 4;
-static __constant__ double c_exp2_poly[5] = {1.0, 2.7076061740622863e-03, 3.6655655969101058e-06,
-                                             3.3083026805413709e-09, 2.2393951908751570e-12};
-#elif PBN_EXP_BITS == 11
-constexpr int kExpDeg = 3;
-static __constant__ double c_exp2_poly[5] = {1.0, 3.3845077175778578e-04, 5.7274462451720403e-08,
-                                             6.4615286729323650e-12, 0.0};
-#else
-#error "PBN_EXP_BITS must be 8 or 11"
-#endif
+constexpr int kExpRep = PBN_EXP_REP;
+constexpr int kExpDeg = PBN_EXP_DEG;
+static_assert(kExpRep == 1 || kExpRep == 2 || kExpRep == 4 || kExpRep == 8 || kExpRep == 16, "PBN_EXP_REP");
+static_assert(kExpDeg >= 2 && kExpDeg <= 4, "PBN_EXP_DEG");
+// train points per shared-memory tile: halved for wide f64 rows so that two CTAs (tiles + table) still
+// fit the 227 KB of an SM
+template <typename T> __host__ __device__ constexpr int pair_tile(int D) {
+    return (sizeof(T) == 8 && D >= 7) ? PairCfg<T>::TILE / 2 : PairCfg<T>::TILE;
+}
+template <typename T> __host__ __device__ constexpr size_t exp_tab_smem_bytes() {
+    return sizeof(T) == 8 ? static_cast<size_t>(kExpTab) * kExpRep * sizeof(double) : 0;
+}
+// P(g) ~ exp(a g), a = ln2/K, |g| <= 1/2: Taylor polynomial of degree kExpDeg + 1 with its leading term
+// replaced by its Chebyshev economisation on [-h, h], h = a/2 (error = next Taylor term / 2^deg):
+//   K =  512, degree 3: 1.1e-15      K = 2048, degree 3: 4.3e-18      K = 256, degree 4 (plain Taylor): 3.8e-17
+//   K = 2048, degree 2: 2.0e-13      K = 1024, degree 2: 1.6e-12      (experimental, PBN_EXP_DEG=2)
+constexpr double kExpA = 0.693147180559945309417232121458 / kExpTab;
+constexpr double kExpH2 = 0.25 * kExpA * kExpA;  // h^2
+constexpr double kExpC0 = kExpDeg == 3 ? 1.0 - kExpH2 * kExpH2 / 192.0 : 1.0;
+constexpr double kExpC1 = kExpDeg == 2 ? kExpA * (1.0 + kExpH2 / 8.0) : kExpA;
+constexpr double kExpC2 = kExpDeg == 3 ? kExpA * kExpA * (0.5 + kExpH2 / 24.0) : 0.5 * kExpA * kExpA;
+constexpr double kExpC3 = kExpA * kExpA * kExpA / 6.0;
+constexpr double kExpC4 = kExpA * kExpA * kExpA * kExpA / 24.0;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -124,10 +146,12 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
 //   2^(t/K) = 2^k * T[j] * P(g),  n = rint(t) = K k + j,  g = t - n.
 // The table holds T'[j] = T[j] with (j << (20 - log2 K)) subtracted from its high word, so that the
 // scaled entry 2^k T[j] is obtained with ONE integer multiply-add: hi' + n * 2^(20 - log2 K).
+// `tab` is the calling lane's copy of the table (tab_base + lane % kExpRep, stride kExpRep).
 // Returns P(g); `scaled` receives 2^k T[j].  SAFE = false requires t > -2^31 (guaranteed by
 // the caller from the bounding boxes of the whitened rows); SAFE = true accepts any t.
 constexpr int kNMin = -1022 * kExpTab;
-constexpr unsigned kHiLim = (PBN_EXP_BITS == 8) ? 0xC10FF000u : 0xC13FF000u;  // -261632.0 / -2093056.0
+// hi word of the double -(1022 * K): sign | (1023 + 9 + log2 K) << 20 | top mantissa bits of 1022/1024
+constexpr unsigned kHiLim = 0x80000000u | (static_cast<unsigned>(1023 + 9 + kExpTabBits) << 20) | 0xFF000u;
 template <bool SAFE>
 __device__ __forceinline__ double exp2_tab(double t, const double* __restrict__ tab, double& scaled) {
     const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
@@ -137,13 +161,16 @@ __device__ __forceinline__ double exp2_tab(double t, const double* __restrict__ 
     double g = t - nd;
     double p;
     if (kExpDeg == 4) {
-        p = fma(c_exp2_poly[4], g, c_exp2_poly[3]);
-        p = fma(p, g, c_exp2_poly[2]);
+        p = fma(kExpC4, g, kExpC3);
+        p = fma(p, g, kExpC2);
+        p = fma(p, g, kExpC1);
+    } else if (kExpDeg == 3) {
+        p = fma(kExpC3, g, kExpC2);
+        p = fma(p, g, kExpC1);
     } else {
-        p = fma(c_exp2_poly[3], g, c_exp2_poly[2]);
+        p = fma(kExpC2, g, kExpC1);
     }
-    p = fma(p, g, c_exp2_poly[1]);
-    p = fma(p, g, 1.0);
+    p = fma(p, g, kExpC0);
     if (SAFE) {
         // hi word of a negative double grows (as unsigned) with its magnitude;
         // kHiLim is the hi word of -(1022 * K)
@@ -152,9 +179,15 @@ __device__ __forceinline__ double exp2_tab(double t, const double* __restrict__ 
     } else {
         n = max(n, kNMin);
     }
-    double tj = tab[n & (kExpTab - 1)];
+    double tj = tab[(n & (kExpTab - 1)) * kExpRep];
     scaled = __hiloint2double(__double2hiint(tj) + n * (1 << (20 - kExpTabBits)), __double2loint(tj));
     return p;
+}
+
+// Fills the interleaved shared-memory copies of the table from the K-entry global table.
+__device__ __forceinline__ void exp_tab_fill(double* __restrict__ tab_s, const double* __restrict__ tab_g, int tid,
+                                             int nthreads) {
+    for (int i = tid; i < kExpTab * kExpRep; i += nthreads) tab_s[i] = tab_g[i / kExpRep];
 }
 
 // One (test tile) x (train tile) unit on the FP64 pipe.
@@ -229,7 +262,7 @@ __global__ void __launch_bounds__(kThreads, PairCfg<T>::MIN_CTAS)
 pair_kernel(const PairJob* __restrict__ jobs, int n_jobs, long long total_units, long long upb,
             const double* __restrict__ exp_tab_g) {
     constexpr int R = PairCfg<T>::R;
-    constexpr int TILE = PairCfg<T>::TILE;
+    constexpr int TILE = pair_tile<T>(D);
     constexpr int TB = kThreads * R;  // test rows per tile
     constexpr uint32_t TILE_BYTES = TILE * D * sizeof(T);
 
@@ -244,9 +277,8 @@ pair_kernel(const PairJob* __restrict__ jobs, int n_jobs, long long total_units,
     if (u1 > total_units) u1 = total_units;
     if (u0 >= u1) return;
 
-    if (sizeof(T) == 8) {
-        for (int i = tid; i < kExpTab; i += kThreads) tab[i] = exp_tab_g[i];
-    }
+    if (sizeof(T) == 8) exp_tab_fill(tab, exp_tab_g, tid, kThreads);
+    tab += tid & (kExpRep - 1);  // this lane's copy
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) mbar_init(&full_bar[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");

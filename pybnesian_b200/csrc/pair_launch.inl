@@ -8,7 +8,7 @@ namespace pbn {
 template <int D, bool CKDE>
 static cudaError_t launch_one(const PairJob* jobs, int n_jobs, long long total_units, long long upb, int grid,
                               const double* tab, cudaStream_t stream) {
-    constexpr size_t smem = kStages * PairCfg<PBN_T>::TILE * D * sizeof(PBN_T) + 64 + kExpTab * sizeof(double);
+    constexpr size_t smem = kStages * pair_tile<PBN_T>(D) * D * sizeof(PBN_T) + 64 + exp_tab_smem_bytes<PBN_T>();
     static bool configured = false;  // per instantiation; attribute is per device function
     auto kern = pair_kernel<PBN_T, D, CKDE>;
     if (!configured || true) {
@@ -34,7 +34,7 @@ cudaError_t PBN_LAUNCH_NAME(int D, bool ckde, const PairJob* jobs, int n_jobs, l
 #undef PBN_CASE
 }
 
-int PBN_TILE_NAME() { return PairCfg<PBN_T>::TILE; }
+int PBN_TILE_NAME(int D) { return pair_tile<PBN_T>(D); }
 int PBN_TB_NAME() { return kThreads * PairCfg<PBN_T>::R; }
 
 }  // namespace pbn

@@ -509,7 +509,7 @@ static int fit_impl(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, 
     for (int i = 0; i < d; ++i) pc[i] = cols[k->perm[i]];
     int rc = moments_impl(ctx, tbl, pc.data(), d, rows, k->mu, nullptr);
     if (rc != PBN_OK) { delete k; return rc; }
-    int tile = k->dtype == PBN_F64 ? pbn::pair_tile_f64() : pbn::pair_tile_f32();
+    int tile = k->dtype == PBN_F64 ? pbn::pair_tile_f64(d) : pbn::pair_tile_f32(d);
     int64_t n_pad = ((n + tile - 1) / tile) * tile + 16;
     size_t ybytes = ((size_t)n_pad * d * elem_size(k->dtype) + 255) / 256 * 256;
     cudaError_t e = cudaMallocAsync(&k->y, ybytes + 256, ctx->stream);
@@ -542,7 +542,7 @@ static int logl_impl(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, cons
     }
     const bool f64 = k->dtype == PBN_F64;
     const size_t es = elem_size(k->dtype);
-    const int TILE = f64 ? pbn::pair_tile_f64() : pbn::pair_tile_f32();
+    const int TILE = f64 ? pbn::pair_tile_f64(d) : pbn::pair_tile_f32(d);
     const int TB = f64 ? pbn::pair_tb_f64() : pbn::pair_tb_f32();
     const bool fast = d <= 8;
 

@@ -249,7 +249,7 @@ int pbn_ucv_create(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, p
     int rc = moments_impl(ctx, tbl, cols, d, rows, s->mu, nullptr);
     if (rc != PBN_OK) { delete s; return rc; }
     const bool f64 = s->dtype == PBN_F64;
-    const int TILE = f64 ? pbn::pair_tile_f64() : pbn::pair_tile_f32();
+    const int TILE = f64 ? pbn::pair_tile_f64(d) : pbn::pair_tile_f32(d);
     const int TB = f64 ? pbn::pair_tb_f64() : pbn::pair_tb_f32();
     s->n_row_tiles = (int)((n + TB - 1) / TB);
     std::vector<long long> prefix(s->n_row_tiles + 1, 0);

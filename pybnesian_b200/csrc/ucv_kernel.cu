@@ -71,7 +71,7 @@ template <typename T, int D>
 __global__ void __launch_bounds__(kThreads, 2)
 ucv_kernel(UcvJob job, long long upb, const double* __restrict__ exp_tab_g) {
     constexpr int R = PairCfg<T>::R;
-    constexpr int TILE = PairCfg<T>::TILE;
+    constexpr int TILE = pair_tile<T>(D);
     constexpr int TB = kThreads * R;
     constexpr uint32_t TILE_BYTES = TILE * D * sizeof(T);
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -89,8 +89,8 @@ ucv_kernel(UcvJob job, long long upb, const double* __restrict__ exp_tab_g) {
     for (int r = 0; r < R; ++r) { s2[r] = 0; s1[r] = 0; }
 
     if (u0 < u1) {
-        if (sizeof(T) == 8)
-            for (int i = tid; i < kExpTab; i += kThreads) tab[i] = exp_tab_g[i];
+        if (sizeof(T) == 8) exp_tab_fill(tab, exp_tab_g, tid, kThreads);
+        tab += tid & (kExpRep - 1);  // this lane's copy
         if (tid == 0) {
             for (int s = 0; s < kStages; ++s) mbar_init(&full_bar[s], 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -183,7 +183,7 @@ ucv_kernel(UcvJob job, long long upb, const double* __restrict__ exp_tab_g) {
 
 template <typename T, int D>
 static cudaError_t launch_ucv_one(const UcvJob& job, long long upb, int grid, const double* tab, cudaStream_t stream) {
-    constexpr size_t smem = kStages * PairCfg<T>::TILE * D * sizeof(T) + 64 + kExpTab * sizeof(double);
+    constexpr size_t smem = kStages * pair_tile<T>(D) * D * sizeof(T) + 64 + exp_tab_smem_bytes<T>();
     auto kern = ucv_kernel<T, D>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;

@@ -34,4 +34,5 @@ if __name__ == "__main__":
     for kind, d, dt in shapes:
         v, s = run(kind, d, n, dt)
         out["%s_d%d_%s" % (kind, d, dt[-2:])] = "%.3e" % v
+        out["%s_d%d_%s_slogl" % (kind, d, dt[-2:])] = "%.15g" % s
     print(os.path.basename(os.environ.get("PBN_CUDA_LIB", "default")), json.dumps(out), flush=True)
