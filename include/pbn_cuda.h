@@ -37,12 +37,17 @@ extern "C" {
 #define PBN_BW_NORMAL_REFERENCE 0 /* kde/NormalReferenceRule.hpp:109-134 */
 #define PBN_BW_SCOTT 1            /* kde/ScottsBandwidth.hpp:91-117 */
 
+#define PBN_FACTOR_CKDE 0            /* factors/continuous/CKDE.hpp */
+#define PBN_FACTOR_LINEAR_GAUSSIAN 1 /* factors/continuous/LinearGaussianCPD.hpp */
+
 #define PBN_MAX_DIM 32
 
 typedef struct pbn_ctx pbn_ctx;     /* one GPU: device id, stream, scratch memory          */
 typedef struct pbn_table pbn_table; /* resident column store (uploaded once, kept in HBM)  */
 typedef struct pbn_kde pbn_kde;     /* fitted KDE or CKDE: whitened training rows on device */
 typedef struct pbn_ucv pbn_ucv;     /* UCVScorer: training rows + scratch resident on device */
+typedef struct pbn_cv pbn_cv;       /* CrossValidation / HoldOut over a resident table: shuffled-order copy + fold statistics */
+typedef struct pbn_intset pbn_intset; /* std::unordered_set<int> (parent / children sets of the DAG) */
 
 typedef struct pbn_rows {
     int64_t b0, e0, b1, e1;
@@ -148,6 +153,73 @@ int64_t pbn_ucv_pairs(const pbn_ucv* scorer);
  * reference's determinant / score guards.  diagonal != 0 writes d values, else d x d. */
 int pbn_ucv_bandwidth(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, pbn_rows rows, int diagonal,
                       double* H_out, int* n_evals);
+
+/* LinearGaussianCPD::fit = MLE<LinearGaussianCPD>::estimate (learning/parameters/mle_LinearGaussianCPD.hpp:11-221):
+ * cols[0] = variable, cols[1..d) = parents; writes beta[d] (intercept first) and the variance
+ * (+inf when rows <= d, as the reference). */
+int pbn_lg_fit(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, pbn_rows rows, double* beta_out,
+               double* variance_out);
+/* LinearGaussianCPD::logl / slogl (factors/continuous/LinearGaussianCPD.cpp:92-149, 251-292); out_logl
+ * (rows.count doubles) and out_slogl may each be NULL. */
+int pbn_lg_logl(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, pbn_rows rows, const double* beta,
+                double variance, double* out_logl, double* out_slogl);
+
+/* ---- cross-validated scores -------------------------------------------------------------------------
+ * CrossValidationProperties (dataset/crossvalidation_adaptator.hpp:15-67): shuffles `indices` (the valid row
+ * ids, n of them) in place with std::shuffle(std::mt19937{seed}) and writes the k + 1 fold limits.  Host
+ * only, bit-exact with the reference (same libstdc++ routines).  PBN_ERR_ARG ("Cannot split ...") if
+ * k <= 1 or k > n. */
+int pbn_cv_split(int32_t* indices, int64_t n, int k, uint32_t seed, int32_t* limits);
+/* HoldOut (dataset/holdout_adaptator.hpp:17-70): shuffle, test_rows = round(n * test_ratio); the first
+ * *n_train shuffled ids are the training rows, the rest the test rows. */
+int pbn_holdout_split(int32_t* indices, int64_t n, double test_ratio, uint32_t seed, int32_t* n_train);
+
+/* Device side of dataset::CrossValidation (crossvalidation_adaptator.{hpp,cpp}) for the score classes:
+ * copies rows `indices[0..n)` of every column of `tbl` into a resident table in that (shuffled) order, so
+ * fold f is the contiguous row range [limits[f], limits[f+1]) and its training set is all other rows, and
+ * accumulates per-fold column sums and centred cross products of all columns (one pass).  A HoldOut is the
+ * k = 2 case scored on fold 1 only (train = fold 0). */
+int pbn_cv_create(pbn_ctx* ctx, const pbn_table* tbl, const int32_t* indices, int64_t n, const int32_t* limits,
+                  int k, pbn_cv** out);
+int pbn_cv_free(pbn_cv* cv);
+const pbn_table* pbn_cv_table(const pbn_cv* cv); /* the shuffled-order table (owned by cv) */
+int pbn_cv_folds(const pbn_cv* cv);
+/* mean and unbiased covariance of the training rows of `fold` for the columns `vars` (DataFrame::cov of the
+ * fold's training DataFrame, dataset/dataset.hpp:341-396), from the fold statistics. */
+int pbn_cv_train_moments(const pbn_cv* cv, int fold, const int* vars, int d, double* mean_out, double* cov_out);
+
+/* One candidate conditional distribution: vars[0] = variable, vars[1..n_vars) = evidence (column indices
+ * of the cv table), factor = PBN_FACTOR_*, rule = PBN_BW_* (CKDE only). */
+typedef struct pbn_cv_item {
+    int factor;
+    int rule;
+    int n_vars;
+    int vars[PBN_MAX_DIM];
+} pbn_cv_item;
+/* CVLikelihood::local_score (learning/scores/cv_likelihood.cpp:11-25) for every item at once:
+ * scores[i] = sum over folds f in [fold_begin, fold_end) of slogl_f(fit on the other rows; eval on fold f),
+ * accumulated in fold order.  All CKDE (item, fold) jobs with the same number of variables share ONE
+ * whitening launch and ONE pair-kernel launch.  status[i] (may be NULL) receives PBN_OK or the error code
+ * of item i (PBN_ERR_SINGULAR: SingularCovarianceData of some fold; its score is then meaningless);
+ * pbn_last_error() holds the message of the first failed item. */
+int pbn_cv_scores(pbn_ctx* ctx, pbn_cv* cv, const pbn_cv_item* items, int n_items, int fold_begin, int fold_end,
+                  double* scores, int* status);
+
+/* ---- host-side integer logic that must match libstdc++ bit for bit -----------------------------------
+ * ArcOperatorSet::find_max_indegree (learning/operators/operators.hpp:489-497): std::sort of the persistent
+ * candidate index vector by delta, descending (unstable: ties resolve as in the reference). */
+int pbn_sort_desc(int32_t* idx, int64_t n, const double* delta);
+/* std::unordered_set<int>, the container behind DNode::parents()/children() (graph/graph_types.hpp:12-51):
+ * BayesianNetwork::parents(node) lists parents in this container's iteration order. */
+int pbn_intset_new(pbn_intset** out);
+int pbn_intset_clone(const pbn_intset* s, pbn_intset** out);
+int pbn_intset_free(pbn_intset* s);
+int pbn_intset_insert(pbn_intset* s, int v);
+int pbn_intset_erase(pbn_intset* s, int v);
+int pbn_intset_clear(pbn_intset* s);
+int pbn_intset_contains(const pbn_intset* s, int v);
+int pbn_intset_size(const pbn_intset* s);
+int pbn_intset_list(const pbn_intset* s, int* out);
 
 /* Device scratch for callers that keep results on the GPU (e.g. bench.py). */
 int pbn_device_alloc(pbn_ctx* ctx, int64_t bytes, void** out);

@@ -29,6 +29,7 @@
 #include <limits>
 #include <numeric>
 #include <random>
+#include <unordered_set>
 #include <vector>
 #ifdef _OPENMP
 #include <omp.h>
@@ -805,6 +806,25 @@ int orc_cv_score(const void* X, int64_t n_rows, int d, int dtype, const int32_t*
                  int factor, int rule, double* out) {
     return dtype == 0 ? cv_score_T<double>(static_cast<const double*>(X), n_rows, d, indices, limits, k, factor, rule, out)
                       : cv_score_T<float>(static_cast<const float*>(X), n_rows, d, indices, limits, k, factor, rule, out);
+}
+
+// ---- containers whose libstdc++ behaviour the reference's hill climbing depends on ----------------
+// std::unordered_set<int> iteration order = order of BayesianNetwork::parents() (graph/graph_types.hpp:12-51)
+void* orc_uset_new() { return new std::unordered_set<int>(); }
+void* orc_uset_clone(const void* s) { return new std::unordered_set<int>(*static_cast<const std::unordered_set<int>*>(s)); }
+void orc_uset_free(void* s) { delete static_cast<std::unordered_set<int>*>(s); }
+void orc_uset_insert(void* s, int v) { static_cast<std::unordered_set<int>*>(s)->insert(v); }
+void orc_uset_erase(void* s, int v) { static_cast<std::unordered_set<int>*>(s)->erase(v); }
+int orc_uset_size(const void* s) { return static_cast<int>(static_cast<const std::unordered_set<int>*>(s)->size()); }
+void orc_uset_list(const void* s, int* out) {
+    int i = 0;
+    for (auto v : *static_cast<const std::unordered_set<int>*>(s)) out[i++] = v;
+}
+// ArcOperatorSet::find_max_indegree: std::sort(sorted_idx, delta desc) (learning/operators/operators.hpp:494)
+void orc_sort_desc(int* idx, int64_t n, const double* delta) {
+    std::vector<int> v(idx, idx + n);
+    std::sort(v.begin(), v.end(), [&delta](auto i1, auto i2) { return delta[i1] > delta[i2]; });
+    std::copy(v.begin(), v.end(), idx);
 }
 
 }  // extern "C"

@@ -5,8 +5,17 @@ Same class names as `pybnesian` for the path: KDE, CKDE, CKDEType, BandwidthSele
 NormalReferenceRule, ScottsBandwidth, SingularCovarianceData, ...
 """
 from ._lib import SingularCovarianceData, Context, default_context, LIB_PATH
-from .dataset import DataFrame
+from .dataset import DataFrame, CrossValidation, HoldOut
 from .kde import BandwidthSelector, NormalReferenceRule, ScottsBandwidth, UCV, UCVScorer, KDE
-from .factors import Factor, FactorType, CKDE, CKDEType
+from .factors import (Factor, FactorType, CKDE, CKDEType, LinearGaussianCPD, LinearGaussianCPDType,
+                      UnknownFactorType)
+from .models import (Dag, BayesianNetwork, BayesianNetworkType, GaussianNetwork, GaussianNetworkType, KDENetwork,
+                     KDENetworkType, SemiparametricBN, SemiparametricBNType)
+from .scores import (Args, Kwargs, Arguments, Score, ValidatedScore, CVLikelihood, HoldoutLikelihood,
+                     ValidatedLikelihood)
+from .operators import (Operator, ArcOperator, AddArc, RemoveArc, FlipArc, ChangeNodeType, OperatorTabuSet,
+                        LocalScoreCache, OperatorSet, ArcOperatorSet, ChangeNodeTypeSet, OperatorPool)
+from .hillclimbing import GreedyHillClimbing, Callback, hc
+from . import parallel
 
 __version__ = "0.1.0"

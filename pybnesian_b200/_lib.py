@@ -23,7 +23,13 @@ EXPORTS = [
     "pbn_kde_logl", "pbn_kde_logl_device", "pbn_ctx_last_fallback_rows", "pbn_device_alloc", "pbn_device_free",
     "pbn_device_read", "pbn_ctx_set_timing", "pbn_ctx_pair_kernel_time", "pbn_ucv_create", "pbn_ucv_free",
     "pbn_ucv_score", "pbn_ucv_pair_sums", "pbn_ucv_pairs", "pbn_ucv_bandwidth",
+    "pbn_lg_fit", "pbn_lg_logl", "pbn_cv_split", "pbn_holdout_split", "pbn_cv_create", "pbn_cv_free", "pbn_cv_table",
+    "pbn_cv_folds", "pbn_cv_train_moments", "pbn_cv_scores", "pbn_sort_desc", "pbn_intset_new", "pbn_intset_clone",
+    "pbn_intset_free", "pbn_intset_insert", "pbn_intset_erase", "pbn_intset_clear", "pbn_intset_contains",
+    "pbn_intset_size", "pbn_intset_list",
 ]
+PBN_MAX_DIM = 32
+FACTOR_CKDE, FACTOR_LINEAR_GAUSSIAN = 0, 1
 
 
 class SingularCovarianceData(ValueError):
@@ -36,6 +42,12 @@ class Rows(ctypes.Structure):
     @staticmethod
     def single(begin, end):
         return Rows(begin, end, 0, 0)
+
+
+class CVItem(ctypes.Structure):
+    """pbn_cv_item."""
+    _fields_ = [("factor", ctypes.c_int), ("rule", ctypes.c_int), ("n_vars", ctypes.c_int),
+                ("vars", ctypes.c_int * PBN_MAX_DIM)]
 
 
 _lib = None
@@ -96,10 +108,40 @@ def lib():
         L.pbn_ucv_pairs.argtypes = [vp]
         L.pbn_ucv_pairs.restype = i64
         L.pbn_ucv_bandwidth.argtypes = [vp, vp, ip, ci, Rows, ci, dp, ip]
+        i32p = ctypes.POINTER(ctypes.c_int32)
+        L.pbn_lg_fit.argtypes = [vp, vp, ip, ci, Rows, dp, dp]
+        L.pbn_lg_logl.argtypes = [vp, vp, ip, ci, Rows, dp, ctypes.c_double, dp, dp]
+        L.pbn_cv_split.argtypes = [i32p, i64, ci, ctypes.c_uint32, i32p]
+        L.pbn_holdout_split.argtypes = [i32p, i64, ctypes.c_double, ctypes.c_uint32, i32p]
+        L.pbn_cv_create.argtypes = [vp, vp, i32p, i64, i32p, ci, ctypes.POINTER(vp)]
+        L.pbn_cv_free.argtypes = [vp]
+        L.pbn_cv_table.argtypes = [vp]
+        L.pbn_cv_table.restype = vp
+        L.pbn_cv_folds.argtypes = [vp]
+        L.pbn_cv_train_moments.argtypes = [vp, ci, ip, ci, dp, dp]
+        L.pbn_cv_scores.argtypes = [vp, vp, ctypes.POINTER(CVItem), ci, ci, ci, dp, ip]
+        L.pbn_sort_desc.argtypes = [i32p, i64, dp]
+        L.pbn_intset_new.argtypes = [ctypes.POINTER(vp)]
+        L.pbn_intset_clone.argtypes = [vp, ctypes.POINTER(vp)]
+        L.pbn_intset_free.argtypes = [vp]
+        L.pbn_intset_insert.argtypes = [vp, ci]
+        L.pbn_intset_erase.argtypes = [vp, ci]
+        L.pbn_intset_clear.argtypes = [vp]
+        L.pbn_intset_contains.argtypes = [vp, ci]
+        L.pbn_intset_size.argtypes = [vp]
+        L.pbn_intset_list.argtypes = [vp, ip]
         L.pbn_ctx_set_timing.argtypes = [vp, ci]
         L.pbn_ctx_pair_kernel_time.argtypes = [vp, dp, ctypes.POINTER(i64), ctypes.POINTER(i64), ci]
         _lib = L
     return _lib
+
+
+def raise_for(rc, msg):
+    if rc == PBN_ERR_SINGULAR:
+        raise SingularCovarianceData(msg)
+    if rc in (PBN_ERR_ARG, PBN_ERR_UNSUPPORTED):
+        raise ValueError(msg)
+    raise RuntimeError(msg)
 
 
 def check(rc):

@@ -123,6 +123,10 @@ int moments_impl(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, pbn
 int whiten_raw_launch(pbn_ctx* ctx, const pbn_table* tbl, const int* cols_internal_order, int d, pbn_rows rows,
                       const double* Wfull, const double* mu, void* out, float* bound);
 
+// MLE<LinearGaussianCPD> from centred moments (cv.cu): Cm = sum (x_a - mean_a)(x_b - mean_b), column-major d x d,
+// variable first; writes beta[p + 1], returns the variance.
+double lg_fit_from_moments(int64_t rows, int p, const double* mean, const double* Cm, double* beta);
+
 namespace pbn {
 cudaError_t launch_pair_f64(int D, bool ckde, const PairJob* jobs, int n_jobs, long long total_units, long long upb,
                             int grid, const double* tab, cudaStream_t stream);

@@ -206,14 +206,149 @@ class DataFrame:
                 self._tables[key] = entry
         return entry, list(range(len(variables))), mask
 
+    def device_table_all(self, code, ctx=None):
+        """(DeviceTable, {column name: index}) holding EVERY column of dtype `code`, null slots filled with
+        NaN.  Used by the cross-validation scores, which address rows through an explicit index list
+        that already excludes the rows with nulls (crossvalidation_adaptator.hpp:24-37)."""
+        ctx = ctx or _lib.default_context()
+        if all(self._col(n).null_count == 0 for n in self.names if _DTYPE_CODE.get(self._col(n).type) == code):
+            tbl, _, _ = self.device_table([n for n in self.names if _DTYPE_CODE.get(self._col(n).type) == code][:1], ctx)
+            return tbl, dict(self._tables[("all", code, id(ctx))][1])
+        key = ("allnull", code, id(ctx))
+        entry = self._tables.get(key)
+        if entry is None:
+            names = [n for n in self.names if _DTYPE_CODE.get(self._col(n).type) == code]
+            cols = [np.asarray(self.column_numpy(n), dtype=_NP_DTYPE[code]) for n in names]
+            entry = (DeviceTable(ctx, cols, code), {n: i for i, n in enumerate(names)})
+            self._tables[key] = entry
+        return entry[0], dict(entry[1])
+
+    @property
+    def num_columns(self):
+        return len(self.names)
+
+    def column_name(self, col):
+        if isinstance(col, (int, np.integer)):
+            if col < 0 or col >= len(self.names):
+                raise IndexError("Column index " + str(col) + " do not exist in DataFrame.")
+            return self.names[int(col)]
+        return col
+
+    def valid_row_indices(self, include_null=False):
+        """Row ids with no null in ANY column (all rows if include_null), as int32."""
+        mask = None if include_null else self.combined_valid()
+        if mask is None:
+            return np.arange(self.num_rows, dtype=np.int32)
+        return np.flatnonzero(mask).astype(np.int32)
+
     def take(self, indices):
         indices = pa.array(np.asarray(indices, dtype=np.int32))
         return DataFrame(self.rb.take(indices))
 
     def loc(self, variables):
-        if isinstance(variables, str):
+        if isinstance(variables, (str, int, np.integer)):
             variables = [variables]
+        variables = [self.column_name(v) for v in variables]
         return DataFrame(pa.RecordBatch.from_arrays([self._col(v) for v in variables], names=list(variables)))
 
     def to_pandas(self):
         return self.rb.to_pandas()
+
+
+def _random_seed(seed):
+    """util::random_seed_arg: std::random_device when no seed is given."""
+    if seed is None:
+        import secrets
+        return secrets.randbits(32)
+    seed = int(seed)
+    if seed < 0 or seed > 0xFFFFFFFF:
+        raise TypeError("seed must be an unsigned 32-bit integer")
+    return seed
+
+
+def _i32p(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+
+
+class _CVProperties:
+    """dataset::CrossValidationProperties (crossvalidation_adaptator.hpp:15-67): shuffled valid-row
+    indices + fold limits, computed by libstdc++'s std::shuffle / std::mt19937 (pbn_cv_split)."""
+
+    def __init__(self, frame, k, seed, include_null):
+        k = int(k)
+        self.k = k
+        self.seed = seed
+        if k <= 1 or k > frame.num_rows:
+            raise ValueError("Cannot split %d instances into %d folds." % (frame.num_rows, k))
+        self.indices = np.ascontiguousarray(frame.valid_row_indices(include_null))
+        self.limits = np.empty(k + 1, dtype=np.int32)
+        check(lib().pbn_cv_split(_i32p(self.indices), self.indices.size, k, ctypes.c_uint32(seed), _i32p(self.limits)))
+
+
+class CrossValidation:
+    """pybnesian.CrossValidation (dataset/crossvalidation_adaptator.{hpp,cpp}, pybindings_dataset.cpp:13-113)."""
+
+    def __init__(self, df, k=10, seed=None, include_null=False, _prop=None):
+        self._frame = DataFrame.wrap(df)
+        self._prop = _prop if _prop is not None else _CVProperties(self._frame, k, _random_seed(seed), bool(include_null))
+
+    @property
+    def k(self):
+        return self._prop.k
+
+    def data(self):
+        return self._frame
+
+    def _fold_indices(self, fold):
+        p = self._prop
+        if fold < 0 or fold >= p.k:
+            raise IndexError("fold index out of range")
+        a, b = int(p.limits[fold]), int(p.limits[fold + 1])
+        train = np.concatenate([p.indices[:a], p.indices[b:int(p.limits[-1])]])
+        return train, p.indices[a:b]
+
+    def fold(self, index):
+        train, test = self._fold_indices(int(index))
+        return self._frame.take(train).rb, self._frame.take(test).rb
+
+    def __iter__(self):
+        for f in range(self._prop.k):
+            yield self.fold(f)
+
+    def indices(self):
+        for f in range(self._prop.k):
+            train, test = self._fold_indices(f)
+            yield train.tolist(), test.tolist()
+
+    def loc(self, columns):
+        return CrossValidation(self._frame.loc(columns), _prop=self._prop)
+
+
+class HoldOut:
+    """pybnesian.HoldOut (dataset/holdout_adaptator.{hpp,cpp}, pybindings_dataset.cpp:116-146)."""
+
+    def __init__(self, df, test_ratio=0.2, seed=None, include_null=False):
+        self._frame = DataFrame.wrap(df)
+        self.seed = _random_seed(seed)
+        test_ratio = float(test_ratio)
+        if test_ratio <= 0 or test_ratio >= 1.0:
+            raise ValueError("test_ratio must be a number between 0 and 1.")
+        idx = np.ascontiguousarray(self._frame.valid_row_indices(bool(include_null)))
+        ntr = ctypes.c_int32()
+        check(lib().pbn_holdout_split(_i32p(idx), idx.size, test_ratio, ctypes.c_uint32(self.seed), ctypes.byref(ntr)))
+        self.train_indices = idx[:ntr.value]
+        self.test_indices = idx[ntr.value:]
+        self._train = self._frame.take(self.train_indices)
+        self._test = self._frame.take(self.test_indices)
+
+    def training_data(self):
+        return self._train.rb
+
+    def test_data(self):
+        return self._test.rb
+
+    def training_frame(self):
+        return self._train
+
+    def test_frame(self):
+        return self._test

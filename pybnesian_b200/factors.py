@@ -73,6 +73,143 @@ class Factor:
             pickle.dump(self, f)
 
 
+class UnknownFactorType(FactorType):
+    """factors/factors.hpp:103-116: placeholder type of a node whose CPD type is not decided yet."""
+
+    def new_factor(self, model, variable, evidence, *args, **kwargs):
+        raise ValueError("UnknownFactorType cannot create a new Factor.")
+
+    def __str__(self):
+        return "UnknownFactorType"
+
+    __repr__ = __str__
+
+
+class LinearGaussianCPDType(FactorType):
+    """factors/continuous/LinearGaussianCPD.hpp:18-58."""
+
+    def new_factor(self, model, variable, evidence, *args, **kwargs):
+        return LinearGaussianCPD(variable, evidence, *args, **kwargs)
+
+    def __str__(self):
+        return "LinearGaussianFactor"
+
+    __repr__ = __str__
+
+
+class LinearGaussianCPD(Factor):
+    """pybnesian.LinearGaussianCPD (factors/continuous/LinearGaussianCPD.{hpp,cpp},
+    learning/parameters/mle_LinearGaussianCPD.hpp): y ~ N(beta0 + beta . evidence, variance)."""
+
+    def __init__(self, variable, evidence, beta=None, variance=None):
+        super().__init__(variable, evidence)
+        self._variables = [variable] + list(evidence)
+        self._fitted = False
+        self._beta = np.empty(0)
+        self._variance = -1.0
+        if beta is not None:
+            beta = np.asarray(beta, dtype=np.float64).ravel()
+            if beta.size != len(self._evidence) + 1:
+                raise ValueError("Wrong number of beta parameters. Beta vector size: %d. Expected beta vector size: %d."
+                                 % (beta.size, len(self._evidence) + 1))
+            if variance is None or variance <= 0:
+                raise ValueError("Variance must be a positive value.")
+            self._beta, self._variance, self._fitted = beta.copy(), float(variance), True
+
+    def type(self):
+        return LinearGaussianCPDType()
+
+    def fitted(self):
+        return self._fitted
+
+    def data_type(self):
+        import pyarrow as pa
+        return pa.float64()
+
+    @property
+    def beta(self):
+        return self._beta
+
+    @beta.setter
+    def beta(self, value):
+        value = np.asarray(value, dtype=np.float64).ravel()
+        if value.size != len(self._evidence) + 1:
+            raise ValueError("Wrong number of beta parameters.")
+        self._beta = value.copy()
+        if self._variance > 0:
+            self._fitted = True
+
+    @property
+    def variance(self):
+        return self._variance
+
+    @variance.setter
+    def variance(self, value):
+        if value <= 0:
+            raise ValueError("Variance must be a positive value.")
+        self._variance = float(value)
+        if self._beta.size == len(self._evidence) + 1:
+            self._fitted = True
+
+    def _check_fitted(self):
+        if not self._fitted:
+            raise ValueError("LinearGaussianCPD factor not fitted.")
+
+    def fit(self, df):
+        import ctypes
+        from ._lib import check, int_array
+        frame = DataFrame.wrap(df)
+        frame.dtype_code(self._variables, "fit LinearGaussianCPD")
+        tbl, cols, _ = frame.device_table(self._variables)
+        beta = np.empty(len(cols))
+        var = ctypes.c_double()
+        check(lib().pbn_lg_fit(tbl.ctx.handle, tbl.handle, int_array(cols), len(cols), tbl.rows(),
+                               beta.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), ctypes.byref(var)))
+        self._beta, self._variance, self._fitted = beta, var.value, True
+
+    def _eval(self, df, want_logl):
+        import ctypes
+        from ._lib import check, int_array
+        self._check_fitted()
+        frame = DataFrame.wrap(df)
+        frame.dtype_code(self._variables, "compute logl")
+        tbl, cols, mask = frame.device_table(self._variables)
+        out = np.empty(tbl.nrows) if want_logl else None
+        s = ctypes.c_double(0.0)
+        dp = ctypes.POINTER(ctypes.c_double)
+        check(lib().pbn_lg_logl(tbl.ctx.handle, tbl.handle, int_array(cols), len(cols), tbl.rows(),
+                                np.ascontiguousarray(self._beta).ctypes.data_as(dp), float(self._variance),
+                                out.ctypes.data_as(dp) if want_logl else None, None if want_logl else ctypes.byref(s)))
+        if want_logl and mask is not None:
+            full = np.full(frame.num_rows, np.nan)
+            full[mask] = out
+            out = full
+        return out, s.value
+
+    def logl(self, df):
+        return self._eval(df, True)[0]
+
+    def slogl(self, df):
+        return self._eval(df, False)[1]
+
+    def __getstate__(self):
+        return (self._variable, self._evidence, self._fitted, self._beta, self._variance)
+
+    def __setstate__(self, t):
+        self.__init__(t[0], t[1])
+        if t[2]:
+            self._beta, self._variance, self._fitted = np.asarray(t[3], dtype=np.float64), float(t[4]), True
+
+    def __str__(self):
+        if not self._fitted:
+            return "[LinearGaussianCPD] P(" + self._variable + (" | " + ", ".join(self._evidence) if self._evidence else "") + ") not fitted."
+        terms = "%.3f" % self._beta[0] + "".join(" + %.3f*%s" % (b, e) for b, e in zip(self._beta[1:], self._evidence))
+        return "[LinearGaussianCPD] P(" + self._variable + (" | " + ", ".join(self._evidence) if self._evidence else "") + \
+            ") = N(" + terms + ", %.3f)" % self._variance
+
+    __repr__ = __str__
+
+
 class CKDEType(FactorType):
     """factors/continuous/CKDE.hpp:17-60, CKDE.cpp:15-41 (discrete parents -> HCKDE is out of scope)."""
 

@@ -1,0 +1,666 @@
+"""Graph and Bayesian-network containers used by the score / hill-climbing path.
+
+Mirrors the slice of the reference that `estimate_hc` touches:
+graph/generic_graph.hpp (Dag: arcs, parents, can_add_arc / can_flip_arc / has_path),
+graph/graph_types.hpp:12-51 (DNode: parents and children are `std::unordered_set<int>`, whose
+iteration order fixes the order in which `parents(node)` lists the evidence of a CPD),
+models/BayesianNetwork.hpp (node types, clone, whitelists), models/SemiparametricBN.hpp:17-169,
+models/GaussianNetwork.hpp, models/KDENetwork.hpp.  The parent / children sets are REAL
+libstdc++ unordered_sets held behind the C ABI (pbn_intset_*), so the evidence order is the
+reference's, not an emulation of it.
+"""
+import ctypes
+import pickle
+
+import numpy as np
+import pyarrow as pa
+
+from ._lib import check, lib
+from .dataset import DataFrame
+from .factors import (CKDEType, FactorType, LinearGaussianCPDType, UnknownFactorType)
+
+
+class _IntSet:
+    """std::unordered_set<int> (pbn_intset)."""
+
+    __slots__ = ("h",)
+
+    def __init__(self, handle=None):
+        if handle is None:
+            handle = ctypes.c_void_p()
+            check(lib().pbn_intset_new(ctypes.byref(handle)))
+        self.h = handle
+
+    def clone(self):
+        h = ctypes.c_void_p()
+        check(lib().pbn_intset_clone(self.h, ctypes.byref(h)))
+        return _IntSet(h)
+
+    def insert(self, v):
+        lib().pbn_intset_insert(self.h, int(v))
+
+    def erase(self, v):
+        lib().pbn_intset_erase(self.h, int(v))
+
+    def __contains__(self, v):
+        return bool(lib().pbn_intset_contains(self.h, int(v)))
+
+    def __len__(self):
+        return lib().pbn_intset_size(self.h)
+
+    def list(self):
+        n = len(self)
+        if n == 0:
+            return []
+        out = (ctypes.c_int * n)()
+        check(lib().pbn_intset_list(self.h, out))
+        return list(out)
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().pbn_intset_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class Dag:
+    """graph::Dag over a fixed node list (graph/generic_graph.hpp:1185-1256, 2557-2740)."""
+
+    def __init__(self, nodes=None, arcs=None):
+        nodes = list(nodes or [])
+        if arcs and not nodes:
+            for s, t in arcs:
+                for n in (s, t):
+                    if n not in nodes:
+                        nodes.append(n)
+        if len(set(nodes)) != len(nodes):
+            raise ValueError("Graph cannot be created with repeated names.")
+        self._names = nodes
+        self._index = {n: i for i, n in enumerate(nodes)}
+        self._parents = [_IntSet() for _ in nodes]
+        self._children = [_IntSet() for _ in nodes]
+        self._arcs = set()
+        for s, t in (arcs or []):
+            self.add_arc(s, t)
+
+    # -- nodes ---------------------------------------------------------------------------
+    def nodes(self):
+        return list(self._names)
+
+    def num_nodes(self):
+        return len(self._names)
+
+    def contains_node(self, name):
+        return name in self._index
+
+    def index(self, name):
+        try:
+            return self._index[name]
+        except KeyError:
+            raise IndexError("Node " + str(name) + " not present in the graph.")
+
+    collapsed_index = index
+
+    def name(self, idx):
+        return self._names[idx]
+
+    collapsed_name = name
+
+    # -- arcs ----------------------------------------------------------------------------
+    def num_arcs(self):
+        return len(self._arcs)
+
+    def arcs(self):
+        return [(self._names[s], self._names[t]) for s, t in sorted(self._arcs)]
+
+    def has_arc(self, source, target):
+        return (self.index(source), self.index(target)) in self._arcs
+
+    def parents(self, node):
+        return [self._names[p] for p in self._parents[self.index(node)].list()]
+
+    def parent_indices(self, node):
+        return self._parents[self.index(node)].list()
+
+    def children(self, node):
+        return [self._names[c] for c in self._children[self.index(node)].list()]
+
+    def num_parents(self, node):
+        return len(self._parents[self.index(node)])
+
+    def num_children(self, node):
+        return len(self._children[self.index(node)])
+
+    def _add_arc_unsafe(self, s, t):
+        self._arcs.add((s, t))
+        self._parents[t].insert(s)
+        self._children[s].insert(t)
+
+    def _remove_arc_unsafe(self, s, t):
+        self._arcs.discard((s, t))
+        self._parents[t].erase(s)
+        self._children[s].erase(t)
+
+    def add_arc_unsafe(self, source, target):
+        self._add_arc_unsafe(self.index(source), self.index(target))
+
+    def add_arc(self, source, target):
+        s, t = self.index(source), self.index(target)
+        if (s, t) in self._arcs:
+            return
+        if not self._can_add(s, t):
+            raise ValueError("Cannot add arc " + source + " -> " + target + ".")
+        self._add_arc_unsafe(s, t)
+
+    def remove_arc(self, source, target):
+        s, t = self.index(source), self.index(target)
+        if (s, t) in self._arcs:
+            self._remove_arc_unsafe(s, t)
+
+    def flip_arc_unsafe(self, source, target):
+        s, t = self.index(source), self.index(target)
+        self._remove_arc_unsafe(s, t)
+        self._add_arc_unsafe(t, s)
+
+    def flip_arc(self, source, target):
+        s, t = self.index(source), self.index(target)
+        if not self._can_flip(s, t):
+            raise ValueError("Cannot flip arc " + source + " -> " + target + ".")
+        if (s, t) in self._arcs:
+            self._remove_arc_unsafe(s, t)
+            self._add_arc_unsafe(t, s)
+
+    # -- acyclicity (DirectedImpl::has_path_unsafe*, DagImpl::can_add/flip_arc_unsafe) --------------
+    def _has_path(self, s, t, skip_direct=False):
+        if not skip_direct and (s, t) in self._arcs:
+            return True
+        seen = {s}
+        stack = []
+        for ch in self._children[s].list():
+            if skip_direct and ch == t:
+                continue
+            stack.append(ch)
+            seen.add(ch)
+        while stack:
+            v = stack.pop()
+            ch = self._children[v]
+            if t in ch:
+                return True
+            for c in ch.list():
+                if c not in seen:
+                    seen.add(c)
+                    stack.append(c)
+        return False
+
+    def has_path(self, source, target):
+        return self._has_path(self.index(source), self.index(target))
+
+    def _can_add(self, s, t):
+        return s != t and (len(self._parents[s]) == 0 or len(self._children[t]) == 0 or not self._has_path(t, s))
+
+    def _can_flip(self, s, t):
+        if s == t:
+            return False
+        if (s, t) in self._arcs:
+            if len(self._parents[t]) == 1 or len(self._children[s]) == 1:
+                return True
+            return not self._has_path(s, t, skip_direct=True)
+        if len(self._parents[t]) == 0 or len(self._children[s]) == 0:
+            return True
+        return not self._has_path(s, t)
+
+    def can_add_arc(self, source, target):
+        return self._can_add(self.index(source), self.index(target))
+
+    def can_flip_arc(self, source, target):
+        return self._can_flip(self.index(source), self.index(target))
+
+    def topological_sort(self):
+        indeg = [len(p) for p in self._parents]
+        stack = [i for i, d in enumerate(indeg) if d == 0]
+        order = []
+        while stack:
+            i = stack.pop()
+            order.append(self._names[i])
+            for ch in self._children[i].list():
+                indeg[ch] -= 1
+                if indeg[ch] == 0:
+                    stack.append(ch)
+        if len(order) != len(self._names):
+            raise ValueError("Graph must be a DAG to obtain a topological sort.")
+        return order
+
+    def clone(self):
+        g = Dag.__new__(Dag)
+        g._names = list(self._names)
+        g._index = dict(self._index)
+        g._parents = [p.clone() for p in self._parents]  # unordered_set copy keeps the iteration order
+        g._children = [c.clone() for c in self._children]
+        g._arcs = set(self._arcs)
+        return g
+
+    def __getstate__(self):
+        return (self._names, self.arcs())
+
+    def __setstate__(self, t):
+        self.__init__(t[0], t[1])
+
+
+# ----------------------------------------------------------------------------------------------
+# Bayesian network types (models/BayesianNetwork.hpp:170-260 BayesianNetworkType)
+# ----------------------------------------------------------------------------------------------
+class BayesianNetworkType:
+    _instances = {}
+
+    def __new__(cls, *a, **k):
+        inst = BayesianNetworkType._instances.get(cls)
+        if inst is None:
+            inst = super().__new__(cls)
+            BayesianNetworkType._instances[cls] = inst
+        return inst
+
+    def is_homogeneous(self):
+        raise NotImplementedError
+
+    def default_node_type(self):
+        raise NotImplementedError
+
+    def data_default_node_type(self, datatype):
+        return []
+
+    def compatible_node_type(self, model, variable, node_type):
+        return True
+
+    def can_have_arc(self, model, source, target):
+        return True
+
+    def alternative_node_type(self, model, variable):
+        return []
+
+    def new_bn(self, nodes):
+        raise NotImplementedError
+
+    def __eq__(self, other):
+        return type(self) is type(other)
+
+    def __hash__(self):
+        return hash(type(self).__name__)
+
+    def __str__(self):
+        return type(self).__name__
+
+    __repr__ = __str__
+
+    def __reduce__(self):
+        return (type(self), ())
+
+
+class GaussianNetworkType(BayesianNetworkType):
+    """models/GaussianNetwork.hpp."""
+
+    def is_homogeneous(self):
+        return True
+
+    def default_node_type(self):
+        return LinearGaussianCPDType()
+
+    def new_bn(self, nodes):
+        return GaussianNetwork(nodes)
+
+    def __str__(self):
+        return "GaussianNetworkType"
+
+    __repr__ = __str__
+
+
+class KDENetworkType(BayesianNetworkType):
+    """models/KDENetwork.hpp."""
+
+    def is_homogeneous(self):
+        return True
+
+    def default_node_type(self):
+        return CKDEType()
+
+    def new_bn(self, nodes):
+        return KDENetwork(nodes)
+
+    def __str__(self):
+        return "KDENetworkType"
+
+    __repr__ = __str__
+
+
+def _is_continuous(datatype):
+    return datatype in (pa.float64(), pa.float32())
+
+
+class SemiparametricBNType(BayesianNetworkType):
+    """models/SemiparametricBN.hpp:17-136 (discrete nodes are SURVEY §8 row f1: not on this path)."""
+
+    def is_homogeneous(self):
+        return False
+
+    def default_node_type(self):
+        raise RuntimeError("default_node_type() for SemiparametricBN is not defined.")
+
+    def data_default_node_type(self, datatype):
+        if _is_continuous(datatype):
+            return [LinearGaussianCPDType(), CKDEType()]
+        raise ValueError("Data type [" + str(datatype) + "] not compatible with SemiparametricBNType")
+
+    def compatible_node_type(self, model, variable, node_type):
+        return node_type == LinearGaussianCPDType() or node_type == CKDEType()
+
+    def can_have_arc(self, model, source, target):
+        return True  # only discrete targets restrict their parents (SemiparametricBN.hpp:96-101)
+
+    def alternative_node_type(self, model, variable):
+        t = model.node_type(variable)
+        if t == LinearGaussianCPDType():
+            return [CKDEType()]
+        if t == CKDEType():
+            return [LinearGaussianCPDType()]
+        return []
+
+    def new_bn(self, nodes):
+        return SemiparametricBN(nodes)
+
+    def __str__(self):
+        return "SemiparametricNetworkType"
+
+    __repr__ = __str__
+
+
+# ----------------------------------------------------------------------------------------------
+# BayesianNetwork (models/BayesianNetwork.hpp:262-1000, unconditional networks only)
+# ----------------------------------------------------------------------------------------------
+class BayesianNetwork:
+    def __init__(self, bn_type, nodes=None, arcs=None, node_types=None, graph=None):
+        self._type = bn_type
+        if isinstance(nodes, Dag):
+            graph, nodes = nodes, None
+        if graph is not None:
+            self._g = graph.clone()
+        else:
+            nodes = list(nodes) if nodes is not None else None
+            # a list of 2-tuples in the first position is an arc list (BNGeneric(type, arcs))
+            if nodes and arcs is None and all(isinstance(n, tuple) and len(n) == 2 for n in nodes) \
+                    and not all(isinstance(n[1], FactorType) for n in nodes):
+                arcs, nodes = nodes, None
+            self._g = Dag(nodes, arcs)
+        n = self._g.num_nodes()
+        self._cpds = []
+        if bn_type.is_homogeneous():
+            self._node_types = []
+            if node_types:
+                raise ValueError("node types cannot be set on a homogeneous Bayesian network")
+        else:
+            self._node_types = [UnknownFactorType() for _ in range(n)]
+            for name, t in (node_types or []):
+                self.set_node_type(name, t)
+
+    # -- graph delegation ----------------------------------------------------------------------
+    def graph(self):
+        return self._g
+
+    def type(self):
+        return self._type
+
+    def nodes(self):
+        return self._g.nodes()
+
+    def num_nodes(self):
+        return self._g.num_nodes()
+
+    def num_arcs(self):
+        return self._g.num_arcs()
+
+    def arcs(self):
+        return self._g.arcs()
+
+    def contains_node(self, name):
+        return self._g.contains_node(name)
+
+    def index(self, node):
+        return self._g.index(node)
+
+    def collapsed_index(self, node):
+        return self._g.index(node)
+
+    def collapsed_name(self, idx):
+        return self._g.name(idx)
+
+    def name(self, idx):
+        return self._g.name(idx)
+
+    def parents(self, node):
+        return self._g.parents(node)
+
+    def children(self, node):
+        return self._g.children(node)
+
+    def num_parents(self, node):
+        return self._g.num_parents(node)
+
+    def num_children(self, node):
+        return self._g.num_children(node)
+
+    def has_arc(self, source, target):
+        return self._g.has_arc(source, target)
+
+    def has_path(self, source, target):
+        return self._g.has_path(source, target)
+
+    def can_add_arc(self, source, target):
+        return self._g.can_add_arc(source, target) and self._type.can_have_arc(self, source, target)
+
+    def can_flip_arc(self, source, target):
+        return self._g.can_flip_arc(source, target) and self._type.can_have_arc(self, target, source)
+
+    def add_arc(self, source, target):
+        if self.can_add_arc(source, target):
+            self._g.add_arc_unsafe(source, target)
+        elif not self.has_arc(source, target):
+            raise ValueError("Cannot add arc " + source + " -> " + target + ".")
+
+    def add_arc_unsafe(self, source, target):
+        self._g.add_arc_unsafe(source, target)
+
+    def remove_arc(self, source, target):
+        self._g.remove_arc(source, target)
+
+    def flip_arc(self, source, target):
+        if self.can_flip_arc(source, target):
+            self._g.flip_arc_unsafe(source, target)
+        else:
+            raise ValueError("Cannot flip arc " + source + " -> " + target + ".")
+
+    def flip_arc_unsafe(self, source, target):
+        self._g.flip_arc_unsafe(source, target)
+
+    def check_blacklist(self, arc_blacklist):
+        for s, t in arc_blacklist:
+            if self.has_arc(s, t):
+                raise ValueError("Arc " + s + " -> " + t + " in blacklist, but it is present in the Bayesian Network.")
+
+    def force_whitelist(self, arc_whitelist):
+        for s, t in arc_whitelist:
+            if not self.has_arc(s, t):
+                if self.has_arc(t, s):
+                    raise ValueError("Arc " + s + " -> " + t + " in whitelist, but arc " + t + " -> " + s +
+                                     " is present in the Bayesian Network.")
+                elif self.can_add_arc(s, t):
+                    self.add_arc_unsafe(s, t)
+                else:
+                    raise ValueError("Arc " + s + " -> " + t + " not allowed in this Bayesian network.")
+        self._g.topological_sort()
+
+    # -- node types (BayesianNetwork.hpp:640-800) ------------------------------------------------------
+    def node_type(self, node):
+        if self._type.is_homogeneous():
+            return self._type.default_node_type()
+        return self._node_types[self.index(node)]
+
+    def node_types(self):
+        return {n: self.node_type(n) for n in self.nodes()}
+
+    def underlying_node_type(self, df, node):
+        if self._type.is_homogeneous():
+            return self._type.default_node_type()
+        t = self._node_types[self.index(node)]
+        if t != UnknownFactorType():
+            return t
+        frame = DataFrame.wrap(df)
+        nt = self._type.data_default_node_type(frame._col(node).type)
+        if not nt:
+            raise ValueError("There is no underlying FactorType for node " + node)
+        return nt[0]
+
+    def _wrong_type(self, node, t):
+        return ValueError("Wrong factor type \"" + str(t) + "\" for node \"" + node + "\" in Bayesian network type \"" +
+                          str(self._type) + "\".")
+
+    def set_node_type(self, node, new_type):
+        if self._type.is_homogeneous():
+            if new_type != self._type.default_node_type():
+                raise self._wrong_type(node, new_type)
+            return
+        if new_type != UnknownFactorType() and not self._type.compatible_node_type(self, node, new_type):
+            raise self._wrong_type(node, new_type)
+        i = self.index(node)
+        self._node_types[i] = new_type
+        if self._cpds and self._cpds[i] is not None and self._cpds[i].type() != new_type:
+            self._cpds[i] = None
+
+    def has_unknown_node_types(self):
+        if self._type.is_homogeneous():
+            return False
+        return any(t == UnknownFactorType() for t in self._node_types)
+
+    def set_unknown_node_types(self, df, type_blacklist=()):
+        if self._type.is_homogeneous():
+            return
+        frame = DataFrame.wrap(df)
+        black = set((n, t) for n, t in type_blacklist)
+        new_types = []
+        for nn in self.nodes():
+            if self.node_type(nn) == UnknownFactorType():
+                for t in self._type.data_default_node_type(frame._col(nn).type):
+                    if (nn, t) not in black:
+                        new_types.append((nn, t))
+                        break
+                else:
+                    raise ValueError("A valid FactorType for node " + nn + " could not be inferred.")
+        self.force_type_whitelist(new_types)
+
+    def force_type_whitelist(self, type_whitelist):
+        if self._type.is_homogeneous():
+            for n, t in type_whitelist:
+                if t != self._type.default_node_type():
+                    raise self._wrong_type(n, t)
+            return
+        old = []
+        for n, t in type_whitelist:
+            i = self.index(n)
+            old.append((i, self._node_types[i]))
+            self._node_types[i] = t
+        for n, t in type_whitelist:
+            if t != UnknownFactorType() and not self._type.compatible_node_type(self, n, t):
+                for i, o in old:
+                    self._node_types[i] = o
+                raise self._wrong_type(n, t)
+        if self._cpds:
+            for n, _ in type_whitelist:
+                i = self.index(n)
+                if self._cpds[i] is not None and self._cpds[i].type() != self._node_types[i]:
+                    self._cpds[i] = None
+
+    # -- CPDs --------------------------------------------------------------------------------
+    def fitted(self):
+        return bool(self._cpds) and all(c is not None and c.fitted() for c in self._cpds)
+
+    def cpd(self, node):
+        i = self.index(node)
+        if not self._cpds or self._cpds[i] is None:
+            raise ValueError("CPD of variable " + node + " not added. Call add_cpds() or fit() to add the CPD.")
+        return self._cpds[i]
+
+    def fit(self, df, construction_args=None):
+        frame = DataFrame.wrap(df)
+        if not self._cpds:
+            self._cpds = [None] * self.num_nodes()
+        for node in self.nodes():
+            i = self.index(node)
+            t = self.underlying_node_type(frame, node)
+            parents = self.parents(node)
+            cur = self._cpds[i]
+            if cur is None or cur.type() != t or cur.evidence() != parents:
+                args, kwargs = construction_args.args(node, t) if construction_args is not None else ((), {})
+                cur = t.new_factor(self, node, parents, *args, **kwargs)
+                self._cpds[i] = cur
+            if not cur.fitted():
+                cur.fit(frame)
+
+    def logl(self, df):
+        frame = DataFrame.wrap(df)
+        total = np.zeros(frame.num_rows)
+        for node in self.nodes():
+            total = total + self.cpd(node).logl(frame)
+        return total
+
+    def slogl(self, df):
+        frame = DataFrame.wrap(df)
+        return float(sum(self.cpd(node).slogl(frame) for node in self.nodes()))
+
+    def clone(self):
+        m = type(self).__new__(type(self))
+        m._type = self._type
+        m._g = self._g.clone()
+        m._node_types = list(self._node_types)
+        m._cpds = list(self._cpds)
+        return m
+
+    def save(self, filename, include_cpd=False):
+        if not filename.endswith(".pickle"):
+            filename += ".pickle"
+        with open(filename, "wb") as f:
+            pickle.dump(self, f)
+
+    def __getstate__(self):
+        return (self._type, self._g.nodes(), self._g.arcs(), list(self._node_types))
+
+    def __setstate__(self, t):
+        self._type = t[0]
+        self._g = Dag(t[1], t[2])
+        self._node_types = list(t[3])
+        self._cpds = []
+
+    def __str__(self):
+        return type(self).__name__ + " with %d nodes and %d arcs" % (self.num_nodes(), self.num_arcs())
+
+    __repr__ = __str__
+
+
+class GaussianNetwork(BayesianNetwork):
+    def __init__(self, nodes=None, arcs=None, graph=None):
+        super().__init__(GaussianNetworkType(), nodes, arcs, None, graph)
+
+
+class KDENetwork(BayesianNetwork):
+    def __init__(self, nodes=None, arcs=None, graph=None):
+        super().__init__(KDENetworkType(), nodes, arcs, None, graph)
+
+
+class SemiparametricBN(BayesianNetwork):
+    """pybnesian.SemiparametricBN (models/SemiparametricBN.hpp:138-169): ctor forms (nodes), (arcs),
+    (nodes, arcs), (graph), each optionally followed by node_types = [(name, FactorType), ...]."""
+
+    def __init__(self, nodes=None, arcs=None, node_types=None, graph=None):
+        # (nodes, node_types) and (arcs, node_types): the second positional is a FactorType list
+        if arcs is not None and node_types is None and len(arcs) > 0 and \
+                all(isinstance(a, tuple) and len(a) == 2 and isinstance(a[1], FactorType) for a in arcs):
+            arcs, node_types = None, arcs
+        super().__init__(SemiparametricBNType(), nodes, arcs, node_types, graph)
