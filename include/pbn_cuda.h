@@ -147,6 +147,8 @@ int pbn_ucv_score(pbn_ucv* scorer, const double* H_or_hdiag, int is_diag, double
  * slices of the tile schedule: the multi-GPU split (each rank one slice, sums all-reduced). */
 int pbn_ucv_pair_sums(pbn_ucv* scorer, const double* H_or_hdiag, int is_diag, int part, int nparts, double* S2,
                       double* S1);
+/* The score from pair sums that were added over all slices (the scalar epilogue of kde/UCV.cpp:296-304, 357). */
+int pbn_ucv_score_from_sums(pbn_ucv* scorer, const double* H_or_hdiag, int is_diag, double S2, double S1, double* out);
 int64_t pbn_ucv_pairs(const pbn_ucv* scorer);
 /* UCV::bandwidth / UCV::diag_bandwidth (kde/UCV.cpp:452-525): Nelder-Mead over vech(chol(H))
  * (or sqrt of the diagonal) from the normal-reference start, ftol_rel = xtol_rel = 1e-4, with the

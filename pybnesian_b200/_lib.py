@@ -23,7 +23,7 @@ EXPORTS = [
     "pbn_kde_logl", "pbn_kde_logl_device", "pbn_ctx_last_fallback_rows", "pbn_device_alloc", "pbn_device_free",
     "pbn_device_read", "pbn_ctx_set_timing", "pbn_ctx_pair_kernel_time", "pbn_ucv_create", "pbn_ucv_free",
     "pbn_ucv_score", "pbn_ucv_pair_sums", "pbn_ucv_pairs", "pbn_ucv_bandwidth",
-    "pbn_lg_fit", "pbn_lg_logl", "pbn_cv_split", "pbn_holdout_split", "pbn_cv_create", "pbn_cv_free", "pbn_cv_table",
+    "pbn_ucv_score_from_sums", "pbn_lg_fit", "pbn_lg_logl", "pbn_cv_split", "pbn_holdout_split", "pbn_cv_create", "pbn_cv_free", "pbn_cv_table",
     "pbn_cv_folds", "pbn_cv_train_moments", "pbn_cv_scores", "pbn_sort_desc", "pbn_intset_new", "pbn_intset_clone",
     "pbn_intset_free", "pbn_intset_insert", "pbn_intset_erase", "pbn_intset_clear", "pbn_intset_contains",
     "pbn_intset_size", "pbn_intset_list",
@@ -105,6 +105,7 @@ def lib():
         L.pbn_ucv_free.argtypes = [vp]
         L.pbn_ucv_score.argtypes = [vp, dp, ci, dp]
         L.pbn_ucv_pair_sums.argtypes = [vp, dp, ci, ci, ci, dp, dp]
+        L.pbn_ucv_score_from_sums.argtypes = [vp, dp, ci, ctypes.c_double, ctypes.c_double, dp]
         L.pbn_ucv_pairs.argtypes = [vp]
         L.pbn_ucv_pairs.restype = i64
         L.pbn_ucv_bandwidth.argtypes = [vp, vp, ip, ci, Rows, ci, dp, ip]

@@ -96,21 +96,28 @@ static double ucv_combine(const pbn_ucv* s, const double* Lchol, double S2, doub
     return exp(c2) + 2.0 * exp(c2) * S2 / N - 4.0 * exp(c1) * S1 / (N - 1.0);
 }
 
-static int ucv_score_full(pbn_ucv* s, const double* H, int is_diag, double* out) {
+// Cholesky factor used by a score call: diag(sqrt(h)) or chol(H), H cast to the data type first
+// (UCV.cpp:388-392 casts the bandwidth to the data type)
+static int ucv_factor(const pbn_ucv* s, const double* H, int is_diag, std::vector<double>& L) {
     const int d = s->d;
-    std::vector<double> L(d * d, 0.0);
+    L.assign(d * d, 0.0);
     if (is_diag) {
         for (int i = 0; i < d; ++i) {
             if (!(H[i] > 0)) return set_error(PBN_ERR_SINGULAR, "diagonal bandwidth must be positive");
             L[i + i * d] = sqrt(H[i]);
         }
-    } else {
-        std::vector<double> Hc(H, H + d * d);
-        if (s->dtype == PBN_F32)
-            for (auto& v : Hc) v = (double)(float)v;  // UCV.cpp:388-392 casts the bandwidth to the data type
-        if (!chol_lower(Hc.data(), d, L.data()))
-            return set_error(PBN_ERR_SINGULAR, "bandwidth matrix is not positive definite");
+        return PBN_OK;
     }
+    std::vector<double> Hc(H, H + d * d);
+    if (s->dtype == PBN_F32)
+        for (auto& v : Hc) v = (double)(float)v;
+    if (!chol_lower(Hc.data(), d, L.data())) return set_error(PBN_ERR_SINGULAR, "bandwidth matrix is not positive definite");
+    return PBN_OK;
+}
+
+static int ucv_score_full(pbn_ucv* s, const double* H, int is_diag, double* out) {
+    std::vector<double> L;
+    PBN_TRY(ucv_factor(s, H, is_diag, L));
     double S2, S1;
     PBN_TRY(ucv_sums(s, L.data(), 0, 1, &S2, &S1));
     *out = ucv_combine(s, L.data(), S2, S1);
@@ -302,14 +309,17 @@ int pbn_ucv_pair_sums(pbn_ucv* s, const double* H_or_hdiag, int is_diag, int par
     if (!s || !H_or_hdiag || !S2 || !S1 || nparts < 1 || part < 0 || part >= nparts)
         return set_error(PBN_ERR_ARG, "invalid argument");
     DevSetter ds(s->ctx->device);
-    const int d = s->d;
-    std::vector<double> L(d * d, 0.0);
-    if (is_diag) {
-        for (int i = 0; i < d; ++i) L[i + i * d] = sqrt(H_or_hdiag[i]);
-    } else if (!chol_lower(H_or_hdiag, d, L.data())) {
-        return set_error(PBN_ERR_SINGULAR, "bandwidth matrix is not positive definite");
-    }
+    std::vector<double> L;
+    PBN_TRY(ucv_factor(s, H_or_hdiag, is_diag, L));
     return ucv_sums(s, L.data(), part, nparts, S2, S1);
+}
+
+int pbn_ucv_score_from_sums(pbn_ucv* s, const double* H_or_hdiag, int is_diag, double S2, double S1, double* out) {
+    if (!s || !H_or_hdiag || !out) return set_error(PBN_ERR_ARG, "invalid argument");
+    std::vector<double> L;
+    PBN_TRY(ucv_factor(s, H_or_hdiag, is_diag, L));
+    *out = ucv_combine(s, L.data(), S2, S1);
+    return PBN_OK;
 }
 
 int64_t pbn_ucv_pairs(const pbn_ucv* s) { return s ? s->n * (s->n - 1) / 2 : 0; }

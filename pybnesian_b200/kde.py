@@ -121,18 +121,27 @@ class UCVScorer:
         d = len(self._variables)
         if h.size != d:
             raise ValueError("Wrong dimension for bandwidth vector. it should be a %d vector." % d)
-        out = ctypes.c_double()
-        check(lib().pbn_ucv_score(self._handle, _dp(h), 1, ctypes.byref(out)))
-        return out.value
+        return self._score(h, 1)
 
     def score_unconstrained(self, bandwidth):
         d = len(self._variables)
         H = np.asarray(bandwidth, dtype=np.float64)
         if H.shape != (d, d):
             raise ValueError("Wrong dimension for bandwidth matrix. it should be a %dx%d matrix." % (d, d))
-        H = np.asfortranarray(H)
+        return self._score(np.asfortranarray(H), 0)
+
+    def _score(self, H, is_diag):
+        from . import parallel
         out = ctypes.c_double()
-        check(lib().pbn_ucv_score(self._handle, _dp(H), 0, ctypes.byref(out)))
+        if parallel.active():
+            # each rank sums its slice of the pair-tile schedule; 2 doubles are all-reduced
+            s2, s1 = ctypes.c_double(), ctypes.c_double()
+            check(lib().pbn_ucv_pair_sums(self._handle, _dp(H), is_diag, parallel.rank(), parallel.world_size(),
+                                          ctypes.byref(s2), ctypes.byref(s1)))
+            tot = parallel.all_reduce_sum(np.array([s2.value, s1.value]), self._tbl.ctx)
+            check(lib().pbn_ucv_score_from_sums(self._handle, _dp(H), is_diag, float(tot[0]), float(tot[1]), ctypes.byref(out)))
+        else:
+            check(lib().pbn_ucv_score(self._handle, _dp(H), is_diag, ctypes.byref(out)))
         return out.value
 
     def pair_sums(self, bandwidth, part=0, nparts=1, diagonal=False):
@@ -220,18 +229,32 @@ def _fit_handle(tbl, cols, rows, H, ckde=False):
 
 
 def _run_logl(fitted, frame, variables, want_logl, want_slogl):
-    """Shared by KDE and CKDE: returns (logl over all rows with NaN at null rows, slogl)."""
+    """Shared by KDE and CKDE: returns (logl over all rows with NaN at null rows, slogl).
+
+    With several ranks (pybnesian_b200.parallel) every rank holds the same frame and evaluates a contiguous
+    shard of its test rows against the replicated training set; slogl is a 1-double all-reduce, logl a
+    zero-padded vector all-reduce (each element written by exactly one rank)."""
+    from . import parallel
     tbl, cols, mask = frame.device_table(variables)
     m = tbl.nrows
-    out = np.empty(m) if want_logl else None
+    b, e = parallel.shard_range(m) if parallel.active() else (0, m)
+    out = np.zeros(m) if want_logl else None
     s = ctypes.c_double(0.0)
-    check(lib().pbn_kde_logl(tbl.ctx.handle, fitted.handle, tbl.handle, int_array(cols), tbl.rows(),
-                             _dp(out) if want_logl else None, ctypes.byref(s) if want_slogl else None))
+    if e > b or not parallel.active():
+        shard = out[b:e] if want_logl else None
+        check(lib().pbn_kde_logl(tbl.ctx.handle, fitted.handle, tbl.handle, int_array(cols), tbl.rows(b, e),
+                                 _dp(shard) if want_logl else None, ctypes.byref(s) if want_slogl else None))
+    total = s.value
+    if parallel.active():
+        if want_slogl:
+            total = float(parallel.all_reduce_sum(np.array([s.value]), tbl.ctx)[0])
+        if want_logl:
+            out = parallel.all_reduce_sum(out, tbl.ctx)
     if want_logl and mask is not None:
         full = np.full(frame.num_rows, np.nan)
         full[mask] = out
         out = full
-    return out, s.value
+    return out, total
 
 
 class KDE:

@@ -67,6 +67,15 @@ def all_reduce_sum(values, ctx=None):
     return t.numpy()
 
 
+def deal(costs, r=None, w=None):
+    """Indices of the work items owned by rank r of w: items are sorted by decreasing cost (ties by index)
+    and dealt round-robin, so every rank gets a similar load and every item exactly one owner."""
+    r = rank() if r is None else r
+    w = world_size() if w is None else w
+    order = sorted(range(len(costs)), key=lambda i: (-costs[i], i))
+    return [i for pos, i in enumerate(order) if pos % w == r]
+
+
 def shard_range(n, r=None, w=None):
     """Contiguous slice [begin, end) of n items owned by rank r of w (first n % w ranks get one more)."""
     r = rank() if r is None else r

@@ -246,33 +246,38 @@ class _FoldScorer:
         return out
 
     def _score_native(self, code, items):
-        handle, index = self._device(code)
-        ctx = handle.tbl.ctx
         rank, world = parallel.rank(), parallel.world_size()
-        # deal the items over the ranks, most expensive first (CKDE cost grows with the family size)
-        cost = [(-(len(v) if f == _lib.FACTOR_CKDE else 0), i) for i, (_, f, _, v) in enumerate(items)]
-        mine = [i for pos, (_, i) in enumerate(sorted(cost)) if pos % world == rank] if world > 1 else list(range(len(items)))
+        # deal the items over the ranks, most expensive first (CKDE cost grows with the family size; LG is free)
+        cost = [len(v) if f == _lib.FACTOR_CKDE else 0 for _, f, _, v in items]
+        mine = parallel.deal(cost, rank, world) if world > 1 else list(range(len(items)))
         scores = np.zeros(len(items))
         if mine:
-            arr = (CVItem * len(mine))()
-            for slot, i in enumerate(mine):
-                _, factor, rule, variables = items[i]
-                arr[slot].factor, arr[slot].rule, arr[slot].n_vars = factor, rule, len(variables)
-                for q, v in enumerate(variables):
-                    arr[slot].vars[q] = index[v]
-            local = np.zeros(len(mine))
-            status = (ctypes.c_int * len(mine))()
-            check(lib().pbn_cv_scores(ctx.handle, handle.h, arr, len(mine), self.fold_begin, self.fold_end,
-                                      local.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), status))
-            bad = [s for s in status if s != _lib.PBN_OK]
-            if bad:
-                _lib.raise_for(bad[0], lib().pbn_last_error().decode("utf-8", "replace"))
-            scores[mine] = local
+            scores[mine] = self._run_items(code, [items[i] for i in mine])
             self.stats["device_items"] += len(mine)
             self.stats["batches"] += 1
         if world > 1:
-            scores = parallel.all_reduce_sum(scores, ctx)
+            scores = parallel.all_reduce_sum(scores, self._ctx(code))
         return {items[i][0]: float(scores[i]) for i in range(len(items))}
+
+    def _ctx(self, code):
+        return self._device(code)[0].tbl.ctx
+
+    def _run_items(self, code, items):
+        """One pbn_cv_scores call for `items` = [(key, factor, rule, variables)]; returns their scores."""
+        handle, index = self._device(code)
+        arr = (CVItem * len(items))()
+        for slot, (_, factor, rule, variables) in enumerate(items):
+            arr[slot].factor, arr[slot].rule, arr[slot].n_vars = factor, rule, len(variables)
+            for q, v in enumerate(variables):
+                arr[slot].vars[q] = index[v]
+        local = np.zeros(len(items))
+        status = (ctypes.c_int * len(items))()
+        check(lib().pbn_cv_scores(handle.tbl.ctx.handle, handle.h, arr, len(items), self.fold_begin, self.fold_end,
+                                  local.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), status))
+        bad = [s for s in status if s != _lib.PBN_OK]
+        if bad:
+            _lib.raise_for(bad[0], lib().pbn_last_error().decode("utf-8", "replace"))
+        return local
 
 
 class CVLikelihood(Score):

@@ -285,3 +285,19 @@ def test_hc_convenience_function(pbn):
     assert v.num_arcs() >= 1
     with pytest.raises(ValueError):
         pbn.hc(data)
+
+
+def test_multi_gpu_shards_match_single_gpu():
+    """Needs >= 2 GPUs (run with `gpurun --gpus 2`): test-row shards, dealt score batches, UCV tile slices and the
+    replicated hill climbing give the single-GPU results (tools/multi_gpu_check.py under torchrun)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29517", os.path.join(root, "tools", "multi_gpu_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "MULTI_GPU_CHECK_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
