@@ -180,8 +180,12 @@ def main():
     os.environ["PBN_CUDA_DEVICE"] = str(local_rank)
 
     import pybnesian_b200 as pbn
-    from pybnesian_b200 import _lib
+    from pybnesian_b200 import _lib, parallel
     import ctypes
+
+    # weak scaling: every rank owns ITS OWN 1M test rows (a different seed per rank) and calls the
+    # single-GPU entry points on them; the API-level sharding of one shared frame (parallel.py) is off
+    parallel.enable(False)
 
     ctx = pbn.default_context()
     stream = torch.cuda.Stream()  # a non-default stream shared by torch and the library
@@ -252,9 +256,14 @@ def main():
     barrier()
     e0 = ctx.counters()
     t0 = time.perf_counter()
+    e2e_sum = torch.zeros(1, dtype=torch.float64, device="cuda")
     for _ in range(args.e2e_steps):
         s_e2e = cpd.slogl(host_rb)
+        if world > 1:   # the job's result is the sum over the ranks' shards
+            e2e_sum[0] = s_e2e
+            dist.all_reduce(e2e_sum)
     ctx.synchronize()
+    torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     e1 = ctx.counters()
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")

@@ -96,7 +96,8 @@ def test_cvl_batch_equals_single_and_memo(pbn):
     batch = cvl.local_score_batch(spbn, reqs)
     fresh = pbn.CVLikelihood(df, 10, seed)
     single = [fresh.local_score_node_type(spbn, t, v, e) for t, v, e in reqs]
-    assert batch == single   # same kernels, same order of additions: bit-identical
+    # same kernels on the same jobs; only the unit split (hence the order of partial sums) may differ
+    assert np.allclose(batch, single, rtol=1e-13, atol=0)
     again = cvl.local_score_batch(spbn, reqs)
     assert again == batch and cvl._scorer.stats["memo_hits"] >= len(reqs)
     # evidence order is part of the key (it changes rounding in the reference too)

@@ -1,0 +1,74 @@
+"""Parity at BASELINE.json's full size (configs[1]: CKDE('d' | a, b, c), float64, 1M train x 1M test rows),
+where the oracle cannot evaluate every row: a test-row sub-sample against the oracle, plus properties that do
+not depend on the size - additivity of the kernel sum over a partition of the training rows, additivity of
+slogl over test shards, CKDE = joint - marginal, and invariance to the order of the training rows."""
+import numpy as np
+import pytest
+
+import oracle
+import util_data
+
+pytestmark = pytest.mark.gpu
+
+N = 1_000_000
+VARS = ["d", "a", "b", "c"]
+
+
+@pytest.fixture(scope="module")
+def setup():
+    import pybnesian_b200 as pbn
+    train = util_data.generate_normal_data(N, seed=0)
+    test = util_data.generate_normal_data(N, seed=1)
+    ftrain, ftest = pbn.DataFrame(train), pbn.DataFrame(test)
+    cpd = pbn.CKDE("d", ["a", "b", "c"])
+    cpd.fit(ftrain)
+    logl = cpd.logl(ftest)
+    return pbn, train, test, ftrain, ftest, cpd, logl
+
+
+def test_subsample_against_oracle(setup):
+    pbn, train, test, ftrain, ftest, cpd, logl = setup
+    rows = np.random.default_rng(0).choice(N, 512, replace=False)
+    X = train[VARS].to_numpy()
+    H = oracle.bandwidth(X)
+    assert np.allclose(cpd.kde_joint().bandwidth, H, rtol=1e-11, atol=0)
+    want, _ = oracle.ckde_logl(X, test.iloc[rows][VARS].to_numpy(), H)
+    assert np.max(np.abs(logl[rows] - want) / np.abs(want)) < 1e-10
+    assert pbn.default_context().last_fallback_rows() == 0
+
+
+def test_slogl_is_additive_over_test_shards(setup):
+    pbn, train, test, ftrain, ftest, cpd, logl = setup
+    total = cpd.slogl(ftest)
+    assert abs(total - logl.sum()) <= 1e-12 * abs(total)
+    cut = 333_337
+    parts = cpd.slogl(pbn.DataFrame(test.iloc[:cut])) + cpd.slogl(pbn.DataFrame(test.iloc[cut:]))
+    assert abs(total - parts) <= 1e-12 * abs(total)
+
+
+def test_ckde_is_joint_minus_marginal(setup):
+    pbn, train, test, ftrain, ftest, cpd, logl = setup
+    sub = pbn.DataFrame(test.iloc[:200_000])
+    joint, marg = cpd.kde_joint().logl(sub), cpd.kde_marg().logl(sub)
+    assert np.max(np.abs((joint - marg) - logl[:200_000]) / np.abs(logl[:200_000])) < 1e-10
+
+
+def test_kernel_sum_is_additive_over_training_partition_and_order(setup):
+    pbn, train, test, ftrain, ftest, cpd, logl = setup
+    sub = pbn.DataFrame(test.iloc[:100_000])
+    H = cpd.kde_joint().bandwidth
+    full = cpd.kde_joint().logl(sub)
+    cut = 400_003
+    parts = []
+    for chunk in (train.iloc[:cut], train.iloc[cut:]):
+        k = pbn.KDE(VARS)
+        k.fit(pbn.DataFrame(chunk))
+        k.bandwidth = H                      # same kernel, different training rows
+        parts.append(k.logl(sub) + np.log(len(chunk)))
+    combined = np.logaddexp(parts[0], parts[1]) - np.log(N)
+    assert np.max(np.abs(combined - full) / np.abs(full)) < 1e-10
+    perm = np.random.default_rng(1).permutation(N)
+    k = pbn.KDE(VARS)
+    k.fit(pbn.DataFrame(train.iloc[perm]))
+    k.bandwidth = H
+    assert np.max(np.abs(k.logl(sub) - full) / np.abs(full)) < 1e-11

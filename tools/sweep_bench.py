@@ -1,0 +1,75 @@
+"""BASELINE.json configs[4]: KDE slogl sweep, n_train = n_test = N, d = 1..8,
+float32 and float64, i.i.d. N(0, I_d), NormalReferenceRule; pair-evals/s of the pair kernel (CUDA events
+inside the library) and its fraction of the FP64 / FP32+MUFU roofline of SURVEY §8(d).
+usage: python tools/sweep_bench.py [--n 1000000] [--dims 1,2,4,8] [--dtypes float64,float32] [--json out.json]
+Under torchrun the test rows of every point are sharded over the ranks (API-level sharding, parallel.py).
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", default="1000000")
+    ap.add_argument("--dims", default="1,2,3,4,5,6,7,8")
+    ap.add_argument("--dtypes", default="float64,float32")
+    ap.add_argument("--json", default="")
+    a = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        lr = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(lr)
+        os.environ["PBN_CUDA_DEVICE"] = str(lr)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    import util_data
+    import pybnesian_b200 as pbn
+    ctx = pbn.default_context()
+    f_hz, sms = 1.965e9, ctx.sm_count
+    rows = []
+    for n in [int(x) for x in a.n.split(",")]:
+        for dt in a.dtypes.split(","):
+            for d in [int(x) for x in a.dims.split(",")]:
+                tr = pbn.DataFrame(util_data.iid_normal(n, d, 0, dt))
+                te = pbn.DataFrame(util_data.iid_normal(n, d, 1, dt))
+                k = pbn.KDE(list(tr.columns))
+                k.fit(tr)
+                k.slogl(te)  # warm
+                ctx.set_timing(True)
+                ctx.pair_kernel_time(reset=True)
+                t0 = time.perf_counter()
+                s = k.slogl(te)
+                wall = time.perf_counter() - t0
+                ms, nl, pe = ctx.pair_kernel_time(reset=True)
+                ctx.set_timing(False)
+                if dt == "float64":
+                    peak_survey = sms * 64 * f_hz / (2 * d + 18)
+                    peak_own = sms * 64 * f_hz / (2 * d + 7)
+                else:
+                    peak_survey = peak_own = min(sms * 128 * f_hz / (2 * d + 2), sms * 16 * f_hz)
+                rate = pe / (ms * 1e-3)
+                rows.append({"n": n, "d": d, "dtype": dt, "n_gpus": world, "pair_evals_per_s_per_gpu_kernel": rate,
+                             "pair_evals_per_s_job_wall": float(n) * n / wall, "frac_survey_roofline": rate / peak_survey,
+                             "frac_own_roofline": rate / peak_own, "slogl": s, "fallback_rows": ctx.last_fallback_rows()})
+                if int(os.environ.get("RANK", "0")) == 0:
+                    print(json.dumps(rows[-1]), flush=True)
+    if a.json and int(os.environ.get("RANK", "0")) == 0:
+        with open(a.json, "w") as f:
+            json.dump(rows, f, indent=1)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
