@@ -32,8 +32,16 @@ def test_subsample_against_oracle(setup):
     X = train[VARS].to_numpy()
     H = oracle.bandwidth(X)
     assert np.allclose(cpd.kde_joint().bandwidth, H, rtol=1e-11, atol=0)
-    want, _ = oracle.ckde_logl(X, test.iloc[rows][VARS].to_numpy(), H)
-    assert np.max(np.abs(logl[rows] - want) / np.abs(want)) < 1e-10
+    T = test.iloc[rows][VARS].to_numpy()
+    want, _ = oracle.ckde_logl(X, T, H)
+    # a CKDE log-likelihood is the difference of two log-sums of magnitude ~10 and crosses zero (|logl| down to
+    # 1e-3 in this sample), so its relative error is unbounded by construction; the two terms are held to the
+    # strict relative bar and the difference to 1e-10 relative + 1e-12 absolute (the reference's own tests use
+    # np.isclose, i.e. atol = 1e-8)
+    joint_want, _ = oracle.kde_logl(X, T, H)
+    joint_got = cpd.kde_joint().logl(pbn.DataFrame(test.iloc[rows]))
+    assert np.max(np.abs(joint_got - joint_want) / np.abs(joint_want)) < 1e-10
+    assert np.all(np.abs(logl[rows] - want) <= 1e-12 + 1e-10 * np.abs(want))
     assert pbn.default_context().last_fallback_rows() == 0
 
 
@@ -50,7 +58,7 @@ def test_ckde_is_joint_minus_marginal(setup):
     pbn, train, test, ftrain, ftest, cpd, logl = setup
     sub = pbn.DataFrame(test.iloc[:200_000])
     joint, marg = cpd.kde_joint().logl(sub), cpd.kde_marg().logl(sub)
-    assert np.max(np.abs((joint - marg) - logl[:200_000]) / np.abs(logl[:200_000])) < 1e-10
+    assert np.allclose(joint - marg, logl[:200_000], rtol=1e-10, atol=1e-12)
 
 
 def test_kernel_sum_is_additive_over_training_partition_and_order(setup):
@@ -66,9 +74,9 @@ def test_kernel_sum_is_additive_over_training_partition_and_order(setup):
         k.bandwidth = H                      # same kernel, different training rows
         parts.append(k.logl(sub) + np.log(len(chunk)))
     combined = np.logaddexp(parts[0], parts[1]) - np.log(N)
-    assert np.max(np.abs(combined - full) / np.abs(full)) < 1e-10
+    assert np.allclose(combined, full, rtol=1e-10, atol=1e-12)
     perm = np.random.default_rng(1).permutation(N)
     k = pbn.KDE(VARS)
     k.fit(pbn.DataFrame(train.iloc[perm]))
     k.bandwidth = H
-    assert np.max(np.abs(k.logl(sub) - full) / np.abs(full)) < 1e-11
+    assert np.allclose(k.logl(sub), full, rtol=1e-11, atol=1e-12)
