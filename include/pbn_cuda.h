@@ -116,6 +116,13 @@ int pbn_kde_fit(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, pbn_
  * H = joint bandwidth; the marginal uses H[1:,1:] on the same rows.  d == 1 is a plain KDE. */
 int pbn_ckde_fit(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, pbn_rows rows, const double* H,
                  pbn_kde** out);
+/* ProductKDE::_fit (kde/ProductKDE.hpp:153-193): diagonal bandwidth h[0..d) (the *variances* returned by
+ * BandwidthSelector::diag_bandwidth), per-variable scale sqrt(h_i) (ProductKDE.cpp:6-29),
+ * lognorm = -d/2 log(2 pi) - 1/2 sum log h_i - log N.  The fitted object is evaluated with pbn_kde_logl
+ * (replaces logl_values_1d_mat + add_logl_values_1d_mat per variable and the column log-sum-exp,
+ * ProductKDE.hpp:233-296, KDE.cl.src:143-170). */
+int pbn_product_kde_fit(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, pbn_rows rows, const double* h,
+                        pbn_kde** out);
 int pbn_kde_free(pbn_kde* kde);
 int64_t pbn_kde_num_instances(const pbn_kde* kde);
 double pbn_kde_lognorm(const pbn_kde* kde); /* joint lognorm (kde/KDE.hpp:476-477) */

@@ -291,3 +291,47 @@ def ref_ucv_score_unconstrained(X, H):
                            ctypes.byref(sh))
     s2, s1 = T(s2h.value), T(sh.value)
     return float(np.exp(lognorm_2H) + float(T(2) * s2 / T(N)) - float(T(4) * s1 / T(N - 1)))
+
+
+def diag_bandwidth(X, rule="normal_reference"):
+    """NormalReferenceRule / ScottsBandwidth diag_bandwidth (d variances, float64)."""
+    X = _fmat(X)
+    n, d = X.shape
+    h = np.empty(d)
+    st = lib().orc_diag_bandwidth(_c_vp(X.ctypes.data), _c_i64(n), _c_int(d), _c_int(_dtype_code(X)),
+                                  _c_int(0 if rule == "normal_reference" else 1), _dptr(h))
+    if st:
+        raise SingularCovariance("status %d" % st)
+    return h
+
+
+def product_kde_logl(train, test, hdiag):
+    """(logl[m], slogl) of a ProductKDE with diagonal bandwidth `hdiag` (variances)."""
+    train, test = _fmat(train), _fmat(test)
+    assert train.dtype == test.dtype and train.shape[1] == test.shape[1]
+    N, d = train.shape
+    m = test.shape[0]
+    h = np.ascontiguousarray(np.asarray(hdiag, dtype=np.float64).ravel())
+    out = np.empty(m)
+    s = ctypes.c_double()
+    lib().orc_product_kde_logl(_c_vp(train.ctypes.data), _c_i64(N), _c_vp(test.ctypes.data), _c_i64(m), _c_int(d),
+                               _c_int(_dtype_code(train)), _dptr(h), _dptr(out), ctypes.byref(s))
+    return out, s.value
+
+
+def ref_product_kde_logl(train, test, hdiag):
+    """ProductKDE logl/slogl computed by the reference's kernels `logl_values_1d_mat` /
+    `add_logl_values_1d_mat` (host logic of kde/ProductKDE.hpp:233-296 restated in ref_driver.cpp)."""
+    train, test = _fmat(train), _fmat(test)
+    N, d = train.shape
+    m = test.shape[0]
+    h = np.asarray(hdiag, dtype=np.float64).ravel()
+    sd = np.sqrt(h) if train.dtype == np.float64 else np.sqrt(h.astype(np.float32))
+    sd = np.ascontiguousarray(sd.astype(train.dtype))
+    lognorm = -0.5 * d * np.log(2 * np.pi) - 0.5 * np.sum(np.log(h)) - np.log(N)
+    out = np.empty(m)
+    s = ctypes.c_double()
+    _reflib().ref_product_kde_logl(_c_vp(train.ctypes.data), _c_int(N), _c_vp(test.ctypes.data), _c_int(m), _c_int(d),
+                                   _c_int(_dtype_code(train)), _c_vp(sd.ctypes.data), ctypes.c_double(lognorm),
+                                   _dptr(out), ctypes.byref(s))
+    return out, s.value

@@ -394,6 +394,99 @@ double ucv_diagonal_T(const T* X, int64_t N, int d, const double* hdiag) {
            static_cast<double>(4 * sh / static_cast<T>(N - 1));
 }
 
+// ---- ProductKDE -----------------------------------------------------
+// NormalReferenceRule::diag_bandwidth (kde/NormalReferenceRule.hpp:72-106, eq. 3.4 of Chacon & Duong 2018)
+// and ScottsBandwidth::diag_bandwidth (kde/ScottsBandwidth.hpp:66-89), in T like the reference.
+// `inverse()` / `determinant()` of the d x d matrix are Eigen PartialPivLU in the reference; Gauss-Jordan
+// with partial pivoting in T stands in (rounding-level agreement only).
+// status: 0 ok, 1 = valid_rows <= d (<= 1 for Scott), 2 = covariance not positive definite.
+template <typename T>
+int diag_bandwidth_T(const T* X, int64_t n, int d, int rule, double* h) {
+    if (n <= (rule == 0 ? d : 1)) return 1;
+    std::vector<T> cov;
+    cov_T<T>(X, n, d, cov);
+    T N = static_cast<T>(n), dd = static_cast<T>(d);
+    if (rule != 0) {
+        double k = std::pow(static_cast<double>(N), -2. / (dd + 4.));
+        for (int i = 0; i < d; ++i) h[i] = k * static_cast<double>(cov[i + i * d]);
+        return 0;
+    }
+    if (!is_psd<T>(cov, d)) return 2;
+    std::vector<T> A(d * d), Inv(d * d, T(0));
+    for (int i = 0; i < d; ++i)
+        for (int j = 0; j < d; ++j) A[i + j * d] = cov[i + j * d] * (T(1) / cov[i + i * d]);
+    for (int i = 0; i < d; ++i) Inv[i + i * d] = 1;
+    T det = 1;
+    for (int c = 0; c < d; ++c) {
+        int piv = c;
+        for (int r = c + 1; r < d; ++r)
+            if (std::fabs(A[r + c * d]) > std::fabs(A[piv + c * d])) piv = r;
+        if (piv != c) {
+            for (int j = 0; j < d; ++j) {
+                std::swap(A[c + j * d], A[piv + j * d]);
+                std::swap(Inv[c + j * d], Inv[piv + j * d]);
+            }
+            det = -det;
+        }
+        T pv = A[c + c * d];
+        det *= pv;
+        for (int j = 0; j < d; ++j) { A[c + j * d] /= pv; Inv[c + j * d] /= pv; }
+        for (int r = 0; r < d; ++r) {
+            if (r == c) continue;
+            T f = A[r + c * d];
+            for (int j = 0; j < d; ++j) { A[r + j * d] -= f * A[c + j * d]; Inv[r + j * d] -= f * Inv[c + j * d]; }
+        }
+    }
+    T tr = 0, tr2 = 0;
+    for (int i = 0; i < d; ++i) {
+        tr += Inv[i + i * d];
+        for (int j = 0; j < d; ++j) tr2 += Inv[i + j * d] * Inv[j + i * d];
+    }
+    T k = 4 * dd * std::sqrt(det) / (2 * tr2 + tr * tr);
+    // `std::pow(k / N, 2. / (d + 4.)) * diag`: pow in double; Eigen promotes the scalar to the vector's
+    // scalar type (float for float data), the product is evaluated in T, then cast to double.
+    T f = static_cast<T>(std::pow(k / N, 2. / (dd + 4.)));
+    for (int i = 0; i < d; ++i) h[i] = static_cast<double>(f * cov[i + i * d]);
+    return 0;
+}
+
+// ProductKDE::_fit lognorm (kde/ProductKDE.hpp:190-192) and ProductKDE::_logl_impl (276-296) with the kernels
+// `logl_values_1d_mat` / `add_logl_values_1d_mat` (KDE.cl.src:143-170) followed by logsumexp_cols_offset:
+// per pair  l = -0.5 u_0^2 + lognorm;  l += -0.5 u_c^2 (c = 1..d-1),  u_c = (train_c - test_c) / sqrt(h_c),
+// all in T except the double literal 0.5 (the products are evaluated in double, then stored to T).
+template <typename T>
+void product_kde_logl_T(const T* train, int64_t N, const T* test, int64_t m, int d, const double* h, T* out) {
+    std::vector<T> sd(d);
+    double slog = 0;
+    for (int c = 0; c < d; ++c) {
+        sd[c] = sizeof(T) == 8 ? static_cast<T>(std::sqrt(h[c])) : std::sqrt(static_cast<T>(h[c]));
+        slog += std::log(h[c]);
+    }
+    T lognorm = static_cast<T>(-0.5 * d * std::log(2 * kPi) - 0.5 * slog - std::log(static_cast<double>(N)));
+#pragma omp parallel
+    {
+        std::vector<T> col(N), work(N);
+#pragma omp for schedule(dynamic, 8)
+        for (int64_t t = 0; t < m; ++t) {
+            for (int64_t i = 0; i < N; ++i) {
+                T u = (train[i] - test[t]) / sd[0];
+                T l = static_cast<T>((-0.5 * static_cast<double>(u)) * static_cast<double>(u) + static_cast<double>(lognorm));
+                for (int c = 1; c < d; ++c) {
+                    T v = (train[i + static_cast<size_t>(c) * N] - test[t + static_cast<size_t>(c) * m]) / sd[c];
+                    l = static_cast<T>(static_cast<double>(l) + (-0.5 * static_cast<double>(v)) * static_cast<double>(v));
+                }
+                col[i] = l;
+            }
+            work = col;
+            T mx = tree_reduce<T, true>(work);
+            for (int64_t i = 0; i < N; ++i) col[i] = exp_T<T>(col[i] - mx);
+            T s = tree_reduce<T, false>(col);
+            col.resize(N);
+            out[t] = log_T<T>(s) + mx;
+        }
+    }
+}
+
 // ---- LinearGaussianCPD ------------------------------------------------------------
 // Householder QR least squares with column pivoting (stands in for Eigen's
 // `colPivHouseholderQr().solve`, mle_LinearGaussianCPD.hpp:166).  A is n x q col-major (consumed).
@@ -686,6 +779,27 @@ int orc_ckde_logl(const void* train, int64_t N, const void* test, int64_t m, int
     } else {
         std::vector<float> l(m);
         ckde_logl_T<float>(static_cast<const float*>(train), N, static_cast<const float*>(test), m, d, Hjoint, l.data());
+        if (out_logl) for (int64_t i = 0; i < m; ++i) out_logl[i] = l[i];
+        if (out_slogl) *out_slogl = slogl_T<float>(l.data(), m);
+    }
+    return 0;
+}
+
+int orc_diag_bandwidth(const void* X, int64_t n, int d, int dtype, int rule, double* h) {
+    return dtype == 0 ? diag_bandwidth_T<double>(static_cast<const double*>(X), n, d, rule, h)
+                      : diag_bandwidth_T<float>(static_cast<const float*>(X), n, d, rule, h);
+}
+
+int orc_product_kde_logl(const void* train, int64_t N, const void* test, int64_t m, int d, int dtype, const double* h,
+                         double* out_logl, double* out_slogl) {
+    if (dtype == 0) {
+        std::vector<double> l(m);
+        product_kde_logl_T<double>(static_cast<const double*>(train), N, static_cast<const double*>(test), m, d, h, l.data());
+        if (out_logl) std::copy(l.begin(), l.end(), out_logl);
+        if (out_slogl) *out_slogl = slogl_T<double>(l.data(), m);
+    } else {
+        std::vector<float> l(m);
+        product_kde_logl_T<float>(static_cast<const float*>(train), N, static_cast<const float*>(test), m, d, h, l.data());
         if (out_logl) for (int64_t i = 0; i < m; ++i) out_logl[i] = l[i];
         if (out_slogl) *out_slogl = slogl_T<float>(l.data(), m);
     }

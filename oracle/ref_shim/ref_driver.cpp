@@ -75,6 +75,7 @@ template <> struct K<double> {
     static void logl_col(double* sq, uint c, double* sol, uint sr, uint idx, double ln) { logl_values_mat_column_double(sq, c, sol, sr, idx, ln); }
     static void logl_row(double* sq, uint c, double* sol, uint sr, uint idx, double ln) { logl_values_mat_row_double(sq, c, sol, sr, idx, ln); }
     static void logl_1d(double* tr, uint n, double* te, uint off, const double* sd, double ln, double* res) { logl_values_1d_mat_double(tr, n, te, off, sd, ln, res); }
+    static void add_logl_1d(double* tr, uint n, double* te, uint off, const double* sd, double* res) { add_logl_values_1d_mat_double(tr, n, te, off, sd, res); }
     static void sub_vec(double* a, double* b) { substract_vectors_double(a, b); }
     static void ucv_1d(double* d, uint off, double* h, double l2, double l1, double* s2, double* s1) { sum_ucv_1d_double(d, off, h, l2, l1, s2, s1); }
     static void tri_sub(double* d, uint pr, uint c, uint off, uint rows, double* res) { triangular_substract_mat_double(d, pr, c, off, rows, res); }
@@ -92,6 +93,7 @@ template <> struct K<float> {
     static void logl_col(float* sq, uint c, float* sol, uint sr, uint idx, float ln) { logl_values_mat_column_float(sq, c, sol, sr, idx, ln); }
     static void logl_row(float* sq, uint c, float* sol, uint sr, uint idx, float ln) { logl_values_mat_row_float(sq, c, sol, sr, idx, ln); }
     static void logl_1d(float* tr, uint n, float* te, uint off, const float* sd, float ln, float* res) { logl_values_1d_mat_float(tr, n, te, off, sd, ln, res); }
+    static void add_logl_1d(float* tr, uint n, float* te, uint off, const float* sd, float* res) { add_logl_values_1d_mat_float(tr, n, te, off, sd, res); }
     static void sub_vec(float* a, float* b) { substract_vectors_float(a, b); }
     static void ucv_1d(float* d, uint off, float* h, float l2, float l1, float* s2, float* s1) { sum_ucv_1d_float(d, off, h, l2, l1, s2, s1); }
     static void tri_sub(float* d, uint pr, uint c, uint off, uint rows, float* res) { triangular_substract_mat_float(d, pr, c, off, rows, res); }
@@ -185,6 +187,31 @@ void kde_logl(const T* train_c, int N, const T* test_c, int m, int d, const T* c
     exec(m - remaining, remaining);
 }
 
+// ProductKDE::_logl_impl + product_logl_mat (kde/ProductKDE.hpp:233-296): one training column per variable,
+// test block column-major m x d, sd[c] = sqrt(h_c) in T, chunks of <= 64 test rows.
+template <typename T>
+void product_kde_logl(const T* train_c, int N, const T* test_c, int m, int d, const T* sd, T lognorm, T* res) {
+    std::vector<T> train(train_c, train_c + (size_t)N * d), test(test_c, test_c + (size_t)m * d);
+    int allocated_m = std::min(m, 64);
+    std::vector<T> mat((size_t)N * allocated_m);
+    int iterations = (int)std::ceil((double)m / (double)allocated_m);
+    auto exec = [&](int test_offset, int test_length) {
+        run_1d((size_t)N * test_length, [&]() { K<T>::logl_1d(train.data(), N, test.data(), test_offset, sd, lognorm, mat.data()); });
+        for (int c = 1; c < d; ++c)
+            run_1d((size_t)N * test_length, [&]() {
+                K<T>::add_logl_1d(train.data() + (size_t)c * N, N, test.data(), (uint)(c * m) + test_offset, sd + c, mat.data());
+            });
+        std::vector<T> sub(mat.begin(), mat.begin() + (size_t)N * test_length), mx(test_length);
+        reduction_cols<T, true>(sub, N, test_length, mx.data(), 0);
+        run_1d((size_t)N * test_length, [&]() { K<T>::lse_coeffs(sub.data(), N, mx.data()); });
+        reduction_cols<T, false>(sub, N, test_length, res, test_offset);
+        run_1d(test_length, [&]() { K<T>::finish_lse(res, test_offset, mx.data()); });
+    };
+    for (int i = 0; i < iterations - 1; ++i) exec(i * allocated_m, allocated_m);
+    int remaining = m - (iterations - 1) * allocated_m;
+    exec(m - remaining, remaining);
+}
+
 template <typename T>
 void ucv_sums(const T* X_c, int N, int d, const T* chol_c, T l2H, T lH, T* s2h_out, T* sh_out) {
     std::vector<T> X(X_c, X_c + (size_t)N * d), chol(chol_c, chol_c + d * d);
@@ -226,6 +253,23 @@ int ref_kde_logl(const void* train, int N, const void* test, int m, int d, int d
     } else {
         std::vector<float> res(m);
         kde_logl<float>((const float*)train, N, (const float*)test, m, d, (const float*)chol, (float)lognorm, res.data());
+        for (int i = 0; i < m; ++i) out[i] = res[i];
+        if (out_sum) *out_sum = sum1d<float>(res);
+    }
+    return 0;
+}
+
+// ProductKDE logl/slogl: sd = sqrt(h) in the data type (ProductKDE.hpp:172-179), lognorm rounded to the data type.
+int ref_product_kde_logl(const void* train, int N, const void* test, int m, int d, int dtype, const void* sd,
+                         double lognorm, double* out, double* out_sum) {
+    if (dtype == 0) {
+        std::vector<double> res(m);
+        product_kde_logl<double>((const double*)train, N, (const double*)test, m, d, (const double*)sd, lognorm, res.data());
+        for (int i = 0; i < m; ++i) out[i] = res[i];
+        if (out_sum) *out_sum = sum1d<double>(res);
+    } else {
+        std::vector<float> res(m);
+        product_kde_logl<float>((const float*)train, N, (const float*)test, m, d, (const float*)sd, (float)lognorm, res.data());
         for (int i = 0; i < m; ++i) out[i] = res[i];
         if (out_sum) *out_sum = sum1d<float>(res);
     }

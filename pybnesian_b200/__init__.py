@@ -6,7 +6,7 @@ NormalReferenceRule, ScottsBandwidth, SingularCovarianceData, ...
 """
 from ._lib import SingularCovarianceData, Context, default_context, LIB_PATH
 from .dataset import DataFrame, CrossValidation, HoldOut
-from .kde import BandwidthSelector, NormalReferenceRule, ScottsBandwidth, UCV, UCVScorer, KDE
+from .kde import BandwidthSelector, NormalReferenceRule, ScottsBandwidth, UCV, UCVScorer, KDE, ProductKDE
 from .factors import (Factor, FactorType, CKDE, CKDEType, LinearGaussianCPD, LinearGaussianCPDType,
                       UnknownFactorType)
 from .models import (Dag, BayesianNetwork, BayesianNetworkType, GaussianNetwork, GaussianNetworkType, KDENetwork,

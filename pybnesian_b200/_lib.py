@@ -19,7 +19,7 @@ EXPORTS = [
     "pbn_last_error", "pbn_version", "pbn_device_count", "pbn_ctx_create", "pbn_ctx_destroy", "pbn_ctx_set_stream",
     "pbn_ctx_stream", "pbn_ctx_synchronize", "pbn_ctx_sm_count", "pbn_ctx_counters", "pbn_table_upload",
     "pbn_table_free", "pbn_table_rows", "pbn_table_cols", "pbn_table_download", "pbn_table_moments", "pbn_bandwidth",
-    "pbn_diag_bandwidth", "pbn_kde_fit", "pbn_ckde_fit", "pbn_kde_free", "pbn_kde_num_instances", "pbn_kde_lognorm",
+    "pbn_diag_bandwidth", "pbn_kde_fit", "pbn_ckde_fit", "pbn_product_kde_fit", "pbn_kde_free", "pbn_kde_num_instances", "pbn_kde_lognorm",
     "pbn_kde_logl", "pbn_kde_logl_device", "pbn_ctx_last_fallback_rows", "pbn_device_alloc", "pbn_device_free",
     "pbn_device_read", "pbn_ctx_set_timing", "pbn_ctx_pair_kernel_time", "pbn_ucv_create", "pbn_ucv_free",
     "pbn_ucv_score", "pbn_ucv_pair_sums", "pbn_ucv_pairs", "pbn_ucv_bandwidth",
@@ -90,6 +90,7 @@ def lib():
         L.pbn_diag_bandwidth.argtypes = [vp, vp, ip, ci, Rows, ci, dp]
         L.pbn_kde_fit.argtypes = [vp, vp, ip, ci, Rows, dp, ctypes.POINTER(vp)]
         L.pbn_ckde_fit.argtypes = [vp, vp, ip, ci, Rows, dp, ctypes.POINTER(vp)]
+        L.pbn_product_kde_fit.argtypes = [vp, vp, ip, ci, Rows, dp, ctypes.POINTER(vp)]
         L.pbn_kde_free.argtypes = [vp]
         L.pbn_kde_num_instances.argtypes = [vp]
         L.pbn_kde_num_instances.restype = i64

@@ -985,6 +985,17 @@ int pbn_kde_fit(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, pbn_
 int pbn_ckde_fit(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, pbn_rows rows, const double* H, pbn_kde** out) {
     return fit_impl(ctx, tbl, cols, d, rows, H, true, out);
 }
+int pbn_product_kde_fit(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, pbn_rows rows, const double* h,
+                        pbn_kde** out) {
+    if (!h || d <= 0 || d > PBN_MAX_DIM) return set_error(PBN_ERR_ARG, "invalid diagonal bandwidth");
+    std::vector<double> H((size_t)d * d, 0.0);
+    for (int i = 0; i < d; ++i) {
+        if (!(h[i] > 0.0) || !std::isfinite(h[i]))
+            return set_error(PBN_ERR_SINGULAR, "diagonal bandwidth entries must be positive");
+        H[i + (size_t)i * d] = h[i];
+    }
+    return fit_impl(ctx, tbl, cols, d, rows, H.data(), false, out);
+}
 int pbn_kde_free(pbn_kde* k) {
     if (!k) return PBN_OK;
     DevSetter ds(k->ctx->device);

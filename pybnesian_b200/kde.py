@@ -220,10 +220,10 @@ class _FittedHandle:
             pass
 
 
-def _fit_handle(tbl, cols, rows, H, ckde=False):
+def _fit_handle(tbl, cols, rows, H, ckde=False, product=False):
     H = np.asfortranarray(np.asarray(H, dtype=np.float64))
     h = ctypes.c_void_p()
-    fn = lib().pbn_ckde_fit if ckde else lib().pbn_kde_fit
+    fn = lib().pbn_product_kde_fit if product else (lib().pbn_ckde_fit if ckde else lib().pbn_kde_fit)
     check(fn(tbl.ctx.handle, tbl.handle, int_array(cols), len(cols), rows, _dp(H), ctypes.byref(h)))
     return _FittedHandle(h)
 
@@ -387,5 +387,140 @@ class KDE:
 
     def __str__(self):
         return "KDE(" + ", ".join(self._variables) + ")"
+
+    __repr__ = __str__
+
+
+class ProductKDE:
+    """pybnesian.ProductKDE (kde/ProductKDE.{hpp,cpp}, pybindings_kde.cpp:304-393): product of univariate Gaussian
+    kernels, i.e. a KDE with a diagonal bandwidth `h` (variances) from `BandwidthSelector.diag_bandwidth`.  Evaluated
+    by the same fused pair kernel as KDE (whitening with diag(1/sqrt(h)), include/pbn_cuda.h: pbn_product_kde_fit)."""
+
+    def __init__(self, variables, bandwidth_selector=None):
+        variables = list(variables)
+        if bandwidth_selector is None:
+            bandwidth_selector = NormalReferenceRule()
+        if not isinstance(bandwidth_selector, BandwidthSelector):
+            raise RuntimeError("Bandwidth selector procedure must be non-null.")
+        if not variables:
+            raise ValueError("Cannot create a ProductKDE model with 0 variables")
+        self._variables = variables
+        self._bselector = bandwidth_selector
+        self._fitted = False
+        self._bandwidth = np.empty(0)
+        self._handle = None
+        self._train = None
+        self._N = 0
+        self._dtype = _lib.PBN_F64
+
+    def variables(self):
+        return list(self._variables)
+
+    def num_variables(self):
+        return len(self._variables)
+
+    def fitted(self):
+        return self._fitted
+
+    def _check_fitted(self):
+        if not self._fitted:
+            raise ValueError("ProductKDE factor not fitted.")
+
+    def num_instances(self):
+        self._check_fitted()
+        return self._N
+
+    def data_type(self):
+        self._check_fitted()
+        return _ARROW_TYPE[self._dtype]
+
+    def bandwidth_type(self):
+        return self._bselector
+
+    @property
+    def bandwidth(self):
+        return self._bandwidth
+
+    @bandwidth.setter
+    def bandwidth(self, new_bandwidth):
+        h = np.asarray(new_bandwidth, dtype=np.float64)
+        d = len(self._variables)
+        if h.ndim != 1 or h.shape[0] != d:
+            raise ValueError("The bandwidth matrix must be a vector with shape (%d)" % d)
+        self._bandwidth = np.array(h)
+        if self._fitted and d > 0:
+            tbl, cols, rows = self._train
+            self._handle = _fit_handle(tbl, cols, rows, self._bandwidth, product=True)
+
+    def fit(self, df):
+        frame = DataFrame.wrap(df)
+        self._dtype = frame.dtype_code(self._variables, "fit ProductKDE")
+        h = np.asarray(self._bselector.diag_bandwidth(frame, self._variables), dtype=np.float64).ravel()
+        d = len(self._variables)
+        if h.shape != (d,):
+            raise ValueError("BandwidthSelector::diag_bandwidth must return a vector with shape (%d)" % d)
+        tbl, cols, _ = frame.device_table(self._variables)
+        self._fit_table(tbl, cols, tbl.rows(), h)
+
+    def _fit_table(self, tbl, cols, rows, h):
+        self._handle = _fit_handle(tbl, cols, rows, h, product=True)
+        self._train = (tbl, list(cols), rows)
+        self._bandwidth = np.array(h)
+        self._N = int(lib().pbn_kde_num_instances(self._handle.handle))
+        self._dtype = tbl.dtype_code
+        self._fitted = True
+
+    def _check_test(self, frame):
+        self._check_fitted()
+        if frame.same_type(self._variables) != _ARROW_TYPE[self._dtype]:
+            raise ValueError("Data type of training and test datasets is different.")
+
+    def logl(self, df):
+        frame = DataFrame.wrap(df)
+        self._check_test(frame)
+        return _run_logl(self._handle, frame, self._variables, True, False)[0]
+
+    def slogl(self, df):
+        frame = DataFrame.wrap(df)
+        self._check_test(frame)
+        return _run_logl(self._handle, frame, self._variables, False, True)[1]
+
+    def dataset(self):
+        """ProductKDE::training_data (kde/ProductKDE.hpp:122-151): read back from the device."""
+        self._check_fitted()
+        tbl, cols, rows = self._train
+        arrays = [pa.array(tbl.download(c, rows)) for c in cols]
+        return pa.RecordBatch.from_arrays(arrays, names=self._variables).to_pandas()
+
+    def lognorm_const(self):
+        self._check_fitted()
+        return lib().pbn_kde_lognorm(self._handle.handle)
+
+    def save(self, filename):
+        if not filename.endswith(".pickle"):
+            filename += ".pickle"
+        with open(filename, "wb") as f:
+            pickle.dump(self, f)
+
+    # pickle layout of ProductKDE::__getstate__ (kde/ProductKDE.hpp:311-337): one training vector per variable
+    def __getstate__(self):
+        bw, training, lognorm, n_export, type_id = np.empty(0), [], -1.0, -1, -1
+        if self._fitted:
+            tbl, cols, rows = self._train
+            training = [tbl.download(c, rows) for c in cols]
+            lognorm, n_export, type_id, bw = self.lognorm_const(), self._N, self._dtype, self._bandwidth
+        return (self._variables, self._fitted, self._bselector, bw, training, lognorm, n_export, type_id)
+
+    def __setstate__(self, t):
+        if len(t) != 8:
+            raise RuntimeError("Not valid ProductKDE.")
+        self.__init__(t[0], t[2])
+        if t[1]:
+            from .dataset import DeviceTable
+            tbl = DeviceTable(_lib.default_context(), [np.asarray(c) for c in t[4]], int(t[7]))
+            self._fit_table(tbl, list(range(len(t[0]))), tbl.rows(), np.asarray(t[3], dtype=np.float64))
+
+    def __str__(self):
+        return "ProductKDE(" + ", ".join(self._variables) + ")"
 
     __repr__ = __str__
