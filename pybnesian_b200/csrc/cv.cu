@@ -146,6 +146,9 @@ struct WhitenJob {
     void* y_train;     // AoS [n - (t1 - t0)][D]
     void* y_test;      // AoS [t1 - t0][D]
     float* bound;      // [0] max |coordinate| over training rows, [1] over test rows
+    double* nrm_train; // f64 only (else null): -sum_{c<dn} y_c^2 per row, for the pair kernel's dot-product form
+    double* nrm_test;
+    int dn;
 };
 
 template <typename T, int D>
@@ -162,14 +165,20 @@ __global__ void whiten_batch_kernel(const WhitenJob* __restrict__ jobs, long lon
                          : static_cast<T*>(jb.y_train) + (r < jb.t0 ? r : r - (jb.t1 - jb.t0)) * D;
         float mx = 0.f;
         int w = 0;
+        double nn = 0;
 #pragma unroll
         for (int i = 0; i < D; ++i) {
             double s = 0;
 #pragma unroll
             for (int k = 0; k <= i; ++k) s = fma(jb.W[w++], x[k], s);
             out[i] = static_cast<T>(s);
+            if (i < jb.dn) nn = fma(-s, s, nn);
             float a = fabsf(static_cast<float>(s));
             mx = (a > mx || a != a) ? (a != a ? INFINITY : a) : mx;  // NaN counts as unbounded
+        }
+        if (sizeof(T) == 8 && jb.nrm_train) {
+            if (is_test) jb.nrm_test[r - jb.t0] = nn;
+            else jb.nrm_train[r < jb.t0 ? r : r - (jb.t1 - jb.t0)] = nn;
         }
         if (is_test) mx_te = mx; else mx_tr = mx;
     }
@@ -726,6 +735,7 @@ int score_ckde_group(pbn_ctx* ctx, pbn_cv* cv, const pbn_cv_item* items, const s
     auto job_bytes = [&](int64_t ntr, int64_t m) {
         size_t a = ((size_t)ntr * d * es + 16 + 255) / 256 * 256;
         size_t b = ((size_t)m * d * es + 16 + 255) / 256 * 256;
+        if (f64) b += ((size_t)ntr * 8 + 16 + 255) / 256 * 256 + ((size_t)m * 8 + 255) / 256 * 256;  // row norms
         return a + b;
     };
     const size_t budget = (size_t)3 << 30;  // whitened-row scratch per chunk
@@ -791,6 +801,7 @@ int score_ckde_group(pbn_ctx* ctx, pbn_cv* cv, const pbn_cv_item* items, const s
                 ybytes += ((size_t)ntr * d * es + 16 + 255) / 256 * 256;
                 y_off_test.push_back(ybytes);
                 ybytes += ((size_t)m * d * es + 16 + 255) / 256 * 256;
+                if (f64) ybytes += ((size_t)ntr * 8 + 16 + 255) / 256 * 256 + ((size_t)m * 8 + 255) / 256 * 256;  // row norms
                 FinJob fin;
                 fin.lognorm_joint = h.lognorm_joint;
                 fin.lognorm_marg = h.lognorm_marg;
@@ -854,6 +865,14 @@ int score_ckde_group(pbn_ctx* ctx, pbn_cv* cv, const pbn_cv_item* items, const s
             wj[j].y_train = base + o_y + y_off_train[j];
             wj[j].y_test = base + o_y + y_off_test[j];
             wj[j].bound = reinterpret_cast<float*>(base + o_bound) + 2 * j;
+            if (f64) {
+                char* after_test = static_cast<char*>(wj[j].y_test) + ((size_t)hj[j].m * d * es + 16 + 255) / 256 * 256;
+                wj[j].nrm_train = reinterpret_cast<double*>(after_test);
+                wj[j].nrm_test = reinterpret_cast<double*>(after_test + ((size_t)hj[j].n_train * 8 + 16 + 255) / 256 * 256);
+                wj[j].dn = ckde ? d - 1 : d;
+                pj[j].train_nrm = wj[j].nrm_train;
+                pj[j].test_nrm = wj[j].nrm_test;
+            }
             pj[j].train = wj[j].y_train;
             pj[j].test = wj[j].y_test;
             pj[j].bound_train = wj[j].bound;

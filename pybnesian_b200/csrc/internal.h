@@ -70,6 +70,7 @@ struct pbn_kde {
     int64_t n;
     void* y;  // whitened training rows AoS [n_pad][d]
     float* d_bound;  // device scalar: max |whitened training coordinate|
+    double* nrm;     // f64, d <= 8 only (else null): -sum_{c<dn} y_c^2 per training row, dn = d-1 if ckde else d
     double W[PBN_MAX_DIM * PBN_MAX_DIM];  // row-major lower-triangular whitening matrix (incl. unit scale)
     double mu[PBN_MAX_DIM];
     int perm[PBN_MAX_DIM];  // internal column k = caller column perm[k]
@@ -110,6 +111,7 @@ struct WhitenParams {
     double W[PBN_MAX_DIM * (PBN_MAX_DIM + 1) / 2];  // packed lower triangle, row-major
     double mu[PBN_MAX_DIM];
     int d;
+    int dn;           // coordinates entering the row norm (see pbn_kde::nrm)
     int64_t b0, n0, b1, n;
 };
 
@@ -121,7 +123,7 @@ int moments_impl(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, pbn
                  double* cov_out);
 // y = W (x - mu) for the rows of a range, AoS output in the table's dtype; `Wfull` row-major d x d lower.
 int whiten_raw_launch(pbn_ctx* ctx, const pbn_table* tbl, const int* cols_internal_order, int d, pbn_rows rows,
-                      const double* Wfull, const double* mu, void* out, float* bound);
+                      const double* Wfull, const double* mu, void* out, float* bound, double* nrm = nullptr, int dn = 0);
 
 // MLE<LinearGaussianCPD> from centred moments (cv.cu): Cm = sum (x_a - mean_a)(x_b - mean_b), column-major d x d,
 // variable first; writes beta[p + 1], returns the variance.

@@ -37,6 +37,8 @@ struct PairJob {
     double* part;          // partial sums: [n_acc][slots][m_pad]
     const float* bound_train;  // max |whitened coordinate| over the training rows (device scalar)
     const float* bound_test;   // same over the test rows
+    const double* train_nrm;   // f64 only, may be null: -sum_{c<DN} y_c^2 per training row (DN = D-1 for CKDE, else D)
+    const double* test_nrm;    // same per test row; both present -> the dot-product form may be used (see tile_f64_dot)
     long long n_train;
     long long m;
     long long m_pad;       // row stride of one slot
@@ -52,7 +54,7 @@ constexpr int kStages = 2;
 
 template <typename T> struct PairCfg;
 #ifndef PBN_F64_R
-#define PBN_F64_R 2
+#define PBN_F64_R 3
 #endif
 #ifndef PBN_F64_TILE
 #define PBN_F64_TILE 512
@@ -68,6 +70,14 @@ template <typename T> struct PairCfg;
 #endif
 #ifndef PBN_F32_MINCTAS
 #define PBN_F32_MINCTAS 3
+#endif
+#ifndef PBN_F64_DOT
+#define PBN_F64_DOT 1
+#endif
+// the dot-product form is used from this many norm coordinates on (measured on B200, N = m = 300k, R = 3:
+// KDE d=4 +7%, d=8 +18%; no gain for DN <= 3, where the extra norm loads cost what the saved DFMAs buy)
+#ifndef PBN_F64_DOT_MIN_DN
+#define PBN_F64_DOT_MIN_DN 4
 #endif
 #ifndef PBN_EXP_BITS
 #define PBN_EXP_BITS 11
@@ -98,6 +108,10 @@ static_assert(kExpDeg >= 2 && kExpDeg <= 4, "PBN_EXP_DEG");
 // fit the 227 KB of an SM
 template <typename T> __host__ __device__ constexpr int pair_tile(int D) {
     return (sizeof(T) == 8 && D >= 7) ? PairCfg<T>::TILE / 2 : PairCfg<T>::TILE;
+}
+// per-stage bytes of the training-row norm tile (dot-product form, f64 only)
+template <typename T> __host__ __device__ constexpr uint32_t pair_nrm_bytes(int D) {
+    return sizeof(T) == 8 ? static_cast<uint32_t>(pair_tile<T>(D) * sizeof(double)) : 0u;
 }
 template <typename T> __host__ __device__ constexpr size_t exp_tab_smem_bytes() {
     return sizeof(T) == 8 ? static_cast<size_t>(kExpTab) * kExpRep * sizeof(double) : 0;
@@ -219,6 +233,41 @@ __device__ __forceinline__ void tile_f64(const double* __restrict__ tp, int cnt,
     }
 }
 
+// Dot-product form of the same unit:  -|yt - yi|^2 = (-|yt|^2) + (-|yi|^2) + sum_c (2 yt_c) yi_c  costs DN + 1
+// FP64 instructions instead of 2 DN (at = -|yt|^2 and nb = -|yi|^2 come from the whitening kernel, yt holds
+// 2 yt_c for c < DN).  For a CKDE the conditioned variable (last coordinate) stays in difference form on top
+// of the marginal exponent.  The cancellation error is ~ sqrt(DN+1) 2^-53 (2 DN B^2) table units (B = largest
+// |whitened coordinate|); the caller only takes this path when that is below 1e-12 relative per term.
+template <int D, bool CKDE, int R>
+__device__ __forceinline__ void tile_f64_dot(const double* __restrict__ tp, const double* __restrict__ nb, int cnt,
+                                             const double (&yt)[R][D], const double (&at)[R],
+                                             const double* __restrict__ tab, double (&sum_j)[R], double (&sum_m)[R]) {
+    constexpr int DN = CKDE ? D - 1 : D;
+#pragma unroll 4
+    for (int i = 0; i < cnt; ++i) {
+        double p[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) p[c] = tp[i * D + c];
+        const double b = nb[i];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            double acc = at[r] + b;
+#pragma unroll
+            for (int c = 0; c < DN; ++c) acc = fma(yt[r][c], p[c], acc);
+            if (CKDE) {
+                double st;
+                double pm = exp2_tab<false>(acc, tab, st);
+                sum_m[r] = fma(st, pm, sum_m[r]);
+                double dl = yt[r][D - 1] - p[D - 1];
+                acc = fma(-dl, dl, acc);
+            }
+            double st;
+            double pj = exp2_tab<false>(acc, tab, st);
+            sum_j[r] = fma(st, pj, sum_j[r]);
+        }
+    }
+}
+
 // Same unit on the FP32 FMA pipe + MUFU.EX2; per-tile float sums are folded into the
 // double accumulators by the caller (summation error stays at ~sqrt(TILE) ulp).
 template <int D, bool CKDE, int R>
@@ -265,11 +314,15 @@ pair_kernel(const PairJob* __restrict__ jobs, int n_jobs, long long total_units,
     constexpr int TILE = pair_tile<T>(D);
     constexpr int TB = kThreads * R;  // test rows per tile
     constexpr uint32_t TILE_BYTES = TILE * D * sizeof(T);
+    constexpr uint32_t NRM_BYTES = pair_nrm_bytes<T>(D);  // per stage; 0 for f32
+    constexpr int DN = CKDE ? D - 1 : D;
+    constexpr bool DOT = PBN_F64_DOT && sizeof(T) == 8 && DN >= PBN_F64_DOT_MIN_DN;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T* tile_buf = reinterpret_cast<T*>(smem_raw);  // [kStages][TILE*D]
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + kStages * TILE_BYTES);
-    double* tab = reinterpret_cast<double*>(smem_raw + kStages * TILE_BYTES + 64);
+    double* nrm_buf = reinterpret_cast<double*>(smem_raw + kStages * TILE_BYTES);  // [kStages][TILE]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + kStages * (TILE_BYTES + NRM_BYTES));
+    double* tab = reinterpret_cast<double*>(smem_raw + kStages * (TILE_BYTES + NRM_BYTES) + 64);
 
     const int tid = threadIdx.x;
     const long long u0 = static_cast<long long>(blockIdx.x) * upb;
@@ -305,8 +358,11 @@ pair_kernel(const PairJob* __restrict__ jobs, int n_jobs, long long total_units,
         if (cnt > TILE) cnt = TILE;
         uint32_t bytes = static_cast<uint32_t>(((cnt * D * sizeof(T)) + 15) & ~15ull);
         const T* src = reinterpret_cast<const T*>(jb.train) + start * D;
-        mbar_expect_tx(&full_bar[stage], bytes);
+        uint32_t nbytes = 0;
+        if (DOT && jb.train_nrm && jb.test_nrm) nbytes = static_cast<uint32_t>((cnt * sizeof(double) + 15) & ~15ull);
+        mbar_expect_tx(&full_bar[stage], bytes + nbytes);
         tma_bulk_g2s(tile_buf + static_cast<size_t>(stage) * TILE * D, src, bytes, &full_bar[stage]);
+        if (nbytes) tma_bulk_g2s(nrm_buf + static_cast<size_t>(stage) * TILE, jb.train_nrm + start, nbytes, &full_bar[stage]);
         ++pu;
     };
     if (tid == 0) {
@@ -315,10 +371,11 @@ pair_kernel(const PairJob* __restrict__ jobs, int n_jobs, long long total_units,
 
     int cj = jlo;
     T yt[R][D];
+    double at[R];
     double sum_j[R], sum_m[R];
     long long cur_tt = -1;
     int cur_job = -1;
-    bool safe = true;
+    bool safe = true, dot = false;
 
     auto flush = [&]() {
         if (cur_job < 0) return;
@@ -364,6 +421,23 @@ pair_kernel(const PairJob* __restrict__ jobs, int n_jobs, long long total_units,
                 float b = jb.bound_test ? *jb.bound_test : INFINITY;
                 float lim = static_cast<float>(D) * (a + b) * (a + b);
                 safe = !(lim < 2.0e9f);
+                if (DOT) {
+                    // cancellation error of the dot-product form, relative per term (see tile_f64_dot):
+                    // sqrt(DN+1) * 2^-53 * 2 DN B^2 * ln2/K < 1e-12
+                    float B = fmaxf(a, b);
+                    float crit = sqrtf(static_cast<float>(DN + 1)) * 2.f * DN * B * B;
+                    dot = jb.train_nrm && jb.test_nrm && crit < static_cast<float>(1e-12 * 9007199254740992.0 / kExpA) && !safe;
+                    if (dot) {
+                        const double* tn = jb.test_nrm;
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            long long row = tt * TB + r * kThreads + tid;
+                            at[r] = row < jb.m ? tn[row] : 0.0;
+#pragma unroll
+                            for (int c = 0; c < DN; ++c) yt[r][c] *= T(2);
+                        }
+                    }
+                }
             }
         }
         long long cnt_ll = jb.n_train - static_cast<long long>(nt) * TILE;
@@ -373,7 +447,9 @@ pair_kernel(const PairJob* __restrict__ jobs, int n_jobs, long long total_units,
         const T* __restrict__ tp = tile_buf + static_cast<size_t>(stage) * TILE * D;
 
         if constexpr (sizeof(T) == 8) {
-            if (safe)
+            if (DOT && dot)
+                tile_f64_dot<D, CKDE, R>(tp, nrm_buf + static_cast<size_t>(stage) * TILE, cnt, yt, at, tab, sum_j, sum_m);
+            else if (safe)
                 tile_f64<D, CKDE, true, R>(tp, cnt, yt, tab, sum_j, sum_m);
             else
                 tile_f64<D, CKDE, false, R>(tp, cnt, yt, tab, sum_j, sum_m);

@@ -8,7 +8,7 @@ namespace pbn {
 template <int D, bool CKDE>
 static cudaError_t launch_one(const PairJob* jobs, int n_jobs, long long total_units, long long upb, int grid,
                               const double* tab, cudaStream_t stream) {
-    constexpr size_t smem = kStages * pair_tile<PBN_T>(D) * D * sizeof(PBN_T) + 64 + exp_tab_smem_bytes<PBN_T>();
+    constexpr size_t smem = kStages * (pair_tile<PBN_T>(D) * D * sizeof(PBN_T) + pair_nrm_bytes<PBN_T>(D)) + 64 + exp_tab_smem_bytes<PBN_T>();
     static bool configured = false;  // per instantiation; attribute is per device function
     auto kern = pair_kernel<PBN_T, D, CKDE>;
     if (!configured || true) {

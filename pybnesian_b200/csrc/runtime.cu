@@ -180,7 +180,8 @@ __global__ void cov_tile_kernel(ColPtrs cols, Vec32 mean, int d, int ntile_side,
 // device kernels: whitening  y = W (x - mu), AoS output
 // ------------------------------------------------------------------------------------
 template <typename T>
-__global__ void whiten_kernel(const __grid_constant__ WhitenParams P, T* __restrict__ out, float* __restrict__ bound) {
+__global__ void whiten_kernel(const __grid_constant__ WhitenParams P, T* __restrict__ out, float* __restrict__ bound,
+                              double* __restrict__ nrm) {
     int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     float mx = 0.f;
     if (r < P.n) {
@@ -189,13 +190,16 @@ __global__ void whiten_kernel(const __grid_constant__ WhitenParams P, T* __restr
         const int d = P.d;
         for (int c = 0; c < d; ++c) x[c] = static_cast<double>(static_cast<const T*>(P.cols.p[c])[rr]) - P.mu[c];
         int w = 0;
+        double nn = 0;
         for (int i = 0; i < d; ++i) {
             double s = 0;
             for (int k = 0; k <= i; ++k) s = fma(P.W[w++], x[k], s);
             out[r * d + i] = static_cast<T>(s);
+            if (i < P.dn) nn = fma(-s, s, nn);
             float a = fabsf(static_cast<float>(s));
             mx = (a > mx || a != a) ? (a != a ? INFINITY : a) : mx;  // NaN counts as unbounded
         }
+        if (nrm) nrm[r] = nn;
     }
     // max |coordinate| of the launch (non-negative floats order like their bit patterns)
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -431,7 +435,7 @@ std::string var_list(const int* cols, int d) {
 }
 
 int whiten_raw_launch(pbn_ctx* ctx, const pbn_table* tbl, const int* cols_io, int d, pbn_rows rows, const double* Wfull,
-                      const double* mu, void* out, float* bound) {
+                      const double* mu, void* out, float* bound, double* nrm, int dn) {
     WhitenParams P;
     memset(&P, 0, sizeof(P));
     for (int i = 0; i < d; ++i) P.cols.p[i] = col_ptr(tbl, cols_io[i]);
@@ -440,6 +444,7 @@ int whiten_raw_launch(pbn_ctx* ctx, const pbn_table* tbl, const int* cols_io, in
         for (int j = 0; j <= i; ++j) P.W[w++] = Wfull[i * d + j];
     for (int i = 0; i < d; ++i) P.mu[i] = mu[i];
     P.d = d;
+    P.dn = nrm ? dn : 0;
     P.b0 = rows.b0;
     P.n0 = rows.e0 - rows.b0;
     P.b1 = rows.b1;
@@ -448,19 +453,19 @@ int whiten_raw_launch(pbn_ctx* ctx, const pbn_table* tbl, const int* cols_io, in
     const int threads = 256;
     int blocks = (int)((P.n + threads - 1) / threads);
     if (tbl->dtype == PBN_F64)
-        whiten_kernel<double><<<blocks, threads, 0, ctx->stream>>>(P, static_cast<double*>(out), bound);
+        whiten_kernel<double><<<blocks, threads, 0, ctx->stream>>>(P, static_cast<double*>(out), bound, nrm);
     else
-        whiten_kernel<float><<<blocks, threads, 0, ctx->stream>>>(P, static_cast<float*>(out), bound);
+        whiten_kernel<float><<<blocks, threads, 0, ctx->stream>>>(P, static_cast<float*>(out), bound, nullptr);
     ctx->launches++;
     PBN_CUDA_TRY(cudaGetLastError());
     return PBN_OK;
 }
 
 static int whiten_launch(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* tbl, const int* cols, pbn_rows rows, void* out,
-                         float* bound) {
+                         float* bound, double* nrm) {
     int pc[PBN_MAX_DIM];
     for (int i = 0; i < k->d; ++i) pc[i] = cols[k->perm[i]];
-    return whiten_raw_launch(ctx, tbl, pc, k->d, rows, k->W, k->mu, out, bound);
+    return whiten_raw_launch(ctx, tbl, pc, k->d, rows, k->W, k->mu, out, bound, nrm, k->ckde ? k->d - 1 : k->d);
 }
 
 double unit_scale(int dtype) {  // kernel exponent units per natural-log unit of -s/2
@@ -512,12 +517,15 @@ static int fit_impl(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, 
     int tile = k->dtype == PBN_F64 ? pbn::pair_tile_f64(d) : pbn::pair_tile_f32(d);
     int64_t n_pad = ((n + tile - 1) / tile) * tile + 16;
     size_t ybytes = ((size_t)n_pad * d * elem_size(k->dtype) + 255) / 256 * 256;
-    cudaError_t e = cudaMallocAsync(&k->y, ybytes + 256, ctx->stream);
+    // row norms for the dot-product form of the pair kernel (f64 fast path only)
+    size_t nbytes = (k->dtype == PBN_F64 && d <= 8) ? ((size_t)n_pad * sizeof(double) + 255) / 256 * 256 : 0;
+    cudaError_t e = cudaMallocAsync(&k->y, ybytes + 256 + nbytes, ctx->stream);
     if (e != cudaSuccess) { delete k; PBN_CUDA_TRY(e); }
-    e = cudaMemsetAsync(k->y, 0, ybytes + 256, ctx->stream);
+    e = cudaMemsetAsync(k->y, 0, ybytes + 256 + nbytes, ctx->stream);
     if (e != cudaSuccess) { cudaFreeAsync(k->y, ctx->stream); delete k; PBN_CUDA_TRY(e); }
     k->d_bound = reinterpret_cast<float*>(static_cast<char*>(k->y) + ybytes);
-    rc = whiten_launch(ctx, k, tbl, cols, rows, k->y, k->d_bound);
+    k->nrm = nbytes ? reinterpret_cast<double*>(static_cast<char*>(k->y) + ybytes + 256) : nullptr;
+    rc = whiten_launch(ctx, k, tbl, cols, rows, k->y, k->d_bound, k->nrm);
     if (rc != PBN_OK) { cudaFreeAsync(k->y, ctx->stream); delete k; return rc; }
     *out = k;
     return PBN_OK;
@@ -548,10 +556,12 @@ static int logl_impl(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, cons
 
     void* ytest = nullptr;
     size_t ytbytes = ((size_t)m * d * es + 255) / 256 * 256;
-    PBN_CUDA_TRY(cudaMallocAsync(&ytest, ytbytes + 256, st));
+    const size_t tnbytes = k->nrm ? ((size_t)m * sizeof(double) + 255) / 256 * 256 : 0;
+    PBN_CUDA_TRY(cudaMallocAsync(&ytest, ytbytes + 256 + tnbytes, st));
     float* bound_test = reinterpret_cast<float*>(static_cast<char*>(ytest) + ytbytes);
+    double* nrm_test = tnbytes ? reinterpret_cast<double*>(static_cast<char*>(ytest) + ytbytes + 256) : nullptr;
     PBN_CUDA_TRY(cudaMemsetAsync(bound_test, 0, 256, st));
-    PBN_TRY(whiten_launch(ctx, k, test, cols, rows, ytest, bound_test));
+    PBN_TRY(whiten_launch(ctx, k, test, cols, rows, ytest, bound_test, nrm_test));
 
     double* out = d_out_logl;
     bool own_out = false;
@@ -586,6 +596,8 @@ static int logl_impl(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, cons
         job.part = part;
         job.bound_train = k->d_bound;
         job.bound_test = bound_test;
+        job.train_nrm = k->nrm;
+        job.test_nrm = nrm_test;
         job.n_train = k->n;
         job.m = m;
         job.m_pad = m_pad;
