@@ -214,6 +214,29 @@ typedef struct pbn_cv_item {
 int pbn_cv_scores(pbn_ctx* ctx, pbn_cv* cv, const pbn_cv_item* items, int n_items, int fold_begin, int fold_end,
                   double* scores, int* status);
 
+/* ---- hybrid factors: one base factor per configuration of the discrete parents -----------------------
+ * factors::discrete::discrete_slice_indices (factors/discrete/discrete_indices.cpp:166-201) with
+ * discrete_indices (discrete_indices.hpp:52-124): codes[v][r] is the dictionary index of discrete variable v
+ * at row r (Arrow DictionaryArray indices widened to int32), valid[r] != 0 marks rows that take part (NULL =
+ * all rows; the reference uses the combined validity bitmap of the discrete variables).  The configuration of
+ * a row is sum_v codes[v][r] * strides[v]; order_out receives the participating row ids grouped by
+ * configuration, ascending inside each group (the reference's per-configuration Int32 index arrays laid end
+ * to end), offsets_out[c] .. offsets_out[c + 1] delimits configuration c (num_factors + 1 values).  Host
+ * only, integer, bit-exact.  PBN_ERR_ARG if a configuration index falls outside [0, num_factors). */
+int pbn_discrete_slices(const int32_t* const* codes, const int32_t* strides, int nvars, int64_t nrows,
+                        const uint8_t* valid, int num_factors, int32_t* order_out, int64_t* offsets_out);
+/* DataFrame::take (arrow::compute::Take, used once per configuration per call by DiscreteAdaptator::fit /
+ * logl / slogl, factors/discrete/DiscreteAdaptator.hpp:243,264,312): gathers rows indices[0..n) of every
+ * column of a resident table into a new resident table, on the device. */
+int pbn_table_take(pbn_ctx* ctx, const pbn_table* tbl, const int32_t* indices, int64_t n, pbn_table** out);
+/* DiscreteAdaptator<CKDE>::logl / slogl (DiscreteAdaptator.hpp:259-325) over a table stored in
+ * configuration-major order: job j evaluates kdes[j] on the row range rows[j] of `test`.  All jobs share ONE
+ * whitening launch and ONE multi-job pair-kernel launch.  kdes[j] == NULL (configuration without a fitted
+ * factor) yields NaN rows and a zero sum.  out_logl (host, sum of the range sizes, job-major) and out_slogl
+ * (host, n_jobs sums, to be added by the caller in configuration order) may each be NULL. */
+int pbn_kde_logl_multi(pbn_ctx* ctx, const pbn_kde* const* kdes, int n_jobs, const pbn_table* test, const int* cols,
+                       const pbn_rows* rows, double* out_logl, double* out_slogl);
+
 /* ---- host-side integer logic that must match libstdc++ bit for bit -----------------------------------
  * ArcOperatorSet::find_max_indegree (learning/operators/operators.hpp:489-497): std::sort of the persistent
  * candidate index vector by delta, descending (unstable: ties resolve as in the reference). */

@@ -9,6 +9,7 @@ from .dataset import DataFrame, CrossValidation, HoldOut
 from .kde import BandwidthSelector, NormalReferenceRule, ScottsBandwidth, UCV, UCVScorer, KDE, ProductKDE
 from .factors import (Factor, FactorType, CKDE, CKDEType, LinearGaussianCPD, LinearGaussianCPDType,
                       UnknownFactorType)
+from .hybrid import Assignment, DiscreteFactor, DiscreteFactorType, HCKDE, CLinearGaussianCPD
 from .models import (Dag, BayesianNetwork, BayesianNetworkType, GaussianNetwork, GaussianNetworkType, KDENetwork,
                      KDENetworkType, SemiparametricBN, SemiparametricBNType)
 from .scores import (Args, Kwargs, Arguments, Score, ValidatedScore, CVLikelihood, HoldoutLikelihood,

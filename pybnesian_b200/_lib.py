@@ -26,7 +26,7 @@ EXPORTS = [
     "pbn_ucv_score_from_sums", "pbn_lg_fit", "pbn_lg_logl", "pbn_cv_split", "pbn_holdout_split", "pbn_cv_create", "pbn_cv_free", "pbn_cv_table",
     "pbn_cv_folds", "pbn_cv_train_moments", "pbn_cv_scores", "pbn_sort_desc", "pbn_intset_new", "pbn_intset_clone",
     "pbn_intset_free", "pbn_intset_insert", "pbn_intset_erase", "pbn_intset_clear", "pbn_intset_contains",
-    "pbn_intset_size", "pbn_intset_list",
+    "pbn_intset_size", "pbn_intset_list", "pbn_discrete_slices", "pbn_table_take", "pbn_kde_logl_multi",
 ]
 PBN_MAX_DIM = 32
 FACTOR_CKDE, FACTOR_LINEAR_GAUSSIAN = 0, 1
@@ -132,6 +132,10 @@ def lib():
         L.pbn_intset_contains.argtypes = [vp, ci]
         L.pbn_intset_size.argtypes = [vp]
         L.pbn_intset_list.argtypes = [vp, ip]
+        L.pbn_discrete_slices.argtypes = [ctypes.POINTER(i32p), i32p, ci, i64, ctypes.POINTER(ctypes.c_uint8), ci, i32p,
+                                          ctypes.POINTER(i64)]
+        L.pbn_table_take.argtypes = [vp, vp, i32p, i64, ctypes.POINTER(vp)]
+        L.pbn_kde_logl_multi.argtypes = [vp, ctypes.POINTER(vp), ci, vp, ip, ctypes.POINTER(Rows), dp, dp]
         L.pbn_ctx_set_timing.argtypes = [vp, ci]
         L.pbn_ctx_pair_kernel_time.argtypes = [vp, dp, ctypes.POINTER(i64), ctypes.POINTER(i64), ci]
         _lib = L

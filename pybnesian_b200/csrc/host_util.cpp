@@ -48,6 +48,32 @@ int pbn_cv_split(int32_t* indices, int64_t n, int k, uint32_t seed, int32_t* lim
     return PBN_OK;
 }
 
+// factors::discrete::discrete_slice_indices (factors/discrete/discrete_indices.cpp:166-201): a counting sort
+// of the participating rows by configuration index; rows keep ascending order inside a configuration.
+int pbn_discrete_slices(const int32_t* const* codes, const int32_t* strides, int nvars, int64_t nrows,
+                        const uint8_t* valid, int num_factors, int32_t* order_out, int64_t* offsets_out) {
+    if ((nvars > 0 && (!codes || !strides)) || !offsets_out || (nrows > 0 && !order_out))
+        return pbn_set_error(PBN_ERR_ARG, "null argument");
+    if (nvars < 0 || nrows < 0 || num_factors < 1) return pbn_set_error(PBN_ERR_ARG, "invalid slice arguments");
+    std::vector<int32_t> conf(nrows, -1);
+    std::vector<int64_t> count(num_factors + 1, 0);
+    for (int64_t r = 0; r < nrows; ++r) {
+        if (valid && !valid[r]) continue;
+        int32_t idx = 0;
+        for (int v = 0; v < nvars; ++v) idx += codes[v][r] * strides[v];
+        if (idx < 0 || idx >= num_factors)
+            return pbn_set_error(PBN_ERR_ARG, "discrete configuration index out of range at row " + std::to_string(r));
+        conf[r] = idx;
+        ++count[idx + 1];
+    }
+    offsets_out[0] = 0;
+    for (int c = 0; c < num_factors; ++c) offsets_out[c + 1] = offsets_out[c] + count[c + 1];
+    std::vector<int64_t> pos(offsets_out, offsets_out + num_factors);
+    for (int64_t r = 0; r < nrows; ++r)
+        if (conf[r] >= 0) order_out[pos[conf[r]]++] = static_cast<int32_t>(r);
+    return PBN_OK;
+}
+
 // HoldOut (dataset/holdout_adaptator.hpp:17-70)
 int pbn_holdout_split(int32_t* indices, int64_t n, double test_ratio, uint32_t seed, int32_t* n_train) {
     if (!indices || !n_train) return pbn_set_error(PBN_ERR_ARG, "null argument");

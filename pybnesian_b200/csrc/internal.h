@@ -125,6 +125,13 @@ int moments_impl(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, pbn
 int whiten_raw_launch(pbn_ctx* ctx, const pbn_table* tbl, const int* cols_internal_order, int d, pbn_rows rows,
                       const double* Wfull, const double* mu, void* out, float* bound, double* nrm = nullptr, int dn = 0);
 
+// whitened rows of `rows` of `tbl` under a fitted KDE's whitening matrix (cols in the KDE's variable order)
+int pbn_whiten_kde(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* tbl, const int* cols, pbn_rows rows, void* out,
+                   float* bound, double* nrm);
+// one fitted KDE against one row range (runtime.cu); device and/or host outputs, each may be null
+int pbn_logl_impl(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const int* cols, pbn_rows rows,
+                  double* d_out_logl, double* d_out_slogl, double* h_out_logl, double* h_out_slogl);
+
 // MLE<LinearGaussianCPD> from centred moments (cv.cu): Cm = sum (x_a - mean_a)(x_b - mean_b), column-major d x d,
 // variable first; writes beta[p + 1], returns the variance.
 double lg_fit_from_moments(int64_t rows, int p, const double* mean, const double* Cm, double* beta);

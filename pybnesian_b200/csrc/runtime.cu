@@ -461,7 +461,7 @@ int whiten_raw_launch(pbn_ctx* ctx, const pbn_table* tbl, const int* cols_io, in
     return PBN_OK;
 }
 
-static int whiten_launch(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* tbl, const int* cols, pbn_rows rows, void* out,
+int pbn_whiten_kde(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* tbl, const int* cols, pbn_rows rows, void* out,
                          float* bound, double* nrm) {
     int pc[PBN_MAX_DIM];
     for (int i = 0; i < k->d; ++i) pc[i] = cols[k->perm[i]];
@@ -525,13 +525,13 @@ static int fit_impl(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, 
     if (e != cudaSuccess) { cudaFreeAsync(k->y, ctx->stream); delete k; PBN_CUDA_TRY(e); }
     k->d_bound = reinterpret_cast<float*>(static_cast<char*>(k->y) + ybytes);
     k->nrm = nbytes ? reinterpret_cast<double*>(static_cast<char*>(k->y) + ybytes + 256) : nullptr;
-    rc = whiten_launch(ctx, k, tbl, cols, rows, k->y, k->d_bound, k->nrm);
+    rc = pbn_whiten_kde(ctx, k, tbl, cols, rows, k->y, k->d_bound, k->nrm);
     if (rc != PBN_OK) { cudaFreeAsync(k->y, ctx->stream); delete k; return rc; }
     *out = k;
     return PBN_OK;
 }
 
-static int logl_impl(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const int* cols, pbn_rows rows,
+int pbn_logl_impl(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const int* cols, pbn_rows rows,
                      double* d_out_logl, double* d_out_slogl, double* h_out_logl, double* h_out_slogl) {
     if (!ctx || !k) return set_error(PBN_ERR_ARG, "null argument");
     PBN_TRY(check_cols(test, cols, k->d));
@@ -561,7 +561,7 @@ static int logl_impl(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, cons
     float* bound_test = reinterpret_cast<float*>(static_cast<char*>(ytest) + ytbytes);
     double* nrm_test = tnbytes ? reinterpret_cast<double*>(static_cast<char*>(ytest) + ytbytes + 256) : nullptr;
     PBN_CUDA_TRY(cudaMemsetAsync(bound_test, 0, 256, st));
-    PBN_TRY(whiten_launch(ctx, k, test, cols, rows, ytest, bound_test, nrm_test));
+    PBN_TRY(pbn_whiten_kde(ctx, k, test, cols, rows, ytest, bound_test, nrm_test));
 
     double* out = d_out_logl;
     bool own_out = false;
@@ -1020,11 +1020,11 @@ double pbn_kde_lognorm(const pbn_kde* k) { return k ? k->lognorm_joint : 0.0; }
 
 int pbn_kde_logl(pbn_ctx* ctx, const pbn_kde* kde, const pbn_table* test, const int* cols, pbn_rows rows, double* out_logl,
                  double* out_slogl) {
-    return logl_impl(ctx, kde, test, cols, rows, nullptr, nullptr, out_logl, out_slogl);
+    return pbn_logl_impl(ctx, kde, test, cols, rows, nullptr, nullptr, out_logl, out_slogl);
 }
 int pbn_kde_logl_device(pbn_ctx* ctx, const pbn_kde* kde, const pbn_table* test, const int* cols, pbn_rows rows,
                         double* d_out_logl, double* d_out_slogl) {
-    return logl_impl(ctx, kde, test, cols, rows, d_out_logl, d_out_slogl, nullptr, nullptr);
+    return pbn_logl_impl(ctx, kde, test, cols, rows, d_out_logl, d_out_slogl, nullptr, nullptr);
 }
 
 int pbn_device_alloc(pbn_ctx* ctx, int64_t bytes, void** out) {

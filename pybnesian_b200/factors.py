@@ -89,6 +89,10 @@ class LinearGaussianCPDType(FactorType):
     """factors/continuous/LinearGaussianCPD.hpp:18-58."""
 
     def new_factor(self, model, variable, evidence, *args, **kwargs):
+        # LinearGaussianCPD.cpp:33-57: a discrete parent makes it a conditional linear Gaussian
+        from . import hybrid
+        if any(model.node_type(e) == hybrid.DiscreteFactorType() for e in evidence):
+            return hybrid.CLinearGaussianCPD(variable, evidence, *args, **kwargs)
         return LinearGaussianCPD(variable, evidence, *args, **kwargs)
 
     def __str__(self):
@@ -211,9 +215,12 @@ class LinearGaussianCPD(Factor):
 
 
 class CKDEType(FactorType):
-    """factors/continuous/CKDE.hpp:17-60, CKDE.cpp:15-41 (discrete parents -> HCKDE is out of scope)."""
+    """factors/continuous/CKDE.hpp:17-60, CKDE.cpp:15-41 (a discrete parent makes it an HCKDE)."""
 
     def new_factor(self, model, variable, evidence, *args, **kwargs):
+        from . import hybrid
+        if any(model.node_type(e) == hybrid.DiscreteFactorType() for e in evidence):
+            return hybrid.HCKDE(variable, evidence, *args, **kwargs)
         return CKDE(variable, evidence, *args, **kwargs)
 
     def __str__(self):

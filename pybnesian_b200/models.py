@@ -18,6 +18,7 @@ import pyarrow as pa
 from ._lib import check, lib
 from .dataset import DataFrame
 from .factors import (CKDEType, FactorType, LinearGaussianCPDType, UnknownFactorType)
+from .hybrid import DiscreteFactorType
 
 
 class _IntSet:
@@ -338,7 +339,7 @@ def _is_continuous(datatype):
 
 
 class SemiparametricBNType(BayesianNetworkType):
-    """models/SemiparametricBN.hpp:17-136 (discrete nodes are SURVEY §8 row f1: not on this path)."""
+    """models/SemiparametricBN.hpp:17-136."""
 
     def is_homogeneous(self):
         return False
@@ -349,13 +350,21 @@ class SemiparametricBNType(BayesianNetworkType):
     def data_default_node_type(self, datatype):
         if _is_continuous(datatype):
             return [LinearGaussianCPDType(), CKDEType()]
+        if pa.types.is_dictionary(datatype):
+            return [DiscreteFactorType()]
         raise ValueError("Data type [" + str(datatype) + "] not compatible with SemiparametricBNType")
 
     def compatible_node_type(self, model, variable, node_type):
-        return node_type == LinearGaussianCPDType() or node_type == CKDEType()
+        # SemiparametricBN.hpp:62-78: a discrete node may only have discrete parents
+        if node_type not in (LinearGaussianCPDType(), CKDEType(), DiscreteFactorType()):
+            return False
+        if node_type == DiscreteFactorType():
+            return all(model.node_type(p) == DiscreteFactorType() for p in model.parents(variable))
+        return True
 
     def can_have_arc(self, model, source, target):
-        return True  # only discrete targets restrict their parents (SemiparametricBN.hpp:96-101)
+        # SemiparametricBN.hpp:96-101
+        return model.node_type(target) != DiscreteFactorType() or model.node_type(source) == DiscreteFactorType()
 
     def alternative_node_type(self, model, variable):
         t = model.node_type(variable)
@@ -592,9 +601,14 @@ class BayesianNetwork:
         frame = DataFrame.wrap(df)
         if not self._cpds:
             self._cpds = [None] * self.num_nodes()
+        # BayesianNetwork.hpp:965-976: nodes without a type take their data's default type first, so that
+        # new_factor sees the (possibly discrete) types of the parents
+        if not self._type.is_homogeneous():
+            self.force_type_whitelist([(n, self.underlying_node_type(frame, n)) for n in self.nodes()
+                                       if self.node_type(n) == UnknownFactorType()])
         for node in self.nodes():
             i = self.index(node)
-            t = self.underlying_node_type(frame, node)
+            t = self.node_type(node)
             parents = self.parents(node)
             cur = self._cpds[i]
             if cur is None or cur.type() != t or cur.evidence() != parents:

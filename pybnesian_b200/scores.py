@@ -12,6 +12,7 @@ over the ranks and the per-candidate scores are summed with one all-reduce.
 import ctypes
 
 import numpy as np
+import pyarrow as pa
 
 from . import _lib, parallel
 from ._lib import CVItem, check, lib
@@ -176,6 +177,9 @@ class _FoldScorer:
         """(dtype code, CVItem fields) if the request can run inside pbn_cv_scores, else None."""
         variables = [variable] + list(evidence)
         if len(variables) > _lib.PBN_MAX_DIM:
+            return None
+        # categorical columns (discrete nodes, HCKDE / CLinearGaussianCPD families): generic loop
+        if any(pa.types.is_dictionary(self.frame._col(v).type) for v in variables if v in self.frame._index):
             return None
         if node_type == LinearGaussianCPDType():
             if args or kwargs:
