@@ -237,6 +237,36 @@ int pbn_table_take(pbn_ctx* ctx, const pbn_table* tbl, const int32_t* indices, i
 int pbn_kde_logl_multi(pbn_ctx* ctx, const pbn_kde* const* kdes, int n_jobs, const pbn_table* test, const int* cols,
                        const pbn_rows* rows, double* out_logl, double* out_slogl);
 
+/* ---- the other side of a fitted CKDE: cdf and sampling --------------------------------
+ * CKDE::cdf (factors/continuous/CKDE.hpp:506-728; kernels univariate_normal_cdf, normal_cdf, conditional_means_*,
+ * exp_elementwise, product_elementwise, division_elementwise, KDE.cl.src:241-245, 366-468):
+ *   cdf(t) = sum_i w_ti Phi((x_t - mean_ti) / sqrt(cond_var)) / sum_i w_ti,   w_ti = marginal kernel weight,
+ * (1/N sum_i Phi((x_t - x_i) / h) without evidence) in ONE fused launch over train x test tiles; `kde` must come
+ * from pbn_ckde_fit, `cols` as in pbn_kde_logl.  out: rows.count doubles (host).  As in the reference the weights are
+ * not max-shifted: a row whose weights all underflow in the data's dtype yields NaN. */
+int pbn_ckde_cdf(pbn_ctx* ctx, const pbn_kde* kde, const pbn_table* test, const int* cols, pbn_rows rows, double* out);
+/* CKDE::_sample_indices_from_weights (CKDE.hpp:402-504; kernels accum_sum_mat_cols, add_accum_sum_mat_cols,
+ * normalize_accum_sum_mat_cols, find_random_indices, KDE.cl.src:254-364): for every evidence row t the training row
+ * i with  cum_t[i] <= u_t * S_t < cum_t[i+1]  (cum = running sum of the marginal kernel weights, S_t their total),
+ * N-1 if there is none.  ev_cols: the d-1 evidence columns in the CKDE's evidence order; random_prob: rows.count
+ * host values in the data's dtype.  Two launches: weight totals, then an in-order scan that stops early. */
+int pbn_ckde_sample_indices(pbn_ctx* ctx, const pbn_kde* kde, const pbn_table* evidence, const int* ev_cols, pbn_rows rows,
+                            const void* random_prob, int32_t* out_idx);
+/* CKDE::sample (CKDE.cpp:97-121, CKDE.hpp:289-400).  H = joint bandwidth (d x d, variable first); train/train_cols/
+ * train_rows = the table the CKDE was fitted on (raw training values of the sampled rows are gathered on the device);
+ * evidence/ev_cols = resident evidence table (first n rows are used), ev_host[j] = the same n evidence values on the
+ * host in the data's dtype (both ignored when d == 1).  The random streams are the reference's: std::mt19937{seed}
+ * with libstdc++'s uniform_int / uniform_real / normal distributions.  out: n values in the data's dtype; idx_out
+ * (may be NULL): the sampled training rows. */
+int pbn_ckde_sample(pbn_ctx* ctx, const pbn_kde* kde, const double* H, const pbn_table* train, const int* train_cols,
+                    pbn_rows train_rows, const pbn_table* evidence, const int* ev_cols, const void* const* ev_host,
+                    int64_t n, uint32_t seed, void* out, int32_t* idx_out);
+/* LinearGaussianCPD::sample (factors/continuous/LinearGaussianCPD.cpp:317-372): host only, bit-exact with the
+ * reference (std::mt19937{seed}, std::normal_distribution<double>(beta[0], sqrt(variance)), then beta[j+1] *
+ * evidence_j added column by column).  ev[j]: n host values of dtype ev_dtype. */
+int pbn_lg_sample(const double* beta, double variance, int p, const void* const* ev, int ev_dtype, int64_t n,
+                  uint32_t seed, double* out);
+
 /* ---- host-side integer logic that must match libstdc++ bit for bit -----------------------------------
  * ArcOperatorSet::find_max_indegree (learning/operators/operators.hpp:489-497): std::sort of the persistent
  * candidate index vector by delta, descending (unstable: ties resolve as in the reference). */

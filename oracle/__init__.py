@@ -335,3 +335,119 @@ def ref_product_kde_logl(train, test, hdiag):
                                    _c_int(_dtype_code(train)), _c_vp(sd.ctypes.data), ctypes.c_double(lognorm),
                                    _dptr(out), ctypes.byref(s))
     return out, s.value
+
+
+# ---- CKDE::cdf / CKDE::sample, LinearGaussianCPD::cdf / sample ----------------------
+def ckde_cdf(train, test, Hjoint):
+    """CKDE(col 0 | cols 1..)::cdf of every test row (float64 out; reference arithmetic in the data's dtype)."""
+    train, test = _fmat(train), _fmat(test)
+    assert train.dtype == test.dtype and train.shape[1] == test.shape[1]
+    N, d = train.shape
+    m = test.shape[0]
+    H = np.asfortranarray(np.asarray(Hjoint, dtype=np.float64).reshape(d, d))
+    out = np.empty(m)
+    lib().orc_ckde_cdf(_c_vp(train.ctypes.data), _c_i64(N), _c_vp(test.ctypes.data), _c_i64(m), _c_int(d),
+                       _c_int(_dtype_code(train)), _dptr(H), _dptr(out))
+    return out
+
+
+def ckde_sample(train, Hjoint, evidence, n, seed):
+    """CKDE::sample(n, evidence, seed): (samples in the data's dtype, sampled training-row indices)."""
+    train = _fmat(train)
+    N, d = train.shape
+    H = np.asfortranarray(np.asarray(Hjoint, dtype=np.float64).reshape(d, d))
+    out = np.empty(n, dtype=train.dtype)
+    idx = np.empty(n, dtype=np.int32)
+    ev = None
+    if d > 1:
+        ev = _fmat(evidence)
+        assert ev.dtype == train.dtype and ev.shape == (n, d - 1)
+    lib().orc_ckde_sample(_c_vp(train.ctypes.data), _c_i64(N), _c_int(d), _c_int(_dtype_code(train)), _dptr(H),
+                          _c_vp(ev.ctypes.data) if ev is not None else None, _c_i64(n), ctypes.c_uint32(seed),
+                          _c_vp(out.ctypes.data), idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)))
+    return out, idx
+
+
+def uniform_real(n, seed, dtype):
+    """n draws of std::uniform_real_distribution<T>(0, 1) from std::mt19937{seed}."""
+    out = np.empty(n, dtype=dtype)
+    lib().orc_uniform_real(_c_i64(n), ctypes.c_uint32(seed), _c_int(_dtype_code(out)), _c_vp(out.ctypes.data))
+    return out
+
+
+def ckde_sample_indices(mtrain, etest, Hmarg, random_prob):
+    """Training-row index drawn for every evidence row from the marginal kernel weights."""
+    mtrain, etest = _fmat(mtrain), _fmat(etest)
+    N, p = mtrain.shape
+    n = etest.shape[0]
+    H = np.asfortranarray(np.asarray(Hmarg, dtype=np.float64).reshape(p, p))
+    rp = np.ascontiguousarray(random_prob, dtype=mtrain.dtype)
+    out = np.empty(n, dtype=np.int32)
+    st = lib().orc_ckde_sample_indices(_c_vp(mtrain.ctypes.data), _c_i64(N), _c_vp(etest.ctypes.data), _c_i64(n),
+                                       _c_int(p), _c_int(_dtype_code(mtrain)), _dptr(H), _c_vp(rp.ctypes.data),
+                                       out.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)))
+    if st:
+        raise SingularCovariance("bandwidth not positive definite")
+    return out
+
+
+def lg_sample(beta, variance, evidence_cols, n, seed):
+    """LinearGaussianCPD::sample: float64 samples; evidence_cols = list of n-vectors (float64 or float32)."""
+    beta = np.ascontiguousarray(beta, dtype=np.float64)
+    cols = [np.ascontiguousarray(c) for c in evidence_cols]
+    code = _dtype_code(cols[0]) if cols else 0
+    ptrs = (_c_vp * max(1, len(cols)))(*[c.ctypes.data for c in cols])
+    out = np.empty(n)
+    lib().orc_lg_sample(_dptr(beta), ctypes.c_double(variance), _c_int(len(cols)), ptrs, _c_int(code), _c_i64(n),
+                        ctypes.c_uint32(seed), _dptr(out))
+    return out
+
+
+def _cond_params(Hjoint):
+    """Host-side quantities of CKDE::_cdf_multivariate / _sample_multivariate (CKDE.hpp:346-360, 594-616)."""
+    H = np.asarray(Hjoint, dtype=np.float64)
+    Lm = np.linalg.cholesky(H[1:, 1:])
+    inv = np.linalg.solve(Lm, np.eye(Lm.shape[0]))
+    R = inv @ H[1:, 0]
+    return Lm, R @ inv, H[0, 0] - R @ R
+
+
+def ref_ckde_cdf(train, test, Hjoint):
+    """CKDE::cdf computed by the reference's kernels (host enqueue logic restated in ref_driver.cpp)."""
+    train, test = _fmat(train), _fmat(test)
+    N, d = train.shape
+    m = test.shape[0]
+    T = train.dtype
+    H = np.asarray(Hjoint, dtype=np.float64).reshape(d, d)
+    out = np.empty(m)
+    x = np.ascontiguousarray(test[:, 0])
+    if d == 1:
+        _reflib().ref_ckde_cdf(_c_vp(train.ctypes.data), _c_int(N), _c_vp(x.ctypes.data), None, _c_int(m), _c_int(1),
+                               _c_int(_dtype_code(train)), None, ctypes.c_double(0.0), None,
+                               ctypes.c_double(float(T.type(1.0 / np.sqrt(H[0, 0])))), _dptr(out))
+        return out
+    Lm, transform, cond_var = _cond_params(H)
+    _, lognorm = kde_prepare(H[1:, 1:], N)
+    et = np.asfortranarray(test[:, 1:])
+    Lt = np.asfortranarray(Lm.astype(T))
+    tr = np.ascontiguousarray(transform.astype(T))
+    _reflib().ref_ckde_cdf(_c_vp(train.ctypes.data), _c_int(N), _c_vp(x.ctypes.data), _c_vp(et.ctypes.data), _c_int(m),
+                           _c_int(d), _c_int(_dtype_code(train)), _c_vp(Lt.ctypes.data),
+                           ctypes.c_double(lognorm + np.log(float(N))), _c_vp(tr.ctypes.data),
+                           ctypes.c_double(float(T.type(1.0 / np.sqrt(cond_var)))), _dptr(out))
+    return out
+
+
+def ref_ckde_sample_indices(mtrain, etest, Hmarg, random_prob):
+    mtrain, etest = _fmat(mtrain), _fmat(etest)
+    N, p = mtrain.shape
+    n = etest.shape[0]
+    L, lognorm = kde_prepare(np.asarray(Hmarg, dtype=np.float64).reshape(p, p), N)
+    Lt = np.asfortranarray(L.astype(mtrain.dtype))
+    rp = np.ascontiguousarray(random_prob, dtype=mtrain.dtype)
+    out = np.empty(n, dtype=np.int32)
+    _reflib().ref_ckde_sample_indices(_c_vp(mtrain.ctypes.data), _c_int(N), _c_vp(etest.ctypes.data), _c_int(n),
+                                      _c_int(p), _c_int(_dtype_code(mtrain)), _c_vp(Lt.ctypes.data),
+                                      ctypes.c_double(lognorm), _c_vp(rp.ctypes.data),
+                                      out.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)))
+    return out

@@ -716,6 +716,176 @@ int cv_score_T(const T* X, int64_t n_rows, int d, const int32_t* indices, const 
     return 0;
 }
 
+// ---- CKDE::cdf and CKDE::sample ----------------------------------------------------
+template <typename T> inline T erfc_T(T x);
+template <> inline double erfc_T<double>(double x) { return std::erfc(x); }
+template <> inline float erfc_T<float>(float x) { return erfcf(x); }
+template <typename T> inline T sqrt1_2();
+template <> inline double sqrt1_2<double>() { return 0.70710678118654752440; }
+template <> inline float sqrt1_2<float>() { return 0.70710678118654752440f; }
+
+// The quantities CKDE::_cdf_multivariate / _sample_multivariate derive from the two bandwidths on the host
+// (factors/continuous/CKDE.hpp:346-360, 586-600): L_marg = chol(H[1:,1:]), R = L_marg^-1 H[1:,0],
+// cond_var = H[0,0] - |R|^2, transform = R^T L_marg^-1 (all in double).
+struct CondParams {
+    std::vector<double> Lm, transform;
+    double cond_var;
+};
+inline CondParams cond_params(const double* Hj, int d) {
+    int p = d - 1;
+    CondParams c;
+    std::vector<double> Hm(p * p);
+    for (int i = 0; i < p; ++i)
+        for (int j = 0; j < p; ++j) Hm[i + j * p] = Hj[(i + 1) + (j + 1) * d];
+    c.Lm.resize(p * p);
+    cholesky_lower(Hm.data(), p, c.Lm.data());
+    std::vector<double> inv(p * p, 0.0);  // L_marg^-1 by forward substitution on the identity (column-major)
+    for (int col = 0; col < p; ++col)
+        for (int i = 0; i < p; ++i) {
+            double v = (i == col) ? 1.0 : 0.0;
+            for (int k = 0; k < i; ++k) v -= c.Lm[i + k * p] * inv[k + col * p];
+            inv[i + col * p] = v / c.Lm[i + i * p];
+        }
+    std::vector<double> R(p, 0.0);
+    for (int i = 0; i < p; ++i)
+        for (int k = 0; k < p; ++k) R[i] += inv[i + k * p] * Hj[(k + 1) + 0 * d];
+    double nrm = 0;
+    for (int i = 0; i < p; ++i) nrm += R[i] * R[i];
+    c.cond_var = Hj[0] - nrm;
+    c.transform.assign(p, 0.0);
+    for (int j = 0; j < p; ++j)
+        for (int i = 0; i < p; ++i) c.transform[j] += R[i] * inv[i + j * p];
+    return c;
+}
+
+// CKDE::_cdf (factors/continuous/CKDE.hpp:506-556), _cdf_univariate (558-592), _cdf_multivariate (594-728)
+// with kernels univariate_normal_cdf, normal_cdf, conditional_means_*, exp_elementwise, product_elementwise,
+// division_elementwise (kde/opencl_kernels/KDE.cl.src:241-245, 366-468) and sum_cols_offset
+// (opencl/opencl_config.hpp:399-515).  train / test are column-major with the variable in column 0.
+// The weights are NOT max-shifted in the reference: a test row whose weights all underflow yields 0/0 = NaN.
+template <typename T>
+void ckde_cdf_T(const T* train, int64_t N, const T* test, int64_t m, int d, const double* Hj, T* out) {
+    if (d == 1) {
+        T inv_std = static_cast<T>(1.0 / std::sqrt(Hj[0]));
+        T inv_N = static_cast<T>(1.0 / N);
+#pragma omp parallel
+        {
+            std::vector<T> col(N);
+#pragma omp for schedule(dynamic, 8)
+            for (int64_t t = 0; t < m; ++t) {
+                col.resize(N);
+                for (int64_t i = 0; i < N; ++i)
+                    col[i] = static_cast<T>(inv_N * (0.5 * erfc_T<T>(sqrt1_2<T>() * inv_std * -(test[t] - train[i]))));
+                out[t] = tree_reduce<T, false>(col);
+            }
+        }
+        return;
+    }
+    const int p = d - 1;
+    CondParams cp = cond_params(Hj, d);
+    std::vector<T> Lt(p * p), tr(p);
+    for (int i = 0; i < p * p; ++i) Lt[i] = static_cast<T>(cp.Lm[i]);
+    for (int j = 0; j < p; ++j) tr[j] = static_cast<T>(cp.transform[j]);
+    T lognorm = static_cast<T>(lognorm_const(cp.Lm.data(), p, N) + std::log(static_cast<double>(N)));
+    T inv_std = static_cast<T>(1.0 / std::sqrt(cp.cond_var));
+    const T* mtrain = train + N;  // evidence columns
+    const T* mtest = test + m;
+#pragma omp parallel
+    {
+        std::vector<T> W(N), mu(N), delta(p);
+#pragma omp for schedule(dynamic, 8)
+        for (int64_t t = 0; t < m; ++t) {
+            W.resize(N);
+            mu.resize(N);
+            for (int64_t i = 0; i < N; ++i) {
+                W[i] = exp_T<T>(pair_logl<T>(mtrain, N, i, mtest, m, t, p, Lt.data(), lognorm, delta.data()));
+                T mean = train[i];
+                for (int j = 0; j < p; ++j)
+                    mean += tr[j] * (mtest[t + static_cast<size_t>(j) * m] - mtrain[i + static_cast<size_t>(j) * N]);
+                T c = static_cast<T>(0.5 * erfc_T<T>(sqrt1_2<T>() * inv_std * (mean - test[t])));
+                mu[i] = c * W[i];
+            }
+            T sumW = tree_reduce<T, false>(W);
+            T num = tree_reduce<T, false>(mu);
+            out[t] = num / sumW;
+        }
+    }
+}
+
+// CKDE::_sample_indices_from_weights (factors/continuous/CKDE.hpp:402-504): weights exp(logl_marg(i, t)) in T,
+// exclusive prefix sum over the training rows (accum_sum_cols, opencl_config.hpp:539-579, KDE.cl.src:254-338),
+// rows 1.. divided by the total (normalize_accum_sum_mat_cols, 340-348), index i in [0, N-2] with
+// cum[i] <= u < cum[i+1], default N-1 (find_random_indices, 351-364).  The reference's scan is a work-group
+// tree whose association depends on the device's work-group size; here the prefix sum is sequential, so an
+// index can differ only when u falls within rounding error of a boundary.
+template <typename T>
+void ckde_sample_indices_T(const T* mtrain, int64_t N, const T* etest, int64_t n, int p, const double* Lm,
+                           const T* random_prob, int32_t* out) {
+    std::vector<T> Lt(p * p);
+    for (int i = 0; i < p * p; ++i) Lt[i] = static_cast<T>(Lm[i]);
+    T lognorm = static_cast<T>(lognorm_const(Lm, p, N));
+#pragma omp parallel
+    {
+        std::vector<T> cum(N + 1), delta(p);
+#pragma omp for schedule(dynamic, 8)
+        for (int64_t t = 0; t < n; ++t) {
+            cum[0] = 0;
+            for (int64_t i = 0; i < N; ++i)
+                cum[i + 1] = cum[i] + exp_T<T>(pair_logl<T>(mtrain, N, i, etest, n, t, p, Lt.data(), lognorm, delta.data()));
+            T total = cum[N];
+            for (int64_t i = 1; i < N; ++i) cum[i] /= total;
+            T u = random_prob[t];
+            int32_t idx = static_cast<int32_t>(N - 1);
+            for (int64_t i = 0; i + 1 < N; ++i)
+                if (cum[i] <= u && u < cum[i + 1]) idx = static_cast<int32_t>(i);
+            out[t] = idx;
+        }
+    }
+}
+
+// CKDE::_sample / _sample_multivariate (factors/continuous/CKDE.hpp:289-400).  `evidence` is n x p column-major
+// (ignored for d == 1).  libstdc++'s std::mt19937 / uniform_int_distribution / uniform_real_distribution /
+// normal_distribution are the reference's generators (it is built with the same standard library).
+template <typename T>
+void ckde_sample_T(const T* train, int64_t N, int d, const double* Hj, const T* evidence, int64_t n, uint32_t seed,
+                   T* out, int32_t* idx_out) {
+    if (d == 1) {
+        std::mt19937 rng{seed};
+        std::uniform_int_distribution<> uniform(0, static_cast<int>(N - 1));
+        std::normal_distribution<T> normal(0, std::sqrt(Hj[0]));
+        for (int64_t i = 0; i < n; ++i) {
+            auto index = uniform(rng);
+            if (idx_out) idx_out[i] = index;
+            out[i] = train[index] + normal(rng);
+        }
+        return;
+    }
+    const int p = d - 1;
+    std::vector<T> random_prob(n);
+    std::mt19937 rng{seed};
+    std::uniform_real_distribution<T> uniform(0, 1);
+    for (int64_t i = 0; i < n; ++i) random_prob[i] = uniform(rng);
+    CondParams cp = cond_params(Hj, d);
+    std::vector<int32_t> idx(n);
+    ckde_sample_indices_T<T>(train + N, N, evidence, n, p, cp.Lm.data(), random_prob.data(), idx.data());
+    if (idx_out) std::copy(idx.begin(), idx.end(), idx_out);
+    std::vector<T> tr(p);
+    for (int j = 0; j < p; ++j) tr[j] = static_cast<T>(cp.transform[j]);
+    // cond_mean = evidence_substract * transform (Eigen row-times-vector product in T), CKDE.hpp:375-384
+    std::vector<T> cond_mean(n);
+    for (int64_t i = 0; i < n; ++i) {
+        T acc = 0;
+        for (int j = 0; j < p; ++j)
+            acc += (evidence[i + static_cast<size_t>(j) * n] - train[idx[i] + static_cast<size_t>(j + 1) * N]) * tr[j];
+        cond_mean[i] = acc;
+    }
+    std::normal_distribution<T> normal(0, std::sqrt(cp.cond_var));
+    for (int64_t i = 0; i < n; ++i) {
+        cond_mean[i] += train[idx[i]] + normal(rng);
+        out[i] = cond_mean[i];
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -939,6 +1109,72 @@ void orc_sort_desc(int* idx, int64_t n, const double* delta) {
     std::vector<int> v(idx, idx + n);
     std::sort(v.begin(), v.end(), [&delta](auto i1, auto i2) { return delta[i1] > delta[i2]; });
     std::copy(v.begin(), v.end(), idx);
+}
+
+
+// ---- CKDE::cdf / CKDE::sample, LinearGaussianCPD::cdf / sample ----
+int orc_ckde_cdf(const void* train, int64_t N, const void* test, int64_t m, int d, int dtype, const double* Hjoint,
+                 double* out) {
+    if (dtype == 0) {
+        ckde_cdf_T<double>(static_cast<const double*>(train), N, static_cast<const double*>(test), m, d, Hjoint, out);
+    } else {
+        std::vector<float> r(m);
+        ckde_cdf_T<float>(static_cast<const float*>(train), N, static_cast<const float*>(test), m, d, Hjoint, r.data());
+        for (int64_t i = 0; i < m; ++i) out[i] = r[i];
+    }
+    return 0;
+}
+
+// out: n values of the data's dtype; idx_out (may be NULL): the sampled training-row indices
+int orc_ckde_sample(const void* train, int64_t N, int d, int dtype, const double* Hjoint, const void* evidence,
+                    int64_t n, uint32_t seed, void* out, int32_t* idx_out) {
+    if (dtype == 0)
+        ckde_sample_T<double>(static_cast<const double*>(train), N, d, Hjoint, static_cast<const double*>(evidence), n,
+                              seed, static_cast<double*>(out), idx_out);
+    else
+        ckde_sample_T<float>(static_cast<const float*>(train), N, d, Hjoint, static_cast<const float*>(evidence), n, seed,
+                             static_cast<float*>(out), idx_out);
+    return 0;
+}
+
+// the uniform draws of CKDE::_sample_multivariate (CKDE.hpp:336-341), for tests of the index kernel alone
+int orc_uniform_real(int64_t n, uint32_t seed, int dtype, void* out) {
+    std::mt19937 rng{seed};
+    if (dtype == 0) {
+        std::uniform_real_distribution<double> u(0, 1);
+        for (int64_t i = 0; i < n; ++i) static_cast<double*>(out)[i] = u(rng);
+    } else {
+        std::uniform_real_distribution<float> u(0, 1);
+        for (int64_t i = 0; i < n; ++i) static_cast<float*>(out)[i] = u(rng);
+    }
+    return 0;
+}
+
+int orc_ckde_sample_indices(const void* mtrain, int64_t N, const void* etest, int64_t n, int p, int dtype,
+                            const double* Hmarg, const void* random_prob, int32_t* out) {
+    std::vector<double> Lm(p * p);
+    if (!cholesky_lower(Hmarg, p, Lm.data())) return 1;
+    if (dtype == 0)
+        ckde_sample_indices_T<double>(static_cast<const double*>(mtrain), N, static_cast<const double*>(etest), n, p,
+                                      Lm.data(), static_cast<const double*>(random_prob), out);
+    else
+        ckde_sample_indices_T<float>(static_cast<const float*>(mtrain), N, static_cast<const float*>(etest), n, p,
+                                     Lm.data(), static_cast<const float*>(random_prob), out);
+    return 0;
+}
+
+// LinearGaussianCPD::sample (factors/continuous/LinearGaussianCPD.cpp:317-372): always double output;
+// ev[j] is evidence column j (dtype of the evidence frame), beta[0] the intercept.
+int orc_lg_sample(const double* beta, double variance, int p, const void* const* ev, int ev_dtype, int64_t n,
+                  uint32_t seed, double* out) {
+    std::mt19937 rng{seed};
+    std::normal_distribution<> normal(beta[0], std::sqrt(variance));
+    for (int64_t i = 0; i < n; ++i) out[i] = normal(rng);
+    for (int j = 0; j < p; ++j)
+        for (int64_t i = 0; i < n; ++i)
+            out[i] += beta[j + 1] * (ev_dtype == 0 ? static_cast<const double*>(ev[j])[i]
+                                                    : static_cast<double>(static_cast<const float*>(ev[j])[i]));
+    return 0;
 }
 
 }  // extern "C"

@@ -105,6 +105,28 @@ int pbn_sort_desc(int32_t* idx, int64_t n, const double* delta) {
     return PBN_OK;
 }
 
+// LinearGaussianCPD::sample (factors/continuous/LinearGaussianCPD.cpp:317-372): the noise comes from
+// std::normal_distribution<double>(beta0, sqrt(variance)) on std::mt19937{seed}; the evidence terms are then
+// added column by column (double accumulation, float evidence widened per element).
+int pbn_lg_sample(const double* beta, double variance, int p, const void* const* ev, int ev_dtype, int64_t n,
+                  uint32_t seed, double* out) {
+    if (n < 0) return pbn_set_error(PBN_ERR_ARG, "n should be a non-negative number");
+    if (!beta || (n > 0 && !out) || (p > 0 && !ev)) return pbn_set_error(PBN_ERR_ARG, "null argument");
+    std::mt19937 rng{seed};
+    std::normal_distribution<> normal(beta[0], std::sqrt(variance));
+    for (int64_t i = 0; i < n; ++i) out[i] = normal(rng);
+    for (int j = 0; j < p; ++j) {
+        if (ev_dtype == PBN_F64) {
+            const double* e = static_cast<const double*>(ev[j]);
+            for (int64_t i = 0; i < n; ++i) out[i] += beta[j + 1] * e[i];
+        } else {
+            const float* e = static_cast<const float*>(ev[j]);
+            for (int64_t i = 0; i < n; ++i) out[i] += beta[j + 1] * e[i];
+        }
+    }
+    return PBN_OK;
+}
+
 // std::unordered_set<int>: DNode::m_parents / m_children (graph/graph_types.hpp:12-51).  The order in
 // which BayesianNetwork::parents() lists a node's parents is this container's iteration order.
 int pbn_intset_new(pbn_intset** out) {

@@ -14,6 +14,14 @@ from .kde import KDE, BandwidthSelector, NormalReferenceRule, _ARROW_TYPE, _fit_
 from ._lib import lib
 
 
+def _random_seed(seed):
+    """util::random_seed_arg (util/util_types.hpp:52-66): an unsigned 32-bit seed, std::random_device when absent."""
+    if seed is None:
+        import os
+        return int.from_bytes(os.urandom(4), "little")
+    return int(seed) & 0xFFFFFFFF
+
+
 class FactorType:
     """factors/factors.hpp:28-101.  Singletons compared by identity/hash like the reference."""
 
@@ -196,6 +204,51 @@ class LinearGaussianCPD(Factor):
     def slogl(self, df):
         return self._eval(df, False)[1]
 
+    def cdf(self, df):
+        """LinearGaussianCPD::cdf (LinearGaussianCPD.cpp:171-315): host arithmetic in the data's dtype,
+        0.5 erfc((mean - x) / (sqrt(2) sigma)); NaN at rows with a null."""
+        from scipy.special import erfc
+        self._check_fitted()
+        frame = DataFrame.wrap(df)
+        code = frame.dtype_code(self._variables, "compute cdf")
+        T = np.float64 if code == _lib.PBN_F64 else np.float32
+        cols, mask = frame.dense_columns(self._variables)
+        x = np.asarray(cols[0], dtype=T)
+        means = np.full(x.shape[0], T(self._beta[0]), dtype=T)
+        for j, c in enumerate(cols[1:], start=1):
+            means += T(self._beta[j]) * np.asarray(c, dtype=T)
+        inv_std = T(1.0 / np.sqrt(self._variance))
+        t = (0.5 * erfc((means - x) * inv_std * T(0.70710678118654752440))).astype(np.float64)
+        if mask is not None:
+            full = np.full(frame.num_rows, np.nan)
+            full[mask] = t
+            t = full
+        return t
+
+    def sample(self, n, evidence_values=None, seed=None):
+        """LinearGaussianCPD::sample (LinearGaussianCPD.cpp:317-372): always float64; the random stream is the
+        reference's (include/pbn_cuda.h: pbn_lg_sample)."""
+        import ctypes
+        import pyarrow as pa
+        from ._lib import check
+        if n < 0:
+            raise ValueError("n should be a non-negative number")
+        self._check_fitted()
+        seed = _random_seed(seed)
+        cols, code = [], _lib.PBN_F64
+        if self._evidence:
+            frame = DataFrame.wrap(evidence_values) if evidence_values is not None else None
+            if frame is None or not frame.has_columns(self._evidence):
+                raise ValueError("Evidence values not present for sampling.")
+            code = frame.dtype_code(self._evidence, "sample")
+            cols = [np.ascontiguousarray(frame.column_numpy(e)[:n]) for e in self._evidence]
+        out = np.empty(n)
+        dp = ctypes.POINTER(ctypes.c_double)
+        ptrs = (ctypes.c_void_p * max(1, len(cols)))(*[c.ctypes.data for c in cols])
+        check(lib().pbn_lg_sample(np.ascontiguousarray(self._beta).ctypes.data_as(dp), float(self._variance), len(cols),
+                                  ptrs, code, n, seed, out.ctypes.data_as(dp)))
+        return pa.array(out)
+
     def __getstate__(self):
         return (self._variable, self._evidence, self._fitted, self._beta, self._variance)
 
@@ -300,6 +353,65 @@ class CKDE(Factor):
         frame = DataFrame.wrap(df)
         self._check_test(frame)
         return _run_logl(self._handle, frame, self._variables, False, True)[1]
+
+    def cdf(self, df):
+        """CKDE::cdf (CKDE.cpp:123-140, CKDE.hpp:506-728): P(variable <= x | evidence) of every row, NaN at rows
+        with a null; one fused launch over train x test tiles (include/pbn_cuda.h: pbn_ckde_cdf)."""
+        import ctypes
+        from ._lib import check, int_array
+        frame = DataFrame.wrap(df)
+        self._check_test(frame)
+        tbl, cols, mask = frame.device_table(self._variables)
+        out = np.empty(tbl.nrows)
+        check(lib().pbn_ckde_cdf(tbl.ctx.handle, self._handle.handle, tbl.handle, int_array(cols), tbl.rows(),
+                                 out.ctypes.data_as(ctypes.POINTER(ctypes.c_double))))
+        if mask is not None:
+            full = np.full(frame.num_rows, np.nan)
+            full[mask] = out
+            out = full
+        return out
+
+    def sample(self, n, evidence_values=None, seed=None, _return_indices=False):
+        """CKDE::sample (CKDE.cpp:97-121, CKDE.hpp:289-504): a training instance is drawn with probability
+        proportional to its marginal kernel weight at the evidence (uniformly without evidence), then the variable is
+        drawn from the conditional Gaussian of that kernel.  Index selection runs on the device
+        (pbn_ckde_sample_indices); the random streams are the reference's.  Returns a pyarrow array of the training
+        dtype."""
+        import ctypes
+        import pyarrow as pa
+        from ._lib import check, int_array
+        from .dataset import DeviceTable, _NP_DTYPE
+        if n < 0:
+            raise ValueError("n should be a non-negative number")
+        self._check_fitted()
+        seed = _random_seed(seed)
+        npdt = _NP_DTYPE[self._dtype]
+        tbl, cols, rows = self._train
+        ev_tbl, ev_cols, ev_host, ev_ptrs = None, None, [], None
+        if self._evidence:
+            frame = DataFrame.wrap(evidence_values) if evidence_values is not None else None
+            if frame is None or not frame.has_columns(self._evidence):
+                raise ValueError("Evidence values not present for sampling.")
+            t = frame.same_type(self._evidence)
+            if t != _ARROW_TYPE[self._dtype]:
+                raise ValueError("Data type of evidence values (%s) is different from CKDE training data (%s)."
+                                 % (t, _ARROW_TYPE[self._dtype]))
+            if frame.num_rows < n:
+                raise ValueError("Evidence values not present for sampling.")
+            ev_host = [np.ascontiguousarray(frame.column_numpy(e)[:n], dtype=npdt) for e in self._evidence]
+            if n > 0:
+                ev_tbl = DeviceTable(tbl.ctx, ev_host, self._dtype)
+                ev_cols = int_array(list(range(len(ev_host))))
+            ev_ptrs = (ctypes.c_void_p * len(ev_host))(*[c.ctypes.data for c in ev_host])
+        out = np.empty(n, dtype=npdt)
+        idx = np.empty(n, dtype=np.int32)
+        H = np.asfortranarray(self._bandwidth, dtype=np.float64)
+        check(lib().pbn_ckde_sample(tbl.ctx.handle, self._handle.handle, H.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                    tbl.handle, int_array(cols), rows, ev_tbl.handle if ev_tbl is not None else None,
+                                    ev_cols, ev_ptrs, n, seed, out.ctypes.data_as(ctypes.c_void_p),
+                                    idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))))
+        arr = pa.array(out)
+        return (arr, idx) if _return_indices else arr
 
     def kde_joint(self):
         """The joint KDE over [variable] + evidence (CKDE.hpp:105-108)."""

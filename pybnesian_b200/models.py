@@ -83,6 +83,11 @@ class Dag:
         self._parents = [_IntSet() for _ in nodes]
         self._children = [_IntSet() for _ in nodes]
         self._arcs = set()
+        # ArcGraph::m_roots (generic_graph.hpp:979-993, 1185-1248): an unordered_set<int> whose iteration order
+        # (insertion / erase history) seeds the stack of topological_sort, hence the per-node seeds of sample()
+        self._roots = _IntSet()
+        for i in range(len(nodes)):
+            self._roots.insert(i)
         for s, t in (arcs or []):
             self.add_arc(s, t)
 
@@ -135,6 +140,8 @@ class Dag:
         return len(self._children[self.index(node)])
 
     def _add_arc_unsafe(self, s, t):
+        if t in self._roots:
+            self._roots.erase(t)
         self._arcs.add((s, t))
         self._parents[t].insert(s)
         self._children[s].insert(t)
@@ -143,6 +150,8 @@ class Dag:
         self._arcs.discard((s, t))
         self._parents[t].erase(s)
         self._children[s].erase(t)
+        if len(self._parents[t]) == 0:
+            self._roots.insert(t)
 
     def add_arc_unsafe(self, source, target):
         self._add_arc_unsafe(self.index(source), self.index(target))
@@ -220,7 +229,7 @@ class Dag:
 
     def topological_sort(self):
         indeg = [len(p) for p in self._parents]
-        stack = [i for i, d in enumerate(indeg) if d == 0]
+        stack = self._roots.list()  # DagImpl::topological_sort (generic_graph.hpp:2659-2708)
         order = []
         while stack:
             i = stack.pop()
@@ -240,6 +249,7 @@ class Dag:
         g._parents = [p.clone() for p in self._parents]  # unordered_set copy keeps the iteration order
         g._children = [c.clone() for c in self._children]
         g._arcs = set(self._arcs)
+        g._roots = self._roots.clone()
         return g
 
     def __getstate__(self):
@@ -628,6 +638,28 @@ class BayesianNetwork:
     def slogl(self, df):
         frame = DataFrame.wrap(df)
         return float(sum(self.cpd(node).slogl(frame) for node in self.nodes()))
+
+    def sample(self, n, seed=None, ordered=False):
+        """BNGeneric::sample (models/BayesianNetwork.hpp:1024-1065): ancestral sampling in topological order; node i of
+        the order is sampled with seed + i given the columns sampled so far.  Returns a pandas DataFrame (columns in
+        topological order, or in nodes() order when `ordered`)."""
+        import pyarrow as pa
+        from .factors import _random_seed
+        if n < 0:
+            raise ValueError("n should be a non-negative number")
+        if not self.fitted():
+            raise ValueError("Model not fitted.")
+        seed = _random_seed(seed)
+        names, arrays = [], []
+        for i, node in enumerate(self._g.topological_sort()):
+            parents = DataFrame(pa.RecordBatch.from_arrays(arrays, names=names)) if arrays else None
+            arr = self.cpd(node).sample(n, parents, (seed + i) & 0xFFFFFFFF)
+            names.append(node)
+            arrays.append(arr)
+        if ordered:
+            order = [names.index(v) for v in self.nodes()]
+            names, arrays = [names[j] for j in order], [arrays[j] for j in order]
+        return pa.RecordBatch.from_arrays(arrays, names=names).to_pandas()
 
     def clone(self):
         m = type(self).__new__(type(self))
