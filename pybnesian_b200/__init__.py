@@ -11,12 +11,12 @@ from .factors import (Factor, FactorType, CKDE, CKDEType, LinearGaussianCPD, Lin
                       UnknownFactorType)
 from .hybrid import Assignment, DiscreteFactor, DiscreteFactorType, HCKDE, CLinearGaussianCPD
 from .models import (Dag, BayesianNetwork, BayesianNetworkType, GaussianNetwork, GaussianNetworkType, KDENetwork,
-                     KDENetworkType, SemiparametricBN, SemiparametricBNType)
+                     KDENetworkType, SemiparametricBN, SemiparametricBNType, load)
 from .scores import (Args, Kwargs, Arguments, Score, ValidatedScore, CVLikelihood, HoldoutLikelihood,
                      ValidatedLikelihood)
 from .operators import (Operator, ArcOperator, AddArc, RemoveArc, FlipArc, ChangeNodeType, OperatorTabuSet,
                         LocalScoreCache, OperatorSet, ArcOperatorSet, ChangeNodeTypeSet, OperatorPool)
-from .hillclimbing import GreedyHillClimbing, Callback, hc
+from .hillclimbing import GreedyHillClimbing, Callback, SaveModel, hc
 from . import parallel
 
 __version__ = "0.1.0"

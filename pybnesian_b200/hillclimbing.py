@@ -23,6 +23,17 @@ class Callback:
         raise NotImplementedError
 
 
+class SaveModel(Callback):
+    """learning/algorithms/callbacks/save_model.hpp:8-22: saves the model of every iteration as
+    `folder_name/NNNNNN.pickle` (six digits, without the CPDs)."""
+
+    def __init__(self, folder_name):
+        self._folder_name = folder_name
+
+    def call(self, model, operator, score, iteration):
+        model.save("%s/%06d" % (self._folder_name, iteration), False)
+
+
 def _validation_delta_score(model, val_score, variables, current_local_scores):
     """hillclimbing.hpp:46-60."""
     prev = 0.0

@@ -667,22 +667,85 @@ class BayesianNetwork:
         m._g = self._g.clone()
         m._node_types = list(self._node_types)
         m._cpds = list(self._cpds)
+        m._include_cpd = self.include_cpd()
         return m
 
+    def check_compatible_cpd(self, cpd):
+        """BNGeneric::check_compatible_cpd (models/BayesianNetwork.hpp:863-912)."""
+        if not self.contains_node(cpd.variable()):
+            raise ValueError("CPD defined on variable which is not present in the model:\n" + str(cpd))
+        evidence = cpd.evidence()
+        for ev in evidence:
+            if not self.contains_node(ev):
+                raise ValueError("Evidence variable " + ev + " is not present in the model:\n" + str(cpd))
+        pa = self.parents(cpd.variable())
+        if len(pa) != len(evidence) or set(pa) != set(evidence):
+            raise ValueError("CPD do not have the model's parent set as evidence:\n" + str(cpd) + "\nParents: ["
+                             + ", ".join(pa) + "]")
+        t = self.node_type(cpd.variable())
+        if t != UnknownFactorType() and cpd.type() != t:
+            raise ValueError("CPD defined with a different node type.\nExpected node type: " + str(t)
+                             + "\nCPD node type: " + str(cpd.type()))
+
+    def add_cpds(self, cpds):
+        """BNGeneric::add_cpds (models/BayesianNetwork.hpp:914-940)."""
+        cpds = list(cpds)
+        for cpd in cpds:
+            self.check_compatible_cpd(cpd)
+        if not self._type.is_homogeneous():
+            self.force_type_whitelist([(c.variable(), c.type()) for c in cpds
+                                       if self.node_type(c.variable()) == UnknownFactorType()])
+        if not self._cpds:
+            self._cpds = [None] * self.num_nodes()
+        for cpd in cpds:
+            self._cpds[self.index(cpd.variable())] = cpd
+
+    def include_cpd(self):
+        return getattr(self, "_include_cpd", False)
+
+    def set_include_cpd(self, include_cpd):
+        self._include_cpd = bool(include_cpd)
+
     def save(self, filename, include_cpd=False):
+        """BNGeneric::save (models/BayesianNetwork.hpp:1127-1137, util/pickle.hpp): pickle into `filename`.pickle;
+        the CPDs travel only when include_cpd (GPU-resident factors are read back through their own __getstate__)."""
+        self._include_cpd = bool(include_cpd)
         if not filename.endswith(".pickle"):
             filename += ".pickle"
         with open(filename, "wb") as f:
-            pickle.dump(self, f)
+            pickle.dump(self, f, protocol=2)
 
+    # BNGeneric::__getstate__ (models/BayesianNetwork.hpp:1139-1167): (graph, type, node types, include_cpd, cpds)
     def __getstate__(self):
-        return (self._type, self._g.nodes(), self._g.arcs(), list(self._node_types))
+        cpds = []
+        if self.include_cpd() and self._cpds:
+            for node in self.nodes():
+                c = self._cpds[self.index(node)]
+                if c is not None:
+                    try:
+                        self.check_compatible_cpd(c)
+                        cpds.append(c)
+                    except ValueError:
+                        pass
+        node_types = []
+        if not self._type.is_homogeneous():
+            node_types = [(n, self._node_types[self.index(n)]) for n in self.nodes()
+                          if self._node_types[self.index(n)] != UnknownFactorType()]
+        return (self._type, self._g.nodes(), self._g.arcs(), node_types, self.include_cpd(), cpds)
 
     def __setstate__(self, t):
         self._type = t[0]
         self._g = Dag(t[1], t[2])
-        self._node_types = list(t[3])
         self._cpds = []
+        if len(t) == 4:  # pickles written before the CPDs were part of the state
+            self._node_types = list(t[3])
+            return
+        self._node_types = [] if self._type.is_homogeneous() else [UnknownFactorType() for _ in t[1]]
+        for name, ft in t[3]:
+            self._node_types[self.index(name)] = ft
+        self._include_cpd = bool(t[4])
+        if t[4] and t[5]:
+            self.add_cpds(t[5])
 
     def __str__(self):
         return type(self).__name__ + " with %d nodes and %d arcs" % (self.num_nodes(), self.num_arcs())
@@ -710,3 +773,9 @@ class SemiparametricBN(BayesianNetwork):
                 all(isinstance(a, tuple) and len(a) == 2 and isinstance(a[1], FactorType) for a in arcs):
             arcs, node_types = None, arcs
         super().__init__(SemiparametricBNType(), nodes, arcs, node_types, graph)
+
+
+def load(filename):
+    """pybnesian.load (util/pickle.hpp, lib.cpp:38-43): the object saved by any `.save()` of this package."""
+    with open(filename, "rb") as f:
+        return pickle.load(f)
