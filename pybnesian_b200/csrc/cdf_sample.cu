@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(kWThreads) weight_kernel(const __grid_constant
     int t0 = MODE == 2 ? 0 : blockIdx.y * P.tiles_per_split;
     int t1 = MODE == 2 ? P.n_train_tiles : min(t0 + P.tiles_per_split, P.n_train_tiles);
 
-    if (sizeof(T) == 8 && DN > 0) exp_tab_fill(tab, P.tab, tid, kWThreads);
+    if (sizeof(T) == 8 && (DN > 0 || MODE == 0)) exp_tab_fill(tab, P.tab, tid, kWThreads);
     if (tid == 0) {
         for (int s = 0; s < kWStages; ++s) mbar_init(&bar[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -158,8 +158,13 @@ __global__ void __launch_bounds__(kWThreads) weight_kernel(const __grid_constant
                     w = st * pg;
                 }
                 if (MODE == 0) {
-                    double z = (yt[DN] - tp[i * D + DN]) * inv_c;
-                    sp = fma(w, normcdf(z), sp);
+                    // w Phi(z) from the JOINT kernel value E = w exp(-z^2/2) = 2^(acc - dl^2) and the tail factor
+                    // t g(u) (normal_tail_tg): one more table exp2, one MUFU reciprocal, one degree-18 Horner
+                    double dl = yt[DN] - tp[i * D + DN];
+                    double st2;
+                    double pg2 = exp2_tab<true>(fma(-dl, dl, acc), tab, st2);
+                    double q = (st2 * pg2) * normal_tail_tg(fabs(dl) * inv_c);
+                    sp += (dl < 0.0) ? q : (w - q);
                 }
                 sw += w;
                 if (MODE == 2) {
@@ -187,8 +192,12 @@ __global__ void __launch_bounds__(kWThreads) weight_kernel(const __grid_constant
                 float w = 1.f;
                 if (DN > 0) asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(w) : "f"(acc));
                 if (MODE == 0) {
-                    float z = (yt[DN] - tp[i * D + DN]) * inv_c;
-                    fp = fmaf(w, normcdff(z), fp);
+                    float dl = yt[DN] - tp[i * D + DN];
+                    float e;
+                    float accj = fmaf(-dl, dl, acc);
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(accj));
+                    float q = e * normal_tail_tg_f(fabsf(dl) * inv_c);
+                    fp += (dl < 0.f) ? q : (w - q);
                 }
                 fw += w;
                 if (MODE == 2) {
@@ -254,6 +263,51 @@ __global__ void cdf_finalize_kernel(WFinal F) {
         return;
     }
     F.out[row] = sp / sw;
+}
+
+// Same epilogue for the fused pair kernel's partial-sum slots (stream-K: one slot per CTA that touched the test tile,
+// added in fixed order; see finalize_kernel in runtime.cu).  Slot block 0 holds sum w Phi, block 1 holds sum w.
+struct CdfPairFinal {
+    const PairJob* job;
+    long long upb;
+    int tb;
+    int has_evidence;
+    double thresh;
+    long long n;
+    double* out;
+    int* flagged;
+    int* n_flagged;
+};
+
+__global__ void cdf_finalize_pair_kernel(CdfPairFinal F) {
+    const PairJob jb = *F.job;
+    long long row = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (row >= jb.m) return;
+    long long tt = row / F.tb;
+    long long ustart = jb.unit_begin + tt * jb.n_train_tiles;
+    int first = (int)(ustart / F.upb);
+    int last = (int)((ustart + jb.n_train_tiles - 1) / F.upb);
+    int ns = last - first + 1;
+    double sp = 0, sw = 0;
+    for (int s = 0; s < ns; ++s) {
+        sp += jb.part[(long long)s * jb.m_pad + row];
+        if (F.has_evidence) sw += jb.part[((long long)jb.slots + s) * jb.m_pad + row];
+    }
+    if (!F.has_evidence) {
+        F.out[row] = sp / (double)F.n;
+        return;
+    }
+    if (sw == sw && !(sw >= F.thresh)) {
+        int slot = atomicAdd(F.n_flagged, 1);
+        F.flagged[slot] = (int)row;
+        return;
+    }
+    F.out[row] = sp / sw;
+}
+
+__global__ void write_cdf_job_kernel(PairJob j, PairJob* dst, int* zero_counter) {
+    *dst = j;
+    *zero_counter = 0;
 }
 
 __global__ void sample_target_kernel(WFinal F) {
@@ -351,16 +405,20 @@ cudaError_t launch_weight_one(const WParams& P, dim3 grid, cudaStream_t st) {
 
 template <typename T, int MODE>
 cudaError_t launch_weight(const WParams& P, dim3 grid, cudaStream_t st) {
-    switch (P.d) {
-        case 1: return launch_weight_one<T, 1, MODE>(P, grid, st);
-        case 2: return launch_weight_one<T, 2, MODE>(P, grid, st);
-        case 3: return launch_weight_one<T, 3, MODE>(P, grid, st);
-        case 4: return launch_weight_one<T, 4, MODE>(P, grid, st);
-        case 5: return launch_weight_one<T, 5, MODE>(P, grid, st);
-        case 6: return launch_weight_one<T, 6, MODE>(P, grid, st);
-        case 7: return launch_weight_one<T, 7, MODE>(P, grid, st);
-        case 8: return launch_weight_one<T, 8, MODE>(P, grid, st);
-        default: return launch_weight_one<T, 0, MODE>(P, grid, st);  // runtime dimension (9..32)
+    if constexpr (MODE == 0) {
+        // families of up to 8 variables take the CDF mode of the fused pair kernel (pair_kernel.cuh)
+        return launch_weight_one<T, 0, MODE>(P, grid, st);
+    } else {
+        switch (P.d) {
+            case 2: return launch_weight_one<T, 2, MODE>(P, grid, st);
+            case 3: return launch_weight_one<T, 3, MODE>(P, grid, st);
+            case 4: return launch_weight_one<T, 4, MODE>(P, grid, st);
+            case 5: return launch_weight_one<T, 5, MODE>(P, grid, st);
+            case 6: return launch_weight_one<T, 6, MODE>(P, grid, st);
+            case 7: return launch_weight_one<T, 7, MODE>(P, grid, st);
+            case 8: return launch_weight_one<T, 8, MODE>(P, grid, st);
+            default: return launch_weight_one<T, 0, MODE>(P, grid, st);  // runtime dimension (9..32)
+        }
     }
 }
 
@@ -509,54 +567,129 @@ int pbn_ckde_cdf(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const in
     if (m == 0) return PBN_OK;
     const bool f64 = k->dtype == PBN_F64;
     const size_t es = elem_size(k->dtype);
+    const double inv_c = 1.0 / sqrt(0.5 * unit_scale(k->dtype));
+    const bool fast = d <= 8;
+
     void* ytest = nullptr;
-    PBN_CUDA_TRY(cudaMallocAsync(&ytest, (size_t)m * d * es, st));
-    PBN_TRY(pbn_whiten_kde(ctx, k, test, cols, rows, ytest, nullptr, nullptr));
-    WParams P;
-    memset(&P, 0, sizeof(P));
-    P.train = k->y;
-    P.test = ytest;
-    P.n = k->n;
-    P.m = m;
-    P.m_pad = (m + 31) / 32 * 32;
-    P.d = d;
-    P.dt = d;
-    const double c = sqrt(0.5 * unit_scale(k->dtype));
-    P.inv_c = 1.0 / c;
-    P.tab = ctx->d_exp_tab;
-    plan_splits(ctx, k->n, m, P);
-    double* part = nullptr;
+    size_t ytbytes = ((size_t)m * d * es + 255) / 256 * 256;
+    const size_t tnbytes = (fast && k->nrm) ? ((size_t)m * sizeof(double) + 255) / 256 * 256 : 0;
+    PBN_CUDA_TRY(cudaMallocAsync(&ytest, ytbytes + 256 + tnbytes, st));
+    float* bound_test = reinterpret_cast<float*>(static_cast<char*>(ytest) + ytbytes);
+    double* nrm_test = tnbytes ? reinterpret_cast<double*>(static_cast<char*>(ytest) + ytbytes + 256) : nullptr;
+    PBN_CUDA_TRY(cudaMemsetAsync(bound_test, 0, 256, st));
+    PBN_TRY(pbn_whiten_kde(ctx, k, test, cols, rows, ytest, bound_test, nrm_test));
+
     double* d_out = nullptr;
     int* flagged = nullptr;
-    PBN_CUDA_TRY(cudaMallocAsync(&part, (size_t)2 * P.n_splits * P.m_pad * sizeof(double), st));
     PBN_CUDA_TRY(cudaMallocAsync(&d_out, (size_t)m * sizeof(double), st));
     PBN_CUDA_TRY(cudaMallocAsync(&flagged, ((size_t)m + 1) * sizeof(int), st));
     int* n_flagged = flagged + m;
-    zero_int_kernel<<<1, 1, 0, st>>>(n_flagged);
-    ctx->launches++;
-    P.part = part;
-    dim3 grid((unsigned)((m + kWThreads - 1) / kWThreads), (unsigned)P.n_splits);
-    {
-        cudaError_t le = f64 ? launch_weight<double, 0>(P, grid, st) : launch_weight<float, 0>(P, grid, st);
+    double* part = nullptr;
+    PairJob* d_job = nullptr;
+
+    if (fast) {
+        // CDF mode of the fused pair kernel: same stream-K schedule and partial-sum slots as pbn_logl_impl
+        const int TILE = f64 ? pbn::pair_tile_f64(d) : pbn::pair_tile_f32(d);
+        const int TB = f64 ? pbn::pair_tb_f64() : pbn::pair_tb_f32();
+        int n_test_tiles = (int)((m + TB - 1) / TB);
+        int n_train_tiles = (int)((k->n + TILE - 1) / TILE);
+        long long U = (long long)n_test_tiles * n_train_tiles;
+        int grid = (int)std::min<long long>(U, ctx->sm_count * 2);
+        long long upb = (U + grid - 1) / grid;
+        grid = (int)((U + upb - 1) / upb);
+        int slots = (int)std::min<long long>((n_train_tiles + upb - 1) / upb + 1, grid);
+        long long m_pad = (m + 31) / 32 * 32;
+        PBN_CUDA_TRY(cudaMallocAsync(&part, (size_t)2 * slots * m_pad * sizeof(double), st));
+        PBN_CUDA_TRY(cudaMallocAsync(&d_job, sizeof(PairJob) + 16, st));
+        PairJob job;
+        memset(&job, 0, sizeof(job));
+        job.train = k->y;
+        job.test = ytest;
+        job.part = part;
+        job.bound_train = k->d_bound;
+        job.bound_test = bound_test;
+        job.train_nrm = k->nrm;
+        job.test_nrm = nrm_test;
+        job.n_train = k->n;
+        job.m = m;
+        job.m_pad = m_pad;
+        job.unit_begin = 0;
+        job.n_train_tiles = n_train_tiles;
+        job.n_test_tiles = n_test_tiles;
+        job.slots = slots;
+        write_cdf_job_kernel<<<1, 1, 0, st>>>(job, d_job, n_flagged);
+        ctx->launches++;
+        PBN_CUDA_TRY(cudaGetLastError());
+        cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+        if (ctx->timing) {
+            PBN_CUDA_TRY(cudaEventCreate(&ev0));
+            PBN_CUDA_TRY(cudaEventCreate(&ev1));
+            PBN_CUDA_TRY(cudaEventRecord(ev0, st));
+        }
+        cudaError_t le = f64 ? pbn::launch_cdf_f64(d, d_job, 1, U, upb, grid, ctx->d_exp_tab, inv_c, st)
+                             : pbn::launch_cdf_f32(d, d_job, 1, U, upb, grid, ctx->d_exp_tab, inv_c, st);
+        ctx->launches++;
         PBN_CUDA_TRY(le);
+        if (ctx->timing) {
+            PBN_CUDA_TRY(cudaEventRecord(ev1, st));
+            ctx->timed.emplace_back(ev0, ev1);
+            ctx->pair_units += (int64_t)k->n * m;
+        }
+        CdfPairFinal F;
+        F.job = d_job;
+        F.upb = upb;
+        F.tb = TB;
+        F.has_evidence = d > 1 ? 1 : 0;
+        F.thresh = f64 ? ldexp(1.0, -900) : ldexp(1.0, -64);
+        F.n = k->n;
+        F.out = d_out;
+        F.flagged = flagged;
+        F.n_flagged = n_flagged;
+        cdf_finalize_pair_kernel<<<(int)((m + 255) / 256), 256, 0, st>>>(F);
+        ctx->launches++;
+        PBN_CUDA_TRY(cudaGetLastError());
+    } else {
+        // wide families (9..32 variables): runtime-dimension weight kernel, test tiles x training splits
+        WParams P;
+        memset(&P, 0, sizeof(P));
+        P.train = k->y;
+        P.test = ytest;
+        P.n = k->n;
+        P.m = m;
+        P.m_pad = (m + 31) / 32 * 32;
+        P.d = d;
+        P.dt = d;
+        P.inv_c = inv_c;
+        P.tab = ctx->d_exp_tab;
+        plan_splits(ctx, k->n, m, P);
+        PBN_CUDA_TRY(cudaMallocAsync(&part, (size_t)2 * P.n_splits * P.m_pad * sizeof(double), st));
+        zero_int_kernel<<<1, 1, 0, st>>>(n_flagged);
+        ctx->launches++;
+        P.part = part;
+        dim3 grid((unsigned)((m + kWThreads - 1) / kWThreads), (unsigned)P.n_splits);
+        {
+            cudaError_t le = f64 ? launch_weight<double, 0>(P, grid, st) : launch_weight<float, 0>(P, grid, st);
+            PBN_CUDA_TRY(le);
+        }
+        ctx->launches++;
+        WFinal F;
+        memset(&F, 0, sizeof(F));
+        F.part = part;
+        F.m = m;
+        F.m_pad = P.m_pad;
+        F.n = k->n;
+        F.n_splits = P.n_splits;
+        F.has_evidence = 1;
+        F.thresh = f64 ? ldexp(1.0, -900) : ldexp(1.0, -64);
+        F.out = d_out;
+        F.flagged = flagged;
+        F.n_flagged = n_flagged;
+        cdf_finalize_kernel<<<(int)((m + 255) / 256), 256, 0, st>>>(F);
+        ctx->launches++;
+        PBN_CUDA_TRY(cudaGetLastError());
     }
-    ctx->launches++;
-    WFinal F;
-    memset(&F, 0, sizeof(F));
-    F.part = part;
-    F.m = m;
-    F.m_pad = P.m_pad;
-    F.n = k->n;
-    F.n_splits = P.n_splits;
-    F.has_evidence = d > 1 ? 1 : 0;
-    F.thresh = f64 ? ldexp(1.0, -900) : ldexp(1.0, -64);
-    F.out = d_out;
-    F.flagged = flagged;
-    F.n_flagged = n_flagged;
-    cdf_finalize_kernel<<<(int)((m + 255) / 256), 256, 0, st>>>(F);
-    ctx->launches++;
-    PBN_CUDA_TRY(cudaGetLastError());
     if (d > 1) {
+        // rows whose unshifted weight sum underflowed: the reference's arithmetic, term by term
         CdfRowParams R;
         R.train = k->y;
         R.test = ytest;
@@ -564,7 +697,7 @@ int pbn_ckde_cdf(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const in
         R.d = d;
         R.u2ln = 1.0 / unit_scale(k->dtype);
         R.c0 = k->lognorm_marg + log((double)k->n);
-        R.inv_c = P.inv_c;
+        R.inv_c = inv_c;
         R.rows = flagged;
         R.count_ptr = n_flagged;
         R.out = d_out;
@@ -581,6 +714,7 @@ int pbn_ckde_cdf(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const in
     ctx->d2h += m * 8 + 4;
     ctx->last_fallback_rows = nf;
     PBN_CUDA_TRY(cudaFreeAsync(part, st));
+    if (d_job) PBN_CUDA_TRY(cudaFreeAsync(d_job, st));
     PBN_CUDA_TRY(cudaFreeAsync(d_out, st));
     PBN_CUDA_TRY(cudaFreeAsync(flagged, st));
     PBN_CUDA_TRY(cudaFreeAsync(ytest, st));

@@ -141,6 +141,10 @@ cudaError_t launch_pair_f64(int D, bool ckde, const PairJob* jobs, int n_jobs, l
                             int grid, const double* tab, cudaStream_t stream);
 cudaError_t launch_pair_f32(int D, bool ckde, const PairJob* jobs, int n_jobs, long long total_units, long long upb,
                             int grid, const double* tab, cudaStream_t stream);
+cudaError_t launch_cdf_f64(int D, const PairJob* jobs, int n_jobs, long long total_units, long long upb, int grid,
+                           const double* tab, double inv_c, cudaStream_t stream);
+cudaError_t launch_cdf_f32(int D, const PairJob* jobs, int n_jobs, long long total_units, long long upb, int grid,
+                           const double* tab, double inv_c, cudaStream_t stream);
 int pair_tile_f64(int D);
 int pair_tile_f32(int D);
 int pair_tb_f64();

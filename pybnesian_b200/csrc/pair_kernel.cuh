@@ -29,6 +29,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "normcdf_coeffs.h"
+
 namespace pbn {
 
 struct PairJob {
@@ -156,6 +158,37 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
         : "memory");
 }
 
+// Upper normal tail without branches (normcdf_coeffs.h), used by the CDF mode of the pair kernel:
+//   Q(a) = 1/2 erfc(a / sqrt 2) = exp(-a^2/2) * t g(u)  for a >= 0,  t = 1/(1 + a/4),  u affine in t,
+// g a degree-18 (f64: 5e-15 relative) / degree-9 (f32: 2e-7) polynomial valid for every a in [0, 39] (beyond that
+// exp(-a^2/2) is 0 in double and the extrapolated polynomial stays finite).  Returns t g(u); the caller multiplies
+// by exp(-a^2/2), which for CKDE::cdf is the JOINT kernel value the pair kernel computes anyway.
+__device__ __forceinline__ double rcp_1toinf(double x) {  // x >= 1: MUFU.RCP64H (2^-23) + one cubic step -> 2^-69
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    return fma(r, fma(e, e, e), r);
+}
+__device__ __forceinline__ double normal_tail_tg(double a) {
+    constexpr double c[kQDeg64 + 1] = PBN_Q64_COEFFS;
+    double t = rcp_1toinf(fma(a, kQInvC, 1.0));
+    double u = fma(t, kQScale, kQShift);
+    double g = c[kQDeg64];
+#pragma unroll
+    for (int k = kQDeg64 - 1; k >= 0; --k) g = fma(g, u, c[k]);
+    return t * g;
+}
+__device__ __forceinline__ float normal_tail_tg_f(float a) {
+    constexpr float c[kQDeg32 + 1] = PBN_Q32_COEFFS;
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(a, static_cast<float>(kQInvC), 1.f)));
+    float u = fmaf(t, static_cast<float>(kQScale), static_cast<float>(kQShift));
+    float g = c[kQDeg32];
+#pragma unroll
+    for (int k = kQDeg32 - 1; k >= 0; --k) g = fmaf(g, u, c[k]);
+    return t * g;
+}
+
 // exp(-s/2) from the f64 kernel exponent t (= K*log2e*(-s/2), t <= 0):
 //   2^(t/K) = 2^k * T[j] * P(g),  n = rint(t) = K k + j,  g = t - n.
 // The table holds T'[j] = T[j] with (j << (20 - log2 K)) subtracted from its high word, so that the
@@ -205,9 +238,14 @@ __device__ __forceinline__ void exp_tab_fill(double* __restrict__ tab_s, const d
 }
 
 // One (test tile) x (train tile) unit on the FP64 pipe.
-template <int D, bool CKDE, bool SAFE, int R>
+// CDF mode (CKDE::cdf, factors/continuous/CKDE.hpp:506-728): the "joint" accumulator receives w Phi(z) instead of the
+// joint kernel value, z = (last whitened coordinate difference) * inv_c being (x_t - conditional mean_ti) / sqrt(cond_var):
+//   w Phi(z) = z < 0 ? E tg(|z|) : w - E tg(|z|),   E = w exp(-z^2/2) = the joint kernel value,  w = marginal value
+// (w = 1 for a CKDE without evidence, CKDE = false, D = 1).
+template <int D, bool CKDE, bool SAFE, int R, bool CDF>
 __device__ __forceinline__ void tile_f64(const double* __restrict__ tp, int cnt, const double (&yt)[R][D],
-                                         const double* __restrict__ tab, double (&sum_j)[R], double (&sum_m)[R]) {
+                                         const double* __restrict__ tab, double (&sum_j)[R], double (&sum_m)[R],
+                                         double inv_c) {
 #pragma unroll 4
     for (int i = 0; i < cnt; ++i) {
         double p[D];
@@ -216,19 +254,31 @@ __device__ __forceinline__ void tile_f64(const double* __restrict__ tp, int cnt,
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             double acc = 0.0;
+            double w = 1.0, dl_last = 0.0;
 #pragma unroll
             for (int c = 0; c < D; ++c) {
                 double dl = yt[r][c] - p[c];
                 acc = fma(-dl, dl, acc);
+                if (CDF && c == D - 1) dl_last = dl;
                 if (CKDE && c == D - 2) {
                     double st;
                     double pm = exp2_tab<SAFE>(acc, tab, st);
-                    sum_m[r] = fma(st, pm, sum_m[r]);
+                    if (CDF) {
+                        w = st * pm;
+                        sum_m[r] += w;
+                    } else {
+                        sum_m[r] = fma(st, pm, sum_m[r]);
+                    }
                 }
             }
             double st;
             double pj = exp2_tab<SAFE>(acc, tab, st);
-            sum_j[r] = fma(st, pj, sum_j[r]);
+            if (CDF) {
+                double q = (st * pj) * normal_tail_tg(fabs(dl_last) * inv_c);
+                sum_j[r] += (dl_last < 0.0) ? q : (w - q);
+            } else {
+                sum_j[r] = fma(st, pj, sum_j[r]);
+            }
         }
     }
 }
@@ -238,10 +288,11 @@ __device__ __forceinline__ void tile_f64(const double* __restrict__ tp, int cnt,
 // 2 yt_c for c < DN).  For a CKDE the conditioned variable (last coordinate) stays in difference form on top
 // of the marginal exponent.  The cancellation error is ~ sqrt(DN+1) 2^-53 (2 DN B^2) table units (B = largest
 // |whitened coordinate|); the caller only takes this path when that is below 1e-12 relative per term.
-template <int D, bool CKDE, int R>
+template <int D, bool CKDE, int R, bool CDF>
 __device__ __forceinline__ void tile_f64_dot(const double* __restrict__ tp, const double* __restrict__ nb, int cnt,
                                              const double (&yt)[R][D], const double (&at)[R],
-                                             const double* __restrict__ tab, double (&sum_j)[R], double (&sum_m)[R]) {
+                                             const double* __restrict__ tab, double (&sum_j)[R], double (&sum_m)[R],
+                                             double inv_c) {
     constexpr int DN = CKDE ? D - 1 : D;
 #pragma unroll 4
     for (int i = 0; i < cnt; ++i) {
@@ -252,27 +303,39 @@ __device__ __forceinline__ void tile_f64_dot(const double* __restrict__ tp, cons
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             double acc = at[r] + b;
+            double w = 1.0, dl_last = 0.0;
 #pragma unroll
             for (int c = 0; c < DN; ++c) acc = fma(yt[r][c], p[c], acc);
             if (CKDE) {
                 double st;
                 double pm = exp2_tab<false>(acc, tab, st);
-                sum_m[r] = fma(st, pm, sum_m[r]);
+                if (CDF) {
+                    w = st * pm;
+                    sum_m[r] += w;
+                } else {
+                    sum_m[r] = fma(st, pm, sum_m[r]);
+                }
                 double dl = yt[r][D - 1] - p[D - 1];
+                dl_last = dl;
                 acc = fma(-dl, dl, acc);
             }
             double st;
             double pj = exp2_tab<false>(acc, tab, st);
-            sum_j[r] = fma(st, pj, sum_j[r]);
+            if (CDF && CKDE) {
+                double q = (st * pj) * normal_tail_tg(fabs(dl_last) * inv_c);
+                sum_j[r] += (dl_last < 0.0) ? q : (w - q);
+            } else {
+                sum_j[r] = fma(st, pj, sum_j[r]);
+            }
         }
     }
 }
 
 // Same unit on the FP32 FMA pipe + MUFU.EX2; per-tile float sums are folded into the
 // double accumulators by the caller (summation error stays at ~sqrt(TILE) ulp).
-template <int D, bool CKDE, int R>
+template <int D, bool CKDE, int R, bool CDF>
 __device__ __forceinline__ void tile_f32(const float* __restrict__ tp, int cnt, const float (&yt)[R][D],
-                                         double (&sum_j)[R], double (&sum_m)[R]) {
+                                         double (&sum_j)[R], double (&sum_m)[R], float inv_c) {
     float facc_j[R], facc_m[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) { facc_j[r] = 0.f; facc_m[r] = 0.f; }
@@ -284,19 +347,27 @@ __device__ __forceinline__ void tile_f32(const float* __restrict__ tp, int cnt, 
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             float acc = 0.f;
+            float w = 1.f, dl_last = 0.f;
 #pragma unroll
             for (int c = 0; c < D; ++c) {
                 float dl = yt[r][c] - p[c];
                 acc = fmaf(-dl, dl, acc);
+                if (CDF && c == D - 1) dl_last = dl;
                 if (CKDE && c == D - 2) {
                     float e;
                     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(acc));
                     facc_m[r] += e;
+                    w = e;
                 }
             }
             float e;
             asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(acc));
-            facc_j[r] += e;
+            if (CDF) {
+                float q = e * normal_tail_tg_f(fabsf(dl_last) * inv_c);
+                facc_j[r] += (dl_last < 0.f) ? q : (w - q);
+            } else {
+                facc_j[r] += e;
+            }
         }
     }
 #pragma unroll
@@ -306,10 +377,12 @@ __device__ __forceinline__ void tile_f32(const float* __restrict__ tp, int cnt, 
     }
 }
 
-template <typename T, int D, bool CKDE>
+// CDF = false: KDE / CKDE log-likelihood sums.  CDF = true: CKDE::cdf sums (see tile_f64); `inv_c` converts a whitened
+// (kernel-unit) coordinate difference into standard-normal units and is only read in that mode.
+template <typename T, int D, bool CKDE, bool CDF = false>
 __global__ void __launch_bounds__(kThreads, PairCfg<T>::MIN_CTAS)
 pair_kernel(const PairJob* __restrict__ jobs, int n_jobs, long long total_units, long long upb,
-            const double* __restrict__ exp_tab_g) {
+            const double* __restrict__ exp_tab_g, double inv_c) {
     constexpr int R = PairCfg<T>::R;
     constexpr int TILE = pair_tile<T>(D);
     constexpr int TB = kThreads * R;  // test rows per tile
@@ -448,13 +521,13 @@ pair_kernel(const PairJob* __restrict__ jobs, int n_jobs, long long total_units,
 
         if constexpr (sizeof(T) == 8) {
             if (DOT && dot)
-                tile_f64_dot<D, CKDE, R>(tp, nrm_buf + static_cast<size_t>(stage) * TILE, cnt, yt, at, tab, sum_j, sum_m);
+                tile_f64_dot<D, CKDE, R, CDF>(tp, nrm_buf + static_cast<size_t>(stage) * TILE, cnt, yt, at, tab, sum_j, sum_m, inv_c);
             else if (safe)
-                tile_f64<D, CKDE, true, R>(tp, cnt, yt, tab, sum_j, sum_m);
+                tile_f64<D, CKDE, true, R, CDF>(tp, cnt, yt, tab, sum_j, sum_m, inv_c);
             else
-                tile_f64<D, CKDE, false, R>(tp, cnt, yt, tab, sum_j, sum_m);
+                tile_f64<D, CKDE, false, R, CDF>(tp, cnt, yt, tab, sum_j, sum_m, inv_c);
         } else {
-            tile_f32<D, CKDE, R>(tp, cnt, yt, sum_j, sum_m);
+            tile_f32<D, CKDE, R, CDF>(tp, cnt, yt, sum_j, sum_m, static_cast<float>(inv_c));
         }
 
         __syncthreads();  // everyone is done with this stage

@@ -5,18 +5,18 @@
 
 namespace pbn {
 
-template <int D, bool CKDE>
+template <int D, bool CKDE, bool CDF = false>
 static cudaError_t launch_one(const PairJob* jobs, int n_jobs, long long total_units, long long upb, int grid,
-                              const double* tab, cudaStream_t stream) {
+                              const double* tab, cudaStream_t stream, double inv_c = 0.0) {
     constexpr size_t smem = kStages * (pair_tile<PBN_T>(D) * D * sizeof(PBN_T) + pair_nrm_bytes<PBN_T>(D)) + 64 + exp_tab_smem_bytes<PBN_T>();
     static bool configured = false;  // per instantiation; attribute is per device function
-    auto kern = pair_kernel<PBN_T, D, CKDE>;
+    auto kern = pair_kernel<PBN_T, D, CKDE, CDF>;
     if (!configured || true) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    kern<<<grid, kThreads, smem, stream>>>(jobs, n_jobs, total_units, upb, tab);
+    kern<<<grid, kThreads, smem, stream>>>(jobs, n_jobs, total_units, upb, tab, inv_c);
     return cudaGetLastError();
 }
 
@@ -28,6 +28,22 @@ cudaError_t PBN_LAUNCH_NAME(int D, bool ckde, const PairJob* jobs, int n_jobs, l
                     : launch_one<d, false>(jobs, n_jobs, total_units, upb, grid, tab, stream);
     switch (D) {
         PBN_CASE(1) PBN_CASE(2) PBN_CASE(3) PBN_CASE(4) PBN_CASE(5) PBN_CASE(6) PBN_CASE(7) PBN_CASE(8)
+        default:
+            return cudaErrorInvalidValue;
+    }
+#undef PBN_CASE
+}
+
+// CDF mode of the same kernel (CKDE::cdf): D = joint dimension; D == 1 is the evidence-free case (w = 1).
+cudaError_t PBN_CDF_LAUNCH_NAME(int D, const PairJob* jobs, int n_jobs, long long total_units, long long upb, int grid,
+                                const double* tab, double inv_c, cudaStream_t stream) {
+#define PBN_CASE(d) \
+    case d:         \
+        return launch_one<d, true, true>(jobs, n_jobs, total_units, upb, grid, tab, stream, inv_c);
+    switch (D) {
+        case 1:
+            return launch_one<1, false, true>(jobs, n_jobs, total_units, upb, grid, tab, stream, inv_c);
+        PBN_CASE(2) PBN_CASE(3) PBN_CASE(4) PBN_CASE(5) PBN_CASE(6) PBN_CASE(7) PBN_CASE(8)
         default:
             return cudaErrorInvalidValue;
     }
