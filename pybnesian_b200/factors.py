@@ -361,10 +361,19 @@ class CKDE(Factor):
         from ._lib import check, int_array
         frame = DataFrame.wrap(df)
         self._check_test(frame)
+        from . import parallel
         tbl, cols, mask = frame.device_table(self._variables)
-        out = np.empty(tbl.nrows)
-        check(lib().pbn_ckde_cdf(tbl.ctx.handle, self._handle.handle, tbl.handle, int_array(cols), tbl.rows(),
-                                 out.ctypes.data_as(ctypes.POINTER(ctypes.c_double))))
+        m = tbl.nrows
+        # several ranks: contiguous test-row shards against the replicated training set, zero-padded vector
+        # all-reduce (each element written by exactly one rank), as _run_logl does
+        b, e = parallel.shard_range(m) if parallel.active() else (0, m)
+        out = np.zeros(m)
+        if e > b:
+            shard = out[b:e]
+            check(lib().pbn_ckde_cdf(tbl.ctx.handle, self._handle.handle, tbl.handle, int_array(cols), tbl.rows(b, e),
+                                     shard.ctypes.data_as(ctypes.POINTER(ctypes.c_double))))
+        if parallel.active():
+            out = parallel.all_reduce_sum(out, tbl.ctx)
         if mask is not None:
             full = np.full(frame.num_rows, np.nan)
             full[mask] = out

@@ -38,6 +38,14 @@ report["slogl_rel_diff"] = abs(s_sharded - s_single) / abs(s_single)
 report["logl_max_rel_diff"] = float(np.max(np.abs(l_sharded - l_single) / np.abs(l_single)))
 # a different unit split changes the order of the partial sums: equal to rounding, not bit for bit
 assert report["slogl_rel_diff"] < 1e-12 and report["logl_max_rel_diff"] < 1e-12, report
+c_sharded = cpd.cdf(test)
+smp_sharded = cpd.sample(1000, test[["a", "b", "c"]], 5).to_numpy()  # replicated: every rank draws the same stream
+parallel.enable(False)
+c_single = cpd.cdf(test)
+smp_single = cpd.sample(1000, test[["a", "b", "c"]], 5).to_numpy()
+parallel.enable(True)
+report["cdf_max_abs_diff"] = float(np.max(np.abs(c_sharded - c_single)))
+assert report["cdf_max_abs_diff"] < 1e-13 and np.array_equal(smp_sharded, smp_single), report
 
 data = nonlinear_data(3000, 0)
 names = list(data.columns)
