@@ -298,9 +298,21 @@ def main():
     i_own = (2 * 4 + 2 * 7) / 2.0
     achieved = kern_pairs / (kern_ms * 1e-3) if kern_ms > 0 else None
     peak = sms * lanes * f_hz / i_survey
+    # DRAM bytes of one launch of this exact configuration, from a committed ncu capture
+    # (tools/gpu_check.sh -> tools/traffic_json.py -> profiles/pair_kernel_traffic.json); null when none matches
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "pair_kernel_traffic.json")) as f:
+            for rec in json.load(f):
+                if rec.get("n_train") == n_train and rec.get("n_test") == n_test and rec.get("kernel") == "pair_kernel<double, 4, 1, 0>":
+                    traffic = rec["dram_bytes_read"] + rec["dram_bytes_write"]
+                    traffic_src = rec.get("source")
+    except Exception:
+        pass
     roofline = {
         "bound": "fp64_fma", "kernel": "pbn::pair_kernel<double,4,CKDE>", "achieved": achieved, "peak": peak,
-        "unit": UNIT, "frac": (achieved / peak) if achieved else None, "traffic": None,
+        "unit": UNIT, "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+        "traffic_source": traffic_src,
         "peak_def": "SMs(%d) x 64 FP64 lanes x %.0f MHz (median SM clock sampled in the timed region) / %.1f FP64-pipe "
                     "instr per pair-eval (SURVEY.md 8d two-pass count; a fused pass may exceed 1.0)" % (sms, f_hz / 1e6, i_survey),
         "own_count": {"fp64_instr_per_pair_eval": i_own, "peak": sms * lanes * f_hz / i_own,

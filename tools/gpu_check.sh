@@ -15,4 +15,6 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
     python bench.py --steps 2 --warmup 3 --no-cpu --e2e-steps 1 > gpurun_out/ncu_launch.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:pair_kernel -s 1 -c 1 -f -o gpurun_out/prof_pair \
     python bench.py --steps 1 --warmup 3 --n-test 131072 --no-cpu --e2e-steps 1 > gpurun_out/ncu_full.log 2>&1
+timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:pair_kernel -s 3 -c 1 --csv \
+    --log-file gpurun_out/traffic.csv python bench.py --steps 1 --warmup 3 --no-cpu --e2e-steps 1 > gpurun_out/ncu_traffic.log 2>&1
 ls -la gpurun_out
