@@ -52,6 +52,10 @@ struct PairJob {
 };
 
 constexpr int kThreads = 256;
+#ifndef PBN_F64_UNROLL
+#define PBN_F64_UNROLL 4
+#endif
+constexpr int kF64Unroll = PBN_F64_UNROLL;  // training points per unrolled step of the f64 tile loops
 constexpr int kStages = 2;
 
 template <typename T> struct PairCfg;
@@ -70,8 +74,9 @@ template <typename T> struct PairCfg;
 #ifndef PBN_F32_TILE
 #define PBN_F32_TILE 1024
 #endif
+// the persistent grid is 2 CTAs per SM (runtime.cu), so a tighter register bound only costs spills in the packed f32 tiles
 #ifndef PBN_F32_MINCTAS
-#define PBN_F32_MINCTAS 3
+#define PBN_F32_MINCTAS 2
 #endif
 #ifndef PBN_F64_DOT
 #define PBN_F64_DOT 1
@@ -89,6 +94,12 @@ template <typename T> struct PairCfg;
 #endif
 #ifndef PBN_EXP_REP
 #define PBN_EXP_REP 1
+#endif
+#ifndef PBN_EXP_INT
+#define PBN_EXP_INT 0
+#endif
+#ifndef PBN_F64_UNROLL
+#define PBN_F64_UNROLL 4
 #endif
 template <> struct PairCfg<double> { static constexpr int R = PBN_F64_R; static constexpr int TILE = PBN_F64_TILE; static constexpr int MIN_CTAS = PBN_F64_MINCTAS; };
 template <> struct PairCfg<float>  { static constexpr int R = PBN_F32_R; static constexpr int TILE = PBN_F32_TILE; static constexpr int MIN_CTAS = PBN_F32_MINCTAS; };
@@ -226,8 +237,19 @@ __device__ __forceinline__ double exp2_tab(double t, const double* __restrict__ 
     } else {
         n = max(n, kNMin);
     }
+#if PBN_EXP_INT == 1
+    // integer glue on the ALU pipe (SHF / LOP3 / IADD3) instead of the FMA pipe (IMAD.SHL / IMAD): the FP64 stream
+    // shares its dispatch port with the FMA pipe (profiles/r1c_tuning.md: DFMA + IMAD 1:1 costs 30% of the DFMA rate,
+    // DFMA + LOP3 10%)
+    unsigned rot, sh;
+    asm("shf.l.wrap.b32 %0, %1, %1, 3;" : "=r"(rot) : "r"(n));          // (n << 3) | (n >> 29); low 3 bits masked off below
+    asm("shf.l.clamp.b32 %0, %1, %2, %3;" : "=r"(sh) : "r"(0), "r"(n), "r"(20 - kExpTabBits));  // n << (20 - log2 K)
+    double tj = *reinterpret_cast<const double*>(reinterpret_cast<const char*>(tab) + (rot & ((kExpTab - 1) << 3)));
+    scaled = __hiloint2double(__double2hiint(tj) + static_cast<int>(sh), __double2loint(tj));
+#else
     double tj = tab[(n & (kExpTab - 1)) * kExpRep];
     scaled = __hiloint2double(__double2hiint(tj) + n * (1 << (20 - kExpTabBits)), __double2loint(tj));
+#endif
     return p;
 }
 
@@ -246,7 +268,7 @@ template <int D, bool CKDE, bool SAFE, int R, bool CDF>
 __device__ __forceinline__ void tile_f64(const double* __restrict__ tp, int cnt, const double (&yt)[R][D],
                                          const double* __restrict__ tab, double (&sum_j)[R], double (&sum_m)[R],
                                          double inv_c) {
-#pragma unroll 4
+#pragma unroll kF64Unroll
     for (int i = 0; i < cnt; ++i) {
         double p[D];
 #pragma unroll
@@ -294,7 +316,7 @@ __device__ __forceinline__ void tile_f64_dot(const double* __restrict__ tp, cons
                                              const double* __restrict__ tab, double (&sum_j)[R], double (&sum_m)[R],
                                              double inv_c) {
     constexpr int DN = CKDE ? D - 1 : D;
-#pragma unroll 4
+#pragma unroll kF64Unroll
     for (int i = 0; i < cnt; ++i) {
         double p[D];
 #pragma unroll
@@ -374,6 +396,96 @@ __device__ __forceinline__ void tile_f32(const float* __restrict__ tp, int cnt, 
     for (int r = 0; r < R; ++r) {
         sum_j[r] += static_cast<double>(facc_j[r]);
         if (CKDE) sum_m[r] += static_cast<double>(facc_m[r]);
+    }
+}
+
+// Packed form of tile_f32 (sm_100 FFMA2 / FADD2: fma.rn.f32x2 / add.rn.f32x2 work on two floats per lane).  Two test rows
+// of a thread share one instruction, which halves the issue slots of the subtract / square-accumulate / sum stream; the
+// FP32 pipe rate itself is unchanged (tools/micro/fp32_peak.cu: 120 lane-ops/clk/SM scalar or packed), so this helps
+// where the scalar kernel is issue-bound (d >= 3).  The squared distance is accumulated positive and negated at the
+// MUFU.EX2 input; p - yt is used instead of yt - p (the sign is squared away), so only -yt is needed, once per tile.
+#ifndef PBN_F32_PACKED
+#define PBN_F32_PACKED 1
+#endif
+#ifndef PBN_F32_PACKED_MIN_D
+#define PBN_F32_PACKED_MIN_D 1
+#endif
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pack_f32x2(float lo, float hi) {
+    f32x2_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack_f32x2(f32x2_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2_t fadd2(f32x2_t a, f32x2_t b) {
+    f32x2_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2_t ffma2(f32x2_t a, f32x2_t b, f32x2_t c) {
+    f32x2_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ float ex2_neg(float s) {  // 2^(-s)
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-s));
+    return e;
+}
+
+template <int D, bool CKDE, int R>
+__device__ __forceinline__ void tile_f32_packed(const float* __restrict__ tp, int cnt, const float (&yt)[R][D],
+                                                double (&sum_j)[R], double (&sum_m)[R]) {
+    static_assert(R % 2 == 0, "packed f32 tile needs an even number of rows per thread");
+    constexpr int H = R / 2;
+    f32x2_t nyt[H][D];
+    f32x2_t facc_j[H], facc_m[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) nyt[h][c] = pack_f32x2(-yt[2 * h][c], -yt[2 * h + 1][c]);
+        facc_j[h] = 0ull;
+        facc_m[h] = 0ull;
+    }
+#pragma unroll 4
+    for (int i = 0; i < cnt; ++i) {
+        f32x2_t p2[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            float v = tp[i * D + c];
+            p2[c] = pack_f32x2(v, v);
+        }
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            f32x2_t s2 = 0ull;
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+                f32x2_t d2 = fadd2(p2[c], nyt[h][c]);
+                s2 = ffma2(d2, d2, s2);
+                if (CKDE && c == D - 2) {
+                    float lo, hi;
+                    unpack_f32x2(s2, lo, hi);
+                    facc_m[h] = fadd2(facc_m[h], pack_f32x2(ex2_neg(lo), ex2_neg(hi)));
+                }
+            }
+            float lo, hi;
+            unpack_f32x2(s2, lo, hi);
+            facc_j[h] = fadd2(facc_j[h], pack_f32x2(ex2_neg(lo), ex2_neg(hi)));
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+        float lo, hi;
+        unpack_f32x2(facc_j[h], lo, hi);
+        sum_j[2 * h] += static_cast<double>(lo);
+        sum_j[2 * h + 1] += static_cast<double>(hi);
+        if (CKDE) {
+            unpack_f32x2(facc_m[h], lo, hi);
+            sum_m[2 * h] += static_cast<double>(lo);
+            sum_m[2 * h + 1] += static_cast<double>(hi);
+        }
     }
 }
 
@@ -527,7 +639,10 @@ pair_kernel(const PairJob* __restrict__ jobs, int n_jobs, long long total_units,
             else
                 tile_f64<D, CKDE, false, R, CDF>(tp, cnt, yt, tab, sum_j, sum_m, inv_c);
         } else {
-            tile_f32<D, CKDE, R, CDF>(tp, cnt, yt, sum_j, sum_m, static_cast<float>(inv_c));
+            if constexpr (PBN_F32_PACKED && !CDF && R % 2 == 0 && D >= PBN_F32_PACKED_MIN_D)
+                tile_f32_packed<D, CKDE, R>(tp, cnt, yt, sum_j, sum_m);
+            else
+                tile_f32<D, CKDE, R, CDF>(tp, cnt, yt, sum_j, sum_m, static_cast<float>(inv_c));
         }
 
         __syncthreads();  // everyone is done with this stage
