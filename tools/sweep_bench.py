@@ -53,9 +53,13 @@ def main():
                 ctx.set_timing(False)
                 if dt == "float64":
                     peak_survey = sms * 64 * f_hz / (2 * d + 18)
-                    peak_own = sms * 64 * f_hz / (2 * d + 7)
+                    # difference form: d sub + d FMA + 7 (table exp2 + accumulate); dot-product form from d >= 4
+                    # (pair_kernel.cuh: tile_f64_dot): 1 add + d FMA + 7
+                    peak_own = sms * 64 * f_hz / ((d + 8) if d >= 4 else (2 * d + 7))
                 else:
-                    peak_survey = peak_own = min(sms * 128 * f_hz / (2 * d + 2), sms * 16 * f_hz)
+                    # FP32 pipe: d sub + d FMA + 1 add lane-ops per pair at 128 lanes/clk/SM; MUFU.EX2 16/clk/SM
+                    peak_survey = min(sms * 128 * f_hz / (2 * d + 2), sms * 16 * f_hz)
+                    peak_own = min(sms * 128 * f_hz / (2 * d + 1), sms * 16 * f_hz)
                 rate = pe / (ms * 1e-3)
                 rows.append({"n": n, "d": d, "dtype": dt, "n_gpus": world, "pair_evals_per_s_per_gpu_kernel": rate,
                              "pair_evals_per_s_job_wall": float(n) * n / wall, "frac_survey_roofline": rate / peak_survey,
