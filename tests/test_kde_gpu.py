@@ -267,3 +267,25 @@ def test_against_reference_kernel_goldens(pbn, dt, variables, N, m):
     assert err(cpd.logl(te), GOLD["ref_ckde_logl_" + key]) < tol
     if dt == "float64":
         assert np.allclose(k.logl(te), GOLD["scipy_kde_logl_" + key], rtol=1e-9, atol=1e-11)
+
+
+@pytest.mark.parametrize("d", [4, 8])
+def test_dot_product_form_on_heavy_tailed_data(pbn, d):
+    """Student-t(4) columns put the bounding box of the whitened rows at 25-50 bandwidths: inside the window where the
+    f64 kernel takes the dot-product form of the exponent (pair_kernel.cuh: tile_f64_dot, worst-case cancellation bound
+    1e-11 per term).  The rows that matter are the outlying ones; every row must still meet the 1e-10 bar."""
+    rng = np.random.default_rng(5)
+    n, m = 100_000, 1500
+    train = pd.DataFrame({"x%d" % i: rng.standard_t(4, n) for i in range(d)})
+    test = pd.DataFrame({"x%d" % i: rng.standard_t(4, m) for i in range(d)})
+    # the most outlying training points are test rows too (their own kernel keeps the sum finite)
+    far = np.argsort(-np.abs(train.to_numpy()).max(axis=1))[:100]
+    test = pd.concat([test, train.iloc[far]], ignore_index=True)
+    k = pbn.KDE(list(train.columns))
+    k.fit(train)
+    got = k.logl(test)
+    X, T = train.to_numpy(), test.to_numpy()
+    want, want_s = oracle.kde_logl(X, T, oracle.bandwidth(X))
+    assert np.all(np.isfinite(want))
+    assert relerr(got, want) < RTOL64
+    assert abs(k.slogl(test) - want_s) <= RTOL64 * abs(want_s)
