@@ -267,6 +267,11 @@ int pbn_ckde_sample(pbn_ctx* ctx, const pbn_kde* kde, const double* H, const pbn
 int pbn_lg_sample(const double* beta, double variance, int p, const void* const* ev, int ev_dtype, int64_t n,
                   uint32_t seed, double* out);
 
+/* n draws of std::uniform_real_distribution<T>(0, 1) from std::mt19937{seed} (T = double for PBN_F64, float for
+ * PBN_F32): the stream DiscreteFactor::sample_indices (factors/discrete/DiscreteFactor.hpp:158-199) and
+ * CKDE::_sample_multivariate (CKDE.hpp:336-341) consume.  Host only, bit-exact with the reference. */
+int pbn_uniform_real(int64_t n, uint32_t seed, int dtype, void* out);
+
 /* ---- host-side integer logic that must match libstdc++ bit for bit -----------------------------------
  * ArcOperatorSet::find_max_indegree (learning/operators/operators.hpp:489-497): std::sort of the persistent
  * candidate index vector by delta, descending (unstable: ties resolve as in the reference). */

@@ -27,7 +27,7 @@ EXPORTS = [
     "pbn_cv_folds", "pbn_cv_train_moments", "pbn_cv_scores", "pbn_sort_desc", "pbn_intset_new", "pbn_intset_clone",
     "pbn_intset_free", "pbn_intset_insert", "pbn_intset_erase", "pbn_intset_clear", "pbn_intset_contains",
     "pbn_intset_size", "pbn_intset_list", "pbn_discrete_slices", "pbn_table_take", "pbn_kde_logl_multi",
-    "pbn_ckde_cdf", "pbn_ckde_sample_indices", "pbn_ckde_sample", "pbn_lg_sample",
+    "pbn_ckde_cdf", "pbn_ckde_sample_indices", "pbn_ckde_sample", "pbn_lg_sample", "pbn_uniform_real",
 ]
 PBN_MAX_DIM = 32
 FACTOR_CKDE, FACTOR_LINEAR_GAUSSIAN = 0, 1
@@ -140,6 +140,7 @@ def lib():
         L.pbn_ckde_cdf.argtypes = [vp, vp, vp, ip, Rows, dp]
         L.pbn_ckde_sample_indices.argtypes = [vp, vp, vp, ip, Rows, vp, i32p]
         L.pbn_ckde_sample.argtypes = [vp, vp, dp, vp, ip, Rows, vp, ip, ctypes.POINTER(vp), i64, ctypes.c_uint32, vp, i32p]
+        L.pbn_uniform_real.argtypes = [i64, ctypes.c_uint32, ci, vp]
         L.pbn_lg_sample.argtypes = [dp, ctypes.c_double, ci, ctypes.POINTER(vp), ci, i64, ctypes.c_uint32, dp]
         L.pbn_ctx_set_timing.argtypes = [vp, ci]
         L.pbn_ctx_pair_kernel_time.argtypes = [vp, dp, ctypes.POINTER(i64), ctypes.POINTER(i64), ci]

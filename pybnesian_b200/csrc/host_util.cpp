@@ -127,6 +127,19 @@ int pbn_lg_sample(const double* beta, double variance, int p, const void* const*
     return PBN_OK;
 }
 
+int pbn_uniform_real(int64_t n, uint32_t seed, int dtype, void* out) {
+    if (n < 0 || (n > 0 && !out)) return pbn_set_error(PBN_ERR_ARG, "invalid argument");
+    std::mt19937 rng{seed};
+    if (dtype == PBN_F64) {
+        std::uniform_real_distribution<double> u(0, 1);
+        for (int64_t i = 0; i < n; ++i) static_cast<double*>(out)[i] = u(rng);
+    } else {
+        std::uniform_real_distribution<float> u(0, 1);
+        for (int64_t i = 0; i < n; ++i) static_cast<float*>(out)[i] = u(rng);
+    }
+    return PBN_OK;
+}
+
 // std::unordered_set<int>: DNode::m_parents / m_children (graph/graph_types.hpp:12-51).  The order in
 // which BayesianNetwork::parents() lists a node's parents is this container's iteration order.
 int pbn_intset_new(pbn_intset** out) {

@@ -16,6 +16,7 @@ import ctypes
 import pickle
 
 import numpy as np
+import pandas as pd
 import pyarrow as pa
 
 from . import _lib
@@ -278,6 +279,39 @@ class DiscreteFactor(Factor):
         # sequential double accumulation in row order (DiscreteFactor.cpp:150-159); cumsum adds left to right
         return float(np.cumsum(self._logprob[idx])[-1])
 
+    def sample(self, n, evidence_values=None, seed=None):
+        """DiscreteFactor::sample / sample_indices (DiscreteFactor.cpp:173-208, DiscreteFactor.hpp:144-207): one
+        std::uniform_real_distribution<double> draw per instance against the running sum of the row of the
+        probability table selected by the discrete evidence; the last category takes the remainder."""
+        from .factors import _random_seed
+        if n < 0:
+            raise ValueError("n should be a non-negative number")
+        self._check_fitted()
+        seed = _random_seed(seed)
+        c0 = int(self._cardinality[0])
+        # running sums over the first c0 - 1 categories of every parent configuration, left to right
+        accum = np.cumsum(np.exp(self._logprob.reshape(-1, c0))[:, :max(c0 - 1, 0)], axis=1)
+        parent = np.zeros(n, dtype=np.int64)
+        if self._evidence:
+            frame = DataFrame.wrap(evidence_values) if evidence_values is not None else None
+            if frame is None or not frame.has_columns(self._evidence):
+                raise ValueError("Evidence values not present for sampling.")
+            for e, vals in zip(self._evidence, self._values[1:]):
+                check_domain_variable(frame, e, vals)
+            if frame.num_rows != n:
+                raise ValueError("Evidence values do not have " + str(n) + " rows to sample.")
+            if frame.null_count(self._evidence) > 0:
+                raise ValueError("Evidence values contain null rows in the evidence variables.")
+            for e, st in zip(self._evidence, self._strides[1:]):
+                parent += _codes(frame, e).astype(np.int64) * (int(st) // c0)
+        u = np.empty(n)
+        check(lib().pbn_uniform_real(n, seed, _lib.PBN_F64, u.ctypes.data_as(ctypes.c_void_p)))
+        # first j with u < accum[parent, j], else the last category
+        idx = (u[:, None] >= accum[parent]).sum(axis=1) if c0 > 1 else np.zeros(n, dtype=np.int64)
+        index_type = self._arrow_type.index_type
+        indices = pa.array(idx.astype(index_type.to_pandas_dtype()), type=index_type)
+        return pa.DictionaryArray.from_arrays(indices, pa.array(self._values[0], type=self._arrow_type.value_type))
+
     def __getstate__(self):
         return (self._variable, self._evidence, self._fitted, self._logprob, self._cardinality, self._strides,
                 self._values, self._arrow_type)
@@ -494,6 +528,47 @@ class DiscreteAdaptator(Factor):
             if f is not None and grouped.count(c) > 0:
                 res += float(sums[c])
         return res
+
+    # -- sample (DiscreteAdaptator.hpp:426-520) --------------------------------------------------------
+    def sample(self, n, evidence_values=None, seed=None):
+        """Configuration i of the discrete evidence is sampled by its base factor with seed + i on the rows of that
+        configuration; rows of a configuration without a factor are NaN.  As in the reference every base factor is asked
+        for n instances (its random streams are laid out for n draws) and the first len(rows) are kept."""
+        from .factors import _random_seed
+        from .dataset import _NP_DTYPE
+        if n < 0:
+            raise ValueError("n should be a non-negative number")
+        frame = DataFrame.wrap(evidence_values) if evidence_values is not None else None
+        if self._evidence:
+            if frame is None:
+                raise ValueError("Evidence values not present for sampling.")
+            self._run_checks(frame, False)
+            if frame.num_rows != n:
+                raise ValueError("Evidence values do not have " + str(n) + " rows to sample.")
+            if frame.null_count(self._evidence) > 0:
+                raise ValueError("Evidence values contain null rows in the evidence variables.")
+        else:
+            self._check_fitted()
+        seed = _random_seed(seed)
+        if not self._discrete_evidence:
+            return self._factors[0].sample(n, frame, seed)
+        order, offsets = discrete_slices(frame, self._discrete_evidence, self._strides, len(self._factors))
+        npdt = _NP_DTYPE[_DTYPE_CODE[self.data_type()]]
+        res = np.full(n, np.nan, dtype=npdt)
+        cont = {e: frame.column_numpy(e) for e in self._continuous_evidence}
+        for i, f in enumerate(self._factors):
+            rows = order[int(offsets[i]):int(offsets[i + 1])]
+            if rows.size == 0 or f is None:
+                continue
+            ev = None
+            if cont:
+                # the configuration's evidence rows, padded to n rows with its first row (the draws beyond len(rows)
+                # are discarded; the reference reads past the end of the filtered columns there)
+                pad = np.concatenate([rows, np.full(n - rows.size, rows[0], dtype=rows.dtype)])
+                ev = pd.DataFrame({e: np.ascontiguousarray(c[pad]) for e, c in cont.items()})
+            smp = f.sample(n, ev, (seed + i) & 0xFFFFFFFF)
+            res[rows] = smp.to_numpy(zero_copy_only=False)[:rows.size]
+        return pa.array(res)
 
     # -- text / pickle -------------------------------------------------------------------------------
     def __str__(self):

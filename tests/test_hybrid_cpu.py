@@ -229,3 +229,58 @@ def test_hybrid_factor_constructor_and_unfitted_errors():
     c = pbn.CLinearGaussianCPD("D", ["A", "C"], [1.0, 2.0], 0.5)
     c._continuous_evidence = ["C"]  # what fit() derives from the data types
     assert c._initialize(pbn.Assignment()).fitted()
+
+
+# ---- sampling (SURVEY §8 f3 on hybrid networks): DiscreteFactor is host only ------------------------------
+def _discrete_sample_restated(logprob, c0, parent_rows, n, seed):
+    """DiscreteFactor::sample_indices (DiscreteFactor.hpp:144-207), line by line."""
+    u = oracle.uniform_real(n, seed, np.float64)
+    out = np.empty(n, dtype=np.int64)
+    for i in range(n):
+        off = int(parent_rows[i]) * c0
+        acc, index = 0.0, c0 - 1
+        for j in range(c0 - 1):
+            acc = np.exp(logprob[off + j]) if j == 0 else acc + np.exp(logprob[off + j])
+            if u[i] < acc:
+                index = j
+                break
+        out[i] = index
+    return out
+
+
+def test_discrete_factor_sample():
+    tr = util_data.generate_hybrid_data(2000, 0)
+    f = pbn.DiscreteFactor("B", ["A"])
+    f.fit(tr)
+    ev = util_data.generate_hybrid_data(500, 3)[["A"]]
+    s = f.sample(500, ev, 17)
+    assert pa.types.is_dictionary(s.type) and s.type == f.data_type() and len(s) == 500
+    assert s.dictionary.to_pylist() == ["b1", "b2", "b3"]
+    parent = ev["A"].cat.codes.to_numpy()
+    want = _discrete_sample_restated(f._logprob, 3, parent, 500, 17)
+    assert np.array_equal(s.indices.to_numpy(), want)
+    # without evidence; frequencies follow the fitted table
+    g = pbn.DiscreteFactor("A", [])
+    g.fit(tr)
+    s = g.sample(4000, None, 1)
+    assert np.array_equal(s.indices.to_numpy(), _discrete_sample_restated(g._logprob, 2, np.zeros(4000, dtype=int), 4000, 1))
+    assert abs(np.mean(s.indices.to_numpy() == 0) - np.exp(g._logprob[0])) < 0.03
+    with pytest.raises(ValueError, match="non-negative"):
+        f.sample(-1, ev, 0)
+    with pytest.raises(ValueError, match="rows to sample"):
+        f.sample(10, ev, 0)
+    with pytest.raises(ValueError, match="not present"):
+        f.sample(500, None, 0)
+    bad = ev.copy()
+    bad["A"] = bad["A"].cat.rename_categories({"a1": "zz"})
+    with pytest.raises(ValueError):
+        f.sample(500, bad, 0)
+
+
+def test_pbn_uniform_real_is_the_libstdcxx_stream():
+    import ctypes
+    from pybnesian_b200 import _lib
+    for dt, code in ((np.float64, 0), (np.float32, 1)):
+        out = np.empty(33, dtype=dt)
+        assert _lib.lib().pbn_uniform_real(33, 7, code, out.ctypes.data_as(ctypes.c_void_p)) == 0
+        assert np.array_equal(out, oracle.uniform_real(33, 7, dt))

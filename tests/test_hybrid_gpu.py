@@ -317,3 +317,60 @@ def start_typed(pbn, tr):
     m = pbn.SemiparametricBN(list(tr.columns))
     m.set_unknown_node_types(tr)
     return m
+
+
+# ---- sampling on hybrid factors / networks ---------------------------------------------------
+def test_hckde_sample_per_configuration_vs_oracle(pbn):
+    """DiscreteAdaptator::sample (DiscreteAdaptator.hpp:426-520): configuration i is sampled by its CKDE with
+    seed + i on its rows, every factor being asked for n draws; replayed here with the oracle's CKDE sampler."""
+    tr, _ = frames(1500, 10, "float64")
+    f = pbn.HCKDE("D", ["A", "C", "B"])
+    f.fit(tr)
+    n, seed = 400, 21
+    ev = util_data.generate_hybrid_data(n, 5)[["A", "C", "B"]]
+    s = f.sample(n, ev, seed)
+    assert s.type == pa.float64() and len(s) == n
+    got = s.to_numpy()
+    cfg = ev["A"].cat.codes.to_numpy() + 2 * ev["B"].cat.codes.to_numpy()
+    for i in range(6):
+        rows = np.flatnonzero(cfg == i)
+        if rows.size == 0:
+            continue
+        sel = (tr["A"].cat.codes.to_numpy() + 2 * tr["B"].cat.codes.to_numpy()) == i
+        X = tr.loc[sel, ["D", "C"]].to_numpy()
+        evc = ev["C"].to_numpy()[np.concatenate([rows, np.full(n - rows.size, rows[0])])].reshape(-1, 1)
+        want, _ = oracle.ckde_sample(X, oracle.bandwidth(X), evc, n, seed + i)
+        close(got[rows], want[:rows.size], 1e-11)
+    with pytest.raises(ValueError, match="rows to sample"):
+        f.sample(n + 1, ev, 0)
+    with pytest.raises(ValueError, match="non-negative"):
+        f.sample(-1, ev, 0)
+
+
+def test_clg_sample_and_hybrid_network_sample(pbn):
+    tr, _ = frames(1500, 10, "float64")
+    g = pbn.CLinearGaussianCPD("D", ["A", "C"])
+    g.fit(tr)
+    ev = util_data.generate_hybrid_data(300, 6)[["A", "C"]]
+    got = g.sample(300, ev, 9).to_numpy()
+    codes = ev["A"].cat.codes.to_numpy()
+    for i in range(2):
+        rows = np.flatnonzero(codes == i)
+        base = g.conditional_factor(pbn.Assignment({"A": "a%d" % (i + 1)}))
+        evc = ev["C"].to_numpy()[np.concatenate([rows, np.full(300 - rows.size, rows[0])])]
+        want = oracle.lg_sample(base.beta, base.variance, [evc], 300, 9 + i)
+        assert np.array_equal(got[rows], want[:rows.size])
+    # ancestral sampling through discrete, conditional-linear-Gaussian and hybrid-CKDE nodes
+    m = pbn.SemiparametricBN(["A", "B", "C", "D"], [("A", "B"), ("A", "D"), ("B", "D"), ("C", "D")],
+                             [("D", pbn.CKDEType())])
+    m.fit(tr)
+    s = m.sample(2000, 3, ordered=True)
+    assert list(s.columns) == ["A", "B", "C", "D"] and len(s) == 2000
+    assert str(s["A"].dtype) == "category" and set(s["B"].cat.categories) == {"b1", "b2", "b3"}
+    assert abs(np.mean(s["A"] == "a1") - 0.75) < 0.05
+    assert np.isfinite(s["D"]).all()
+    # the law of D given (a1, b2) is -2 + C + N(0, 2): compare the sampled conditional mean with the training one
+    sel_s = (s["A"] == "a1") & (s["B"] == "b2")
+    sel_t = (tr["A"] == "a1") & (tr["B"] == "b2")
+    assert abs(s.loc[sel_s, "D"].mean() - tr.loc[sel_t, "D"].mean()) < 0.5
+    assert s.equals(m.sample(2000, 3, ordered=True))
