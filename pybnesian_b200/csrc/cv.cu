@@ -174,8 +174,15 @@ __global__ void whiten_batch_kernel(const WhitenJob* __restrict__ jobs, long lon
     }
     if ((threadIdx.x & 31) == 0) {
         // non-negative floats order like their bit patterns
-        if (mx_tr > 0.f) atomicMax(reinterpret_cast<int*>(jb.bound), __float_as_int(mx_tr * 1.0001f));
-        if (mx_te > 0.f) atomicMax(reinterpret_cast<int*>(jb.bound + 1), __float_as_int(mx_te * 1.0001f));
+        // issued only when the value can still raise the maximum (see whiten_kernel in runtime.cu)
+        if (mx_tr > 0.f) {
+            const int v = __float_as_int(mx_tr * 1.0001f);
+            if (v > *reinterpret_cast<volatile int*>(jb.bound)) atomicMax(reinterpret_cast<int*>(jb.bound), v);
+        }
+        if (mx_te > 0.f) {
+            const int v = __float_as_int(mx_te * 1.0001f);
+            if (v > *reinterpret_cast<volatile int*>(jb.bound + 1)) atomicMax(reinterpret_cast<int*>(jb.bound + 1), v);
+        }
     }
 }
 

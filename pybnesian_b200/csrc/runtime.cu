@@ -179,31 +179,57 @@ __global__ void cov_tile_kernel(ColPtrs cols, Vec32 mean, int d, int ntile_side,
 // ------------------------------------------------------------------------------------
 // device kernels: whitening  y = W (x - mu), AoS output
 // ------------------------------------------------------------------------------------
-template <typename T>
+// DT = compile-time number of variables (1..8: everything stays in registers), 0 = run-time d up to PBN_MAX_DIM
+template <typename T, int DT>
 __global__ void whiten_kernel(const __grid_constant__ WhitenParams P, T* __restrict__ out, float* __restrict__ bound,
                               double* __restrict__ nrm) {
-    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    // the block's rows form one contiguous chunk of the AoS output: stage them in shared memory and write the chunk
+    // with coalesced stores (a thread's own d values are 8 d bytes apart from its neighbour's)
+    extern __shared__ __align__(16) unsigned char whiten_smem[];
+    T* tile = reinterpret_cast<T*>(whiten_smem);
+    constexpr int DA = DT ? DT : PBN_MAX_DIM;
+    const int64_t base = blockIdx.x * (int64_t)blockDim.x;
+    int64_t r = base + threadIdx.x;
     float mx = 0.f;
+    const int d = DT ? DT : P.d;
     if (r < P.n) {
         int64_t rr = map_row(r, P.b0, P.n0, P.b1);
-        double x[PBN_MAX_DIM];
-        const int d = P.d;
-        for (int c = 0; c < d; ++c) x[c] = static_cast<double>(static_cast<const T*>(P.cols.p[c])[rr]) - P.mu[c];
-        int w = 0;
+        double x[DA];
+#pragma unroll
+        for (int c = 0; c < DA; ++c)
+            if (c < d) x[c] = static_cast<double>(static_cast<const T*>(P.cols.p[c])[rr]) - P.mu[c];
         double nn = 0;
-        for (int i = 0; i < d; ++i) {
-            double s = 0;
-            for (int k = 0; k <= i; ++k) s = fma(P.W[w++], x[k], s);
-            out[r * d + i] = static_cast<T>(s);
-            if (i < P.dn) nn = fma(-s, s, nn);
-            float a = fabsf(static_cast<float>(s));
-            mx = (a > mx || a != a) ? (a != a ? INFINITY : a) : mx;  // NaN counts as unbounded
+#pragma unroll
+        for (int i = 0; i < DA; ++i) {
+            if (i < d) {
+                double s = 0;
+#pragma unroll
+                for (int k = 0; k < DA; ++k)
+                    if (k <= i) s = fma(P.W[i * (i + 1) / 2 + k], x[k], s);
+                tile[threadIdx.x * d + i] = static_cast<T>(s);
+                if (i < P.dn) nn = fma(-s, s, nn);
+                float a = fabsf(static_cast<float>(s));
+                mx = (a > mx || a != a) ? (a != a ? INFINITY : a) : mx;  // NaN counts as unbounded
+            }
         }
         if (nrm) nrm[r] = nn;
     }
-    // max |coordinate| of the launch (non-negative floats order like their bit patterns)
+    __syncthreads();
+    {
+        int64_t rows_here = P.n - base;
+        if (rows_here > blockDim.x) rows_here = blockDim.x;
+        const int64_t cnt = rows_here * d;
+        T* dst = out + base * d;
+        for (int64_t j = threadIdx.x; j < cnt; j += blockDim.x) dst[j] = tile[j];
+    }
+    // max |coordinate| of the launch (non-negative floats order like their bit patterns).  One atomic per warp on a
+    // single address serialises in L2 (it was the whole run time of this kernel at 8M rows), so a warp only issues it
+    // when its value can still raise the current maximum (the plain read may be stale: the atomic stays correct).
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if (bound && (threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(reinterpret_cast<int*>(bound), __float_as_int(mx * 1.0001f));
+    if (bound && (threadIdx.x & 31) == 0 && mx > 0.f) {
+        const int v = __float_as_int(mx * 1.0001f);
+        if (v > *reinterpret_cast<volatile int*>(bound)) atomicMax(reinterpret_cast<int*>(bound), v);
+    }
 }
 
 // ------------------------------------------------------------------------------------
@@ -452,10 +478,27 @@ int whiten_raw_launch(pbn_ctx* ctx, const pbn_table* tbl, const int* cols_io, in
     if (P.n == 0) return PBN_OK;
     const int threads = 256;
     int blocks = (int)((P.n + threads - 1) / threads);
-    if (tbl->dtype == PBN_F64)
-        whiten_kernel<double><<<blocks, threads, 0, ctx->stream>>>(P, static_cast<double*>(out), bound, nrm);
-    else
-        whiten_kernel<float><<<blocks, threads, 0, ctx->stream>>>(P, static_cast<float*>(out), bound, nullptr);
+    const size_t smem = (size_t)threads * d * elem_size(tbl->dtype);
+    const bool f64 = tbl->dtype == PBN_F64;
+#define PBN_WHITEN_CASE(DT)                                                                                              \
+    case DT:                                                                                                             \
+        if (f64) whiten_kernel<double, DT><<<blocks, threads, smem, ctx->stream>>>(P, static_cast<double*>(out), bound, nrm); \
+        else whiten_kernel<float, DT><<<blocks, threads, smem, ctx->stream>>>(P, static_cast<float*>(out), bound, nullptr);   \
+        break;
+    switch (d) {
+        PBN_WHITEN_CASE(1) PBN_WHITEN_CASE(2) PBN_WHITEN_CASE(3) PBN_WHITEN_CASE(4)
+        PBN_WHITEN_CASE(5) PBN_WHITEN_CASE(6) PBN_WHITEN_CASE(7) PBN_WHITEN_CASE(8)
+        default:
+            if (smem > 48 * 1024) {  // d > 24 doubles per row: opt in to the larger carve-out
+                if (f64)
+                    PBN_CUDA_TRY(cudaFuncSetAttribute(whiten_kernel<double, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                else
+                    PBN_CUDA_TRY(cudaFuncSetAttribute(whiten_kernel<float, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            }
+            if (f64) whiten_kernel<double, 0><<<blocks, threads, smem, ctx->stream>>>(P, static_cast<double*>(out), bound, nrm);
+            else whiten_kernel<float, 0><<<blocks, threads, smem, ctx->stream>>>(P, static_cast<float*>(out), bound, nullptr);
+    }
+#undef PBN_WHITEN_CASE
     ctx->launches++;
     PBN_CUDA_TRY(cudaGetLastError());
     return PBN_OK;

@@ -71,7 +71,10 @@ __global__ void whiten_seg_kernel(const SegWhitenJob* __restrict__ jobs) {
     }
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     // non-negative floats order like their bit patterns
-    if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(reinterpret_cast<int*>(jb.bound), __float_as_int(mx * 1.0001f));
+    if ((threadIdx.x & 31) == 0 && mx > 0.f) {  // issued only when it can still raise the maximum (runtime.cu: whiten_kernel)
+        const int v = __float_as_int(mx * 1.0001f);
+        if (v > *reinterpret_cast<volatile int*>(jb.bound)) atomicMax(reinterpret_cast<int*>(jb.bound), v);
+    }
 }
 
 template <typename T>
