@@ -227,6 +227,19 @@ class Dag:
     def can_flip_arc(self, source, target):
         return self._can_flip(self.index(source), self.index(target))
 
+    def roots(self):
+        """ArcGraph::roots (graph/generic_graph.hpp:1133): names of the nodes without parents."""
+        return {self._names[i] for i in self._roots.list()}
+
+    def leaves(self):
+        return {n for i, n in enumerate(self._names) if len(self._children[i]) == 0}
+
+    def save(self, filename):
+        if not filename.endswith(".pickle"):
+            filename += ".pickle"
+        with open(filename, "wb") as f:
+            pickle.dump(self, f, protocol=2)
+
     def topological_sort(self):
         indeg = [len(p) for p in self._parents]
         stack = self._roots.list()  # DagImpl::topological_sort (generic_graph.hpp:2659-2708)
