@@ -289,3 +289,59 @@ def test_dot_product_form_on_heavy_tailed_data(pbn, d):
     assert np.all(np.isfinite(want))
     assert relerr(got, want) < RTOL64
     assert abs(k.slogl(test) - want_s) <= RTOL64 * abs(want_s)
+
+
+def test_edge_cases_empty_small_and_wide(pbn):
+    """Empty test sets, all-null test sets, too few instances, the widest supported family."""
+    df = util_data.generate_normal_data(300, 0)
+    k = pbn.KDE(["a", "b"])
+    k.fit(df)
+    empty = df.iloc[:0]
+    assert k.logl(empty).shape == (0,) and k.slogl(empty) == 0.0
+    cpd = pbn.CKDE("c", ["a", "b"])
+    cpd.fit(df)
+    assert cpd.logl(empty).shape == (0,) and cpd.slogl(empty) == 0.0 and cpd.cdf(empty).shape == (0,)
+    allnull = df.iloc[:5].copy()
+    allnull["a"] = np.nan
+    assert np.all(np.isnan(k.logl(allnull))) and k.slogl(allnull) == 0.0
+    assert np.all(np.isnan(cpd.cdf(allnull)))
+    # valid_rows <= d: SingularCovarianceData (NormalReferenceRule.hpp:37-60), a ValueError
+    with pytest.raises(pbn.SingularCovarianceData):
+        pbn.KDE(["a", "b"]).fit(df.iloc[:2])
+    with pytest.raises(ValueError):
+        pbn.CKDE("c", ["a", "b"]).fit(df.iloc[:3])
+    # a training set evaluated on itself (the zero-distance pair contributes exp(0) = 1 exactly)
+    X = df[["a", "b"]].to_numpy()
+    want, _ = oracle.kde_logl(X, X, oracle.bandwidth(X))
+    assert relerr(k.logl(df), want) < RTOL64
+    # the widest family the C ABI takes (PBN_MAX_DIM = 32 variables) and one more
+    wide = util_data.iid_normal(400, 33, seed=2)
+    names = list(wide.columns)
+    k32 = pbn.KDE(names[:32])
+    k32.fit(wide)
+    W = wide[names[:32]].to_numpy()
+    want, _ = oracle.kde_logl(W, W[:20], oracle.bandwidth(W))
+    assert relerr(k32.logl(wide.iloc[:20]), want) < RTOL64
+    c32 = pbn.CKDE(names[0], names[1:32])
+    c32.fit(wide)
+    wantc, _ = oracle.ckde_logl(W, W[:20], oracle.bandwidth(W))
+    assert np.allclose(c32.logl(wide.iloc[:20]), wantc, rtol=1e-9, atol=1e-9)
+    wantcdf = oracle.ckde_cdf(W, W[:20], oracle.bandwidth(W))
+    assert np.allclose(c32.cdf(wide.iloc[:20]), wantcdf, rtol=1e-9, atol=1e-10)
+    with pytest.raises(ValueError):
+        pbn.KDE(names).fit(wide)
+
+
+def test_non_finite_test_values_propagate(pbn):
+    df = util_data.generate_normal_data(300, 0)
+    k = pbn.KDE(["a", "b"])
+    k.fit(df)
+    t = df.iloc[:4].copy()
+    t.loc[t.index[1], "a"] = np.inf
+    t.loc[t.index[2], "b"] = -np.inf
+    got = k.logl(t)
+    want, _ = oracle.kde_logl(df[["a", "b"]].to_numpy(), t[["a", "b"]].to_numpy(), oracle.bandwidth(df[["a", "b"]].to_numpy()))
+    # the reference's arithmetic turns an infinite coordinate into exp(-inf) terms: logl = -inf (or NaN from inf - inf)
+    assert np.isfinite(got[0]) and np.isfinite(got[3])
+    for i in (1, 2):
+        assert not np.isfinite(got[i]) and not np.isfinite(want[i])
