@@ -45,7 +45,8 @@ struct WParams {
     double* part;       // [2][n_splits][m_pad]: sum w, sum w Phi
     const double* tab;  // exp2 table (f64)
     // scan pass
-    const double* target;  // [m]: u_t * S_t (+inf: no index)
+    const double* target;  // [m]: weight still to be accumulated INSIDE the selected split before the index is reached
+    const int* sel_split;  // [m]: training split that holds the index of row t (-1: none, index N-1)
     int* idx;              // [m]
 };
 
@@ -75,7 +76,8 @@ struct TilePipe {
 
 // MODE 0: cdf sums (sum w, sum w Phi) over the training tiles of split blockIdx.y
 // MODE 1: weight sums only (sum w) - first pass of the index sampling
-// MODE 2: index scan - one CTA walks ALL training tiles in order, stops when every row has its index
+// MODE 2: index scan - CTA (test tile, split) walks the tiles of its split in order for the rows whose index lies in that
+//         split (chosen from the split totals of MODE 1), and stops when each of them has its index
 template <typename T, int DT, int MODE>
 __global__ void __launch_bounds__(kWThreads) weight_kernel(const __grid_constant__ WParams P) {
     constexpr int DA = DT ? DT : PBN_MAX_DIM;
@@ -92,9 +94,14 @@ __global__ void __launch_bounds__(kWThreads) weight_kernel(const __grid_constant
     const int tid = threadIdx.x;
     const long long row = static_cast<long long>(blockIdx.x) * kWThreads + tid;
     const bool ok = row < P.m;
-    int t0 = MODE == 2 ? 0 : blockIdx.y * P.tiles_per_split;
-    int t1 = MODE == 2 ? P.n_train_tiles : min(t0 + P.tiles_per_split, P.n_train_tiles);
+    int t0 = blockIdx.y * P.tiles_per_split;
+    int t1 = min(t0 + P.tiles_per_split, P.n_train_tiles);
 
+    bool active = true;
+    if (MODE == 2) {
+        active = ok && P.sel_split[row] == static_cast<int>(blockIdx.y);
+        if (!__syncthreads_or(active)) return;  // no row of this tile has its index in this split (nothing in flight yet)
+    }
     if (sizeof(T) == 8 && (DN > 0 || MODE == 0)) exp_tab_fill(tab, P.tab, tid, kWThreads);
     if (tid == 0) {
         for (int s = 0; s < kWStages; ++s) mbar_init(&bar[s], 1);
@@ -126,8 +133,8 @@ __global__ void __launch_bounds__(kWThreads) weight_kernel(const __grid_constant
     double target = 0.0;
     int found = -1;
     if (MODE == 2) {
-        target = ok ? P.target[row] : 0.0;
-        if (!ok) found = 0;
+        target = active ? P.target[row] : 0.0;
+        if (!active) found = 0;
     }
     const T inv_c = static_cast<T>(P.inv_c);
 
@@ -155,7 +162,7 @@ __global__ void __launch_bounds__(kWThreads) weight_kernel(const __grid_constant
                 if (DN > 0) {
                     double st;
                     double pg = exp2_tab<true>(acc, tab, st);
-                    w = st * pg;
+                    w = __dmul_rn(st, pg);  // no contraction: MODE 1 and MODE 2 must produce the same running sums
                 }
                 if (MODE == 0) {
                     // w Phi(z) from the JOINT kernel value E = w exp(-z^2/2) = 2^(acc - dl^2) and the tail factor
@@ -166,7 +173,7 @@ __global__ void __launch_bounds__(kWThreads) weight_kernel(const __grid_constant
                     double q = (st2 * pg2) * normal_tail_tg(fabs(dl) * inv_c);
                     sp += (dl < 0.0) ? q : (w - q);
                 }
-                sw += w;
+                sw = __dadd_rn(sw, w);
                 if (MODE == 2) {
                     if (found < 0 && sw > target) found = base + i;
                 }
@@ -224,7 +231,13 @@ __global__ void __launch_bounds__(kWThreads) weight_kernel(const __grid_constant
 
     if (!ok) return;
     if (MODE == 2) {
-        P.idx[row] = found >= 0 ? found : static_cast<int>(P.n - 1);
+        // the split was selected with the same predicate on the same running sums, so an active row always finds its
+        // index; the last row of the split is the defensive default
+        if (active) {
+            long long last = static_cast<long long>(t1) * kWTile;
+            if (last > P.n) last = P.n;
+            P.idx[row] = found >= 0 ? found : static_cast<int>(last - 1);
+        }
     } else {
         P.part[static_cast<long long>(blockIdx.y) * P.m_pad + row] = sw;
         if (MODE == 0) P.part[(static_cast<long long>(P.n_splits) + blockIdx.y) * P.m_pad + row] = sp;
@@ -242,7 +255,9 @@ struct WFinal {
     int* n_flagged;
     const void* u;     // sampling: uniform draws in the data's dtype
     int u_f64;
-    double* target;    // sampling: u * S (+inf when the weights underflow: index N-1 as in the reference)
+    double* target;    // sampling: weight left to accumulate inside the selected split
+    int* sel_split;    // sampling: selected split per row (-1: none)
+    int* idx;          // sampling: preset to N - 1, the reference's default
 };
 
 __global__ void cdf_finalize_kernel(WFinal F) {
@@ -316,7 +331,27 @@ __global__ void sample_target_kernel(WFinal F) {
     double sw = 0;
     for (int s = 0; s < F.n_splits; ++s) sw += F.part[(long long)s * F.m_pad + row];
     double u = F.u_f64 ? static_cast<const double*>(F.u)[row] : (double)static_cast<const float*>(F.u)[row];
-    F.target[row] = (sw >= F.thresh) ? u * sw : INFINITY;
+    // the index is the first training row whose running weight sum exceeds u * S: find the split it lies in from the
+    // split totals (added in split order), keep what is left to accumulate inside that split.  Weights that underflow
+    // (S below the threshold), NaN evidence and u * S >= S by rounding leave the reference's default, row N - 1.
+    int sel = -1;
+    double rest = 0.0;
+    if (sw >= F.thresh) {
+        const double target = u * sw;
+        double prefix = 0.0;
+        for (int s = 0; s < F.n_splits; ++s) {
+            const double ps = F.part[(long long)s * F.m_pad + row];
+            if (ps > target - prefix) {
+                sel = s;
+                rest = target - prefix;
+                break;
+            }
+            prefix += ps;
+        }
+    }
+    F.target[row] = rest;
+    F.sel_split[row] = sel;
+    F.idx[row] = static_cast<int>(F.n - 1);
 }
 
 // Rows whose unshifted weight sum underflowed: the reference's arithmetic, term by term (weights
@@ -488,9 +523,11 @@ int sample_indices_device(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* ev, c
     double* part = nullptr;
     void* d_u = nullptr;
     double* target = nullptr;
+    int* sel_split = nullptr;
     PBN_CUDA_TRY(cudaMallocAsync(&part, (size_t)P.n_splits * P.m_pad * sizeof(double), st));
     PBN_CUDA_TRY(cudaMallocAsync(&d_u, (size_t)m * es, st));
     PBN_CUDA_TRY(cudaMallocAsync(&target, (size_t)m * sizeof(double), st));
+    PBN_CUDA_TRY(cudaMallocAsync(&sel_split, (size_t)m * sizeof(int), st));
     PBN_CUDA_TRY(cudaMemcpyAsync(d_u, h_random_prob, (size_t)m * es, cudaMemcpyHostToDevice, st));
     ctx->h2d += (int64_t)(m * es);
     P.part = part;
@@ -511,12 +548,15 @@ int sample_indices_device(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* ev, c
     F.u = d_u;
     F.u_f64 = f64 ? 1 : 0;
     F.target = target;
+    F.sel_split = sel_split;
+    F.idx = d_idx;
     sample_target_kernel<<<(int)((m + 255) / 256), 256, 0, st>>>(F);
     ctx->launches++;
     PBN_CUDA_TRY(cudaGetLastError());
     P.target = target;
+    P.sel_split = sel_split;
     P.idx = d_idx;
-    dim3 grid2((unsigned)((m + kWThreads - 1) / kWThreads), 1);
+    dim3 grid2((unsigned)((m + kWThreads - 1) / kWThreads), (unsigned)P.n_splits);
     {
         cudaError_t le = f64 ? launch_weight<double, 2>(P, grid2, st) : launch_weight<float, 2>(P, grid2, st);
         PBN_CUDA_TRY(le);
@@ -525,6 +565,7 @@ int sample_indices_device(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* ev, c
     PBN_CUDA_TRY(cudaFreeAsync(part, st));
     PBN_CUDA_TRY(cudaFreeAsync(d_u, st));
     PBN_CUDA_TRY(cudaFreeAsync(target, st));
+    PBN_CUDA_TRY(cudaFreeAsync(sel_split, st));
     PBN_CUDA_TRY(cudaFreeAsync(ytest, st));
     return PBN_OK;
 }
