@@ -10,6 +10,11 @@
 // The reference materialises N x 64 matrices (weights, conditional means, cdf values, prefix sums) in global
 // memory per chunk of 64 test rows; here every (train, test) pair lives in registers.
 //
+// Kernels: the cdf of families of up to 8 variables is the CDF mode of the fused pair kernel (pair_kernel.cuh:
+// pair_kernel<T, D, CKDE, CDF = true>, same stream-K schedule and partial-sum slots as logl; its finalize is
+// cdf_finalize_pair_kernel below).  weight_kernel below serves (MODE 0) the cdf of wider families with a run-time
+// dimension, (MODE 1) the weight totals and (MODE 2) the index scan of the sampler.
+//
 // Both use the whitened layout of the fitted CKDE (runtime.cu: fit_impl): y = c L^-1 (x - mu) with the
 // conditioned variable stored LAST.  Then, for a test row t and a training row i,
 //   weight      w_ti  = exp(-1/2 |L_e^-1 (e_t - e_i)|^2)          = 2^(-(sum_{c<p} (yt_c - yi_c)^2) [/K])
@@ -17,7 +22,8 @@
 // because the last row of L^-1 is (x - H_ve H_ee^-1 e) / sqrt(Schur complement): the conditional mean
 // x_i + H_ve H_ee^-1 (e_t - e_i) and variance of CKDE.hpp:594-616 are already inside the whitening matrix.
 //   cdf(t)   = sum_i w_ti Phi_ti / sum_i w_ti                       (no evidence: 1/N sum_i Phi_ti)
-//   index(t) = first i with (sum_{j<=i} w_tj) > u_t sum_j w_tj,  N-1 if none   (find_random_indices)
+//   index(t) = first i with (sum_{j<=i} w_tj) > u_t sum_j w_tj,  N-1 if none   (find_random_indices); the sum is taken
+//              hierarchically: split totals in split order, then the running sum inside the selected split
 #include "internal.h"
 
 #include <random>
