@@ -80,3 +80,49 @@ def test_kernel_sum_is_additive_over_training_partition_and_order(setup):
     k.fit(pbn.DataFrame(train.iloc[perm]))
     k.bandwidth = H
     assert np.allclose(k.logl(sub), full, rtol=1e-11, atol=1e-12)
+
+
+# ---- CKDE.cdf / CKDE.sample at the full training size ---------------------------------------------
+def test_cdf_full_training_set_subsample_and_properties(setup):
+    """1M training rows: a 48-row sub-sample against the oracle; the cdf is a probability, monotone in the variable for
+    fixed evidence, and tends to 0 / 1 far below / above the data."""
+    pbn, train, test, ftrain, ftest, cpd, logl = setup
+    sub = test.iloc[np.random.default_rng(3).choice(N, 48, replace=False)]
+    got = cpd.cdf(sub)
+    X = train[VARS].to_numpy()
+    want = oracle.ckde_cdf(X, sub[VARS].to_numpy(), cpd.kde_joint().bandwidth)
+    assert np.allclose(got, want, rtol=1e-10, atol=1e-10)
+    block = test.iloc[:50_000]
+    c = cpd.cdf(block)
+    assert np.all((c >= 0) & (c <= 1)) and 0.45 < c.mean() < 0.55
+    # fixed evidence, increasing d
+    base = test.iloc[:200].copy()
+    lo, hi = base.copy(), base.copy()
+    lo["d"] = base["d"] - 0.25
+    hi["d"] = base["d"] + 0.25
+    c0, c1, c2 = cpd.cdf(lo), cpd.cdf(base), cpd.cdf(hi)
+    assert np.all(c0 <= c1) and np.all(c1 <= c2) and np.any(c0 < c2)
+    far = base.copy()
+    far["d"] = base["d"] + 50.0
+    assert np.allclose(cpd.cdf(far), 1.0, rtol=0, atol=1e-12)
+    far["d"] = base["d"] - 50.0
+    assert np.allclose(cpd.cdf(far), 0.0, rtol=0, atol=1e-12)
+
+
+def test_sample_full_training_set(setup):
+    """Indices chosen against 1M training rows equal the oracle's on a 64-row sub-sample; the sampled values follow the
+    conditional law of the generator (d | a, b, c is linear-Gaussian with sd 0.5)."""
+    pbn, train, test, ftrain, ftest, cpd, logl = setup
+    n = 64
+    ev = test.iloc[:n][["a", "b", "c"]]
+    arr, idx = cpd.sample(n, ev, 123, _return_indices=True)
+    X = train[VARS].to_numpy()
+    want, want_idx = oracle.ckde_sample(X, cpd.kde_joint().bandwidth, ev.to_numpy(), n, 123)
+    assert np.array_equal(idx, want_idx)
+    assert np.allclose(arr.to_numpy(), want, rtol=1e-12, atol=1e-10)
+    n = 20_000
+    ev = test.iloc[:n][["a", "b", "c"]]
+    s, idx = cpd.sample(n, ev, 7, _return_indices=True)
+    assert idx.min() >= 0 and idx.max() < N
+    resid = s.to_numpy() - (1.5 - 0.9 * ev["a"] + 5.6 * ev["b"] + 0.3 * ev["c"]).to_numpy()
+    assert abs(resid.mean()) < 0.05 and 0.4 < resid.std() < 0.75
