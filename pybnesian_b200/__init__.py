@@ -8,10 +8,11 @@ from ._lib import SingularCovarianceData, Context, default_context, LIB_PATH
 from .dataset import DataFrame, CrossValidation, HoldOut
 from .kde import BandwidthSelector, NormalReferenceRule, ScottsBandwidth, UCV, UCVScorer, KDE, ProductKDE
 from .factors import (Factor, FactorType, CKDE, CKDEType, LinearGaussianCPD, LinearGaussianCPDType,
-                      UnknownFactorType)
-from .hybrid import Assignment, DiscreteFactor, DiscreteFactorType, HCKDE, CLinearGaussianCPD
+                      UnknownFactorType, MLE, MLELinearGaussianCPD, LinearGaussianParams)
+from .hybrid import (Assignment, DiscreteFactor, DiscreteFactorType, HCKDE, CLinearGaussianCPD, MLEDiscreteFactor,
+                     DiscreteFactorParams)
 from .models import (Dag, BayesianNetwork, BayesianNetworkType, GaussianNetwork, GaussianNetworkType, KDENetwork,
-                     KDENetworkType, SemiparametricBN, SemiparametricBNType, load)
+                     KDENetworkType, SemiparametricBN, SemiparametricBNType, HeterogeneousBN, HeterogeneousBNType, load)
 from .scores import (Args, Kwargs, Arguments, Score, ValidatedScore, CVLikelihood, HoldoutLikelihood,
                      ValidatedLikelihood)
 from .operators import (Operator, ArcOperator, AddArc, RemoveArc, FlipArc, ChangeNodeType, OperatorTabuSet,

@@ -267,6 +267,45 @@ class LinearGaussianCPD(Factor):
     __repr__ = __str__
 
 
+class LinearGaussianParams:
+    """pybnesian.LinearGaussianParams (pybindings_parameters.cpp:43-62): beta (intercept first) and variance."""
+
+    def __init__(self, beta, variance):
+        self.beta = np.asarray(beta, dtype=np.float64).ravel().copy()
+        self.variance = float(variance)
+
+
+class MLELinearGaussianCPD:
+    """MLE<LinearGaussianCPD> (learning/parameters/mle_LinearGaussianCPD.hpp:11-221) on the resident table
+    (include/pbn_cuda.h: pbn_lg_fit).  Created with MLE(LinearGaussianCPDType())."""
+
+    def estimate(self, df, variable, evidence):
+        import ctypes
+        from ._lib import check, int_array
+        frame = DataFrame.wrap(df)
+        variable = frame.column_name(variable)
+        evidence = [frame.column_name(e) for e in evidence]
+        variables = [variable] + evidence
+        frame.dtype_code(variables, "fit LinearGaussianCPD")
+        tbl, cols, _ = frame.device_table(variables)
+        beta = np.empty(len(cols))
+        var = ctypes.c_double()
+        check(lib().pbn_lg_fit(tbl.ctx.handle, tbl.handle, int_array(cols), len(cols), tbl.rows(),
+                               beta.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), ctypes.byref(var)))
+        return LinearGaussianParams(beta, var.value)
+
+
+def MLE(factor_type):
+    """pybnesian.MLE (pybindings_parameters.cpp:31-40, pybindings_mle.cpp): only the factor types with a closed-form
+    estimator have one; the CKDE is fitted, not estimated."""
+    from . import hybrid
+    if factor_type == LinearGaussianCPDType():
+        return MLELinearGaussianCPD()
+    if factor_type == hybrid.DiscreteFactorType():
+        return hybrid.MLEDiscreteFactor()
+    raise ValueError("MLE not available for factor type " + str(factor_type) + ".")
+
+
 class CKDEType(FactorType):
     """factors/continuous/CKDE.hpp:17-60, CKDE.cpp:15-41 (a discrete parent makes it an HCKDE)."""
 

@@ -329,6 +329,25 @@ class DiscreteFactor(Factor):
     __repr__ = __str__
 
 
+class DiscreteFactorParams:
+    """pybnesian.DiscreteFactorParams (pybindings_parameters.cpp:93-130): the log-probability table, one axis per
+    variable (variable first)."""
+
+    def __init__(self, logprob):
+        self.logprob = np.asarray(logprob, dtype=np.float64)
+
+
+class MLEDiscreteFactor:
+    """MLE<DiscreteFactor> (learning/parameters/mle_DiscreteFactor.cpp:14-36)."""
+
+    def estimate(self, df, variable, evidence):
+        frame = DataFrame.wrap(df)
+        f = DiscreteFactor(frame.column_name(variable), [frame.column_name(e) for e in evidence])
+        f.fit(frame)
+        shape = [int(c) for c in f._cardinality]
+        return DiscreteFactorParams(f._logprob.reshape(shape, order="F"))
+
+
 # ----------------------------------------------------------------------------------------------
 # DiscreteAdaptator (factors/discrete/DiscreteAdaptator.hpp:88-568)
 # ----------------------------------------------------------------------------------------------

@@ -406,6 +406,80 @@ class SemiparametricBNType(BayesianNetworkType):
     __repr__ = __str__
 
 
+class HeterogeneousBNType(BayesianNetworkType):
+    """models/HeterogeneousBN.hpp:28-196: the default factor types of a node are given by the user, either one list for
+    every data type or one list per Arrow data type (first entry = default, compared by type id as DataTypeEqualTo)."""
+
+    def __new__(cls, *a, **k):  # parametrised: not a per-class singleton
+        return object.__new__(cls)
+
+    def __init__(self, default_factor_types):
+        if isinstance(default_factor_types, dict):
+            self._single = False
+            self._ftype = []
+            self._ftypes = {dt: list(fts) for dt, fts in default_factor_types.items() if list(fts)}
+            if not self._ftypes:
+                raise ValueError("Default factor_type cannot be empty.")
+            for dt, fts in self._ftypes.items():
+                if dt is None:
+                    raise ValueError("Default factor_types cannot contain null DataType.")
+                if any(f is None for f in fts):
+                    raise ValueError("Default factor_type cannot contain null FactorType.")
+        else:
+            self._single = True
+            self._ftype = list(default_factor_types)
+            self._ftypes = {}
+            if not self._ftype:
+                raise ValueError("Default factor_type cannot be empty.")
+            if any(f is None for f in self._ftype):
+                raise ValueError("Default factor_type cannot contain null FactorType.")
+
+    def is_homogeneous(self):
+        return False
+
+    def default_node_type(self):
+        raise RuntimeError("default_node_type() for HeterogeneousBN is not defined.")
+
+    def data_default_node_type(self, datatype):
+        if self._single:
+            return list(self._ftype)
+        for dt, fts in self._ftypes.items():
+            if dt.id == datatype.id:
+                return list(fts)
+        raise ValueError("Not valid FactorType for DataType " + str(datatype))
+
+    def single_default(self):
+        return self._single
+
+    def default_node_types(self):
+        return {None: list(self._ftype)} if self._single else {dt: list(f) for dt, f in self._ftypes.items()}
+
+    def new_bn(self, nodes):
+        return HeterogeneousBN(self._ftype if self._single else self._ftypes, nodes)
+
+    def _key(self):
+        if self._single:
+            return ("single", tuple(str(f) for f in self._ftype))
+        return ("multi", frozenset((dt.id, tuple(str(f) for f in fts)) for dt, fts in self._ftypes.items()))
+
+    def __eq__(self, other):
+        return isinstance(other, HeterogeneousBNType) and self._key() == other._key()
+
+    def __hash__(self):
+        return hash(self._key())
+
+    def __str__(self):
+        if self._single:
+            return "HeterogeneousBNType([" + ", ".join(str(f) for f in self._ftype) + "])"
+        return "HeterogeneousBNType({" + ", ".join(str(dt) + ": [" + ", ".join(str(f) for f in fts) + "]"
+                                                    for dt, fts in self._ftypes.items()) + "})"
+
+    __repr__ = __str__
+
+    def __reduce__(self):
+        return (HeterogeneousBNType, (self._ftype if self._single else self._ftypes,))
+
+
 # ----------------------------------------------------------------------------------------------
 # BayesianNetwork (models/BayesianNetwork.hpp:262-1000, unconditional networks only)
 # ----------------------------------------------------------------------------------------------
@@ -792,3 +866,16 @@ def load(filename):
     """pybnesian.load (util/pickle.hpp, lib.cpp:38-43): the object saved by any `.save()` of this package."""
     with open(filename, "rb") as f:
         return pickle.load(f)
+
+
+class HeterogeneousBN(BayesianNetwork):
+    """pybnesian.HeterogeneousBN (models/HeterogeneousBN.hpp:198-290): HeterogeneousBN(factor_types, nodes | arcs | graph
+    [, node_types]) with factor_types a list of FactorType or {pyarrow.DataType: [FactorType]}."""
+
+    def __init__(self, factor_types, nodes=None, arcs=None, node_types=None, graph=None):
+        bn_type = factor_types if isinstance(factor_types, HeterogeneousBNType) else HeterogeneousBNType(factor_types)
+        # (nodes, node_types) and (arcs, node_types) positional forms of the reference constructors
+        if arcs is not None and node_types is None and arcs and all(
+                isinstance(a, tuple) and len(a) == 2 and isinstance(a[1], FactorType) for a in arcs):
+            arcs, node_types = None, arcs
+        super().__init__(bn_type, nodes, arcs, node_types, graph)

@@ -302,3 +302,25 @@ def test_multi_gpu_shards_match_single_gpu():
            "--master-port", "29517", os.path.join(root, "tools", "multi_gpu_check.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0 and "MULTI_GPU_CHECK_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+def test_mle_linear_gaussian_like_the_reference_test(pbn):
+    """tests/learning/parameters/mle_test.py: MLE(LinearGaussianCPDType()).estimate against numpy lstsq;
+    MLE(CKDEType()) is not available."""
+    df = util_data.generate_normal_data(10000, 0)
+    with pytest.raises(ValueError, match="MLE not available"):
+        pbn.MLE(pbn.CKDEType())
+    mle = pbn.MLE(pbn.LinearGaussianCPDType())
+    for variable, evidence in [("a", []), ("b", ["a"]), ("c", ["a", "b"]), ("d", ["a", "b", "c"])]:
+        p = mle.estimate(df, variable, evidence)
+        A = np.column_stack([np.ones(len(df))] + [df[e].to_numpy() for e in evidence])
+        beta, res, _, _ = np.linalg.lstsq(A, df[variable].to_numpy(), rcond=None)
+        assert np.allclose(p.beta, beta, rtol=1e-8, atol=1e-10)
+        assert np.isclose(p.variance, res[0] / (len(df) - len(evidence) - 1), rtol=1e-9)
+    dfn = df.copy()
+    dfn.loc[5, "a"] = np.nan
+    p = mle.estimate(dfn, "b", ["a"])
+    sub = dfn.dropna()
+    A = np.column_stack([np.ones(len(sub)), sub["a"].to_numpy()])
+    beta, _, _, _ = np.linalg.lstsq(A, sub["b"].to_numpy(), rcond=None)
+    assert np.allclose(p.beta, beta, rtol=1e-8)

@@ -284,3 +284,49 @@ def test_pbn_uniform_real_is_the_libstdcxx_stream():
         out = np.empty(33, dtype=dt)
         assert _lib.lib().pbn_uniform_real(33, 7, code, out.ctypes.data_as(ctypes.c_void_p)) == 0
         assert np.array_equal(out, oracle.uniform_real(33, 7, dt))
+
+
+def test_mle_discrete_factor():
+    tr = util_data.generate_hybrid_data(2000, 0)
+    p = pbn.MLE(pbn.DiscreteFactorType()).estimate(tr, "B", ["A"])
+    assert p.logprob.shape == (3, 2)
+    assert np.allclose(np.exp(p.logprob).sum(axis=0), 1.0)
+    tab = pd.crosstab(tr["B"], tr["A"], normalize="columns").to_numpy()
+    assert np.allclose(np.exp(p.logprob), tab, rtol=1e-12)
+
+
+def test_heterogeneous_bn_type_equality_like_the_reference_test():
+    """tests/models/HeterogeneousBN_test.py:5-55."""
+    nodes = ["a", "b", "c", "d"]
+    het_single = pbn.HeterogeneousBN([pbn.CKDEType(), pbn.LinearGaussianCPDType()], nodes)
+    het2_single = pbn.HeterogeneousBN([pbn.CKDEType(), pbn.LinearGaussianCPDType()], nodes)
+    assert het_single.type() == het2_single.type()
+    het3_single = pbn.HeterogeneousBN([pbn.LinearGaussianCPDType(), pbn.CKDEType()], nodes)
+    assert het_single.type() != het3_single.type()
+    cont = [pbn.CKDEType(), pbn.LinearGaussianCPDType()]
+    het_dt = pbn.HeterogeneousBN({pa.float64(): cont, pa.float32(): cont,
+                                  pa.dictionary(pa.int8(), pa.string()): [pbn.DiscreteFactorType()]}, nodes)
+    het2_dt = pbn.HeterogeneousBN({pa.dictionary(pa.int8(), pa.string()): [pbn.DiscreteFactorType()],
+                                   pa.float32(): cont, pa.float64(): cont}, nodes)
+    assert het_dt.type() == het2_dt.type()  # the order of the map is not relevant
+    het3_dt = pbn.HeterogeneousBN({pa.dictionary(pa.int8(), pa.string()): [pbn.DiscreteFactorType()],
+                                   pa.float32(): [pbn.LinearGaussianCPDType(), pbn.CKDEType()], pa.float64(): cont}, nodes)
+    assert het_dt.type() != het3_dt.type()  # the order of the default FactorTypes is relevant
+    assert het_single.type() != pbn.HeterogeneousBN({pa.float64(): cont}, nodes).type()
+    # the rest of the type's surface
+    t = het_dt.type()
+    assert not t.is_homogeneous() and not t.single_default() and het_single.type().single_default()
+    assert t.data_default_node_type(pa.dictionary(pa.int32(), pa.string())) == [pbn.DiscreteFactorType()]  # by type id
+    assert t.data_default_node_type(pa.float32()) == cont
+    with pytest.raises(ValueError, match="Not valid FactorType"):
+        pbn.HeterogeneousBNType({pa.float64(): cont}).data_default_node_type(pa.float32())
+    with pytest.raises(ValueError, match="cannot be empty"):
+        pbn.HeterogeneousBNType([])
+    with pytest.raises(RuntimeError):
+        t.default_node_type()
+    r = pickle.loads(pickle.dumps(het_dt))
+    assert type(r) is pbn.HeterogeneousBN and r.type() == t and r.nodes() == nodes
+    assert type(t.new_bn(["x", "y"])) is pbn.HeterogeneousBN
+    assert all(het_dt.node_type(n) == pbn.UnknownFactorType() for n in nodes)
+    m = pbn.HeterogeneousBN(cont, nodes, [("a", "b")], [("a", pbn.LinearGaussianCPDType())])
+    assert m.has_arc("a", "b") and m.node_type("a") == pbn.LinearGaussianCPDType()

@@ -374,3 +374,21 @@ def test_clg_sample_and_hybrid_network_sample(pbn):
     sel_t = (tr["A"] == "a1") & (tr["B"] == "b2")
     assert abs(s.loc[sel_s, "D"].mean() - tr.loc[sel_t, "D"].mean()) < 0.5
     assert s.equals(m.sample(2000, 3, ordered=True))
+
+
+def test_heterogeneous_bn_fit_and_default_types(pbn):
+    """A HeterogeneousBN whose continuous default is CKDE: fit() gives every node the first default type of its data
+    type (BayesianNetwork.hpp:965-976), HCKDE / DiscreteFactor included, and equals the SemiparametricBN with the same
+    node types."""
+    tr, te = frames(1200, 200, "float64")
+    types = {pa.float64(): [pbn.CKDEType(), pbn.LinearGaussianCPDType()],
+             pa.dictionary(pa.int8(), pa.string()): [pbn.DiscreteFactorType()]}
+    arcs = [("A", "B"), ("A", "D"), ("C", "D")]
+    m = pbn.HeterogeneousBN(types, ["A", "B", "C", "D"], arcs)
+    m.fit(tr)
+    assert m.node_type("C") == pbn.CKDEType() and m.node_type("A") == pbn.DiscreteFactorType()
+    assert isinstance(m.cpd("D"), pbn.HCKDE) and isinstance(m.cpd("C"), pbn.CKDE)
+    s = pbn.SemiparametricBN(["A", "B", "C", "D"], arcs, [("C", pbn.CKDEType()), ("D", pbn.CKDEType())])
+    s.fit(tr)
+    close(m.logl(te), s.logl(te), 1e-12)
+    assert len(m.sample(50, 1)) == 50
