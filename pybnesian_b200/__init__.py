@@ -13,7 +13,7 @@ from .hybrid import (Assignment, DiscreteFactor, DiscreteFactorType, HCKDE, CLin
                      DiscreteFactorParams)
 from .models import (Dag, BayesianNetwork, BayesianNetworkType, GaussianNetwork, GaussianNetworkType, KDENetwork,
                      KDENetworkType, SemiparametricBN, SemiparametricBNType, HeterogeneousBN, HeterogeneousBNType, load)
-from .scores import (Args, Kwargs, Arguments, Score, ValidatedScore, CVLikelihood, HoldoutLikelihood,
+from .scores import (Args, Kwargs, Arguments, Score, ValidatedScore, BIC, CVLikelihood, HoldoutLikelihood,
                      ValidatedLikelihood)
 from .operators import (Operator, ArcOperator, AddArc, RemoveArc, FlipArc, ChangeNodeType, OperatorTabuSet,
                         LocalScoreCache, OperatorSet, ArcOperatorSet, ChangeNodeTypeSet, OperatorPool)

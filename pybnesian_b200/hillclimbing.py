@@ -10,7 +10,7 @@ import time
 from .dataset import DataFrame
 from .factors import FactorType
 from .operators import ArcOperatorSet, ChangeNodeTypeSet, LocalScoreCache, OperatorPool, OperatorSet, OperatorTabuSet
-from .scores import CVLikelihood, HoldoutLikelihood, Score, ValidatedLikelihood, ValidatedScore
+from .scores import BIC, CVLikelihood, HoldoutLikelihood, Score, ValidatedLikelihood, ValidatedScore
 
 MACHINE_TOL = 1.4901161193847656e-08  # util::machine_tol = sqrt(DBL_EPSILON) (util/math_constants.hpp:30)
 INT_MAX = 2147483647
@@ -177,8 +177,10 @@ def _check_valid_score(df, bn_type, score, seed, num_folds, test_holdout_ratio):
             return HoldoutLikelihood(df, test_holdout_ratio, seed)
         if score == "validated-lik":
             return ValidatedLikelihood(df, test_holdout_ratio, num_folds, seed)
-        if score in ("bic", "bge"):
-            raise NotImplementedError("score \"%s\" is outside the likelihood-score path of pybnesian_b200" % score)
+        if score == "bic":
+            return BIC(df)
+        if score == "bge":
+            raise NotImplementedError("score \"bge\" is outside the likelihood-score path of pybnesian_b200")
         raise ValueError("Wrong Bayesian Network score \"" + score + "\" specified. The possible alternatives are "
                          "\"bic\" (Bayesian Information Criterion), \"bge\" (Bayesian Gaussian equivalent), "
                          "\"cv-lik\" (Cross-Validated likelihood), \"holdout-l\" (Hold-out likelihood) "
@@ -186,7 +188,7 @@ def _check_valid_score(df, bn_type, score, seed, num_folds, test_holdout_ratio):
     if bn_type == SemiparametricBNType() or bn_type == KDENetworkType():
         return ValidatedLikelihood(df, test_holdout_ratio, num_folds, seed)
     if bn_type == GaussianNetworkType():
-        raise NotImplementedError("the default score of GaussianNetwork (bic) is outside the path of pybnesian_b200")
+        return BIC(df)
     raise ValueError("Default score not defined for " + str(bn_type) + ".")
 
 

@@ -410,3 +410,90 @@ class ValidatedLikelihood(ValidatedScore):
         return "ValidatedLikelihood"
 
     __repr__ = __str__
+
+
+class BIC(Score):
+    """pybnesian.BIC (learning/scores/bic.{hpp,cpp}): closed-form Bayesian information criterion of linear Gaussian,
+    conditional linear Gaussian and discrete nodes.  The linear-Gaussian fits run on the resident table
+    (pbn_lg_fit through MLELinearGaussianCPD); everything else is host integer / scalar work as in the reference.
+    The default score of GaussianNetwork hill climbing (util/validate_options.cpp:36-44)."""
+
+    _MACHINE_TOL = float(np.sqrt(np.finfo(np.float64).eps))
+
+    def __init__(self, df):
+        self._frame = DataFrame.wrap(df)
+
+    def data(self):
+        return self._frame
+
+    def _bic_lineargaussian(self, frame, variable, parents):
+        from .factors import MLELinearGaussianCPD
+        p = MLELinearGaussianCPD().estimate(frame, variable, parents)
+        if p.variance < self._MACHINE_TOL or np.isinf(p.variance):
+            return None
+        rows = frame.valid_rows([variable] + list(parents))
+        k = len(parents)
+        return 0.5 * (1 + float(k) - float(rows)) - 0.5 * rows * np.log(2 * np.pi) - rows * 0.5 * np.log(p.variance), rows
+
+    def _bic_clg(self, variable, discrete_parents, continuous_parents):
+        from . import hybrid
+        frame = self._frame
+        card, strides = hybrid.create_cardinality_strides(frame, discrete_parents)
+        num_configs = int(card.prod())
+        order, offsets = hybrid.discrete_slices(frame, discrete_parents, strides, num_configs)
+        sub = frame.loc([variable] + list(continuous_parents))
+        loglik = 0.0
+        for i in range(num_configs):
+            rows = order[int(offsets[i]):int(offsets[i + 1])]
+            if rows.size == 0:
+                continue
+            r = self._bic_lineargaussian(sub.take(rows), variable, continuous_parents)
+            if r is None:
+                return -np.inf
+            loglik += r[0]
+        valid = frame.valid_rows([variable] + list(discrete_parents) + list(continuous_parents))
+        return loglik - np.log(valid) * 0.5 * num_configs * (len(continuous_parents) + 2)
+
+    def _bic_discrete(self, variable, parents):
+        from . import hybrid
+        f = hybrid.DiscreteFactor(variable, parents)
+        card, strides = hybrid.create_cardinality_strides(self._frame, [variable] + list(parents))
+        idx, _ = f._indices(self._frame, strides)
+        counts = np.bincount(idx, minlength=int(card.prod())).astype(np.int64).reshape(-1, int(card[0]))
+        ll = 0.0
+        for row in counts:  # per parent configuration, categories in order (bic.cpp:73-92)
+            tot = int(row.sum())
+            if tot > 0:
+                inv = 1.0 / tot
+                for c in row:
+                    if c > 0:
+                        ll += float(c) * np.log(float(c) * inv)
+        return ll - np.log(float(counts.sum())) * 0.5 * (int(card[0]) - 1) * counts.shape[0]
+
+    def local_score(self, model, variable, evidence=None):
+        if evidence is None:
+            evidence = model.parents(variable)
+        return self.local_score_node_type(model, model.underlying_node_type(self._frame, variable), variable, evidence)
+
+    def local_score_node_type(self, model, variable_type, variable, evidence):
+        from .factors import LinearGaussianCPDType
+        from .hybrid import DiscreteFactorType
+        evidence = list(evidence)
+        if variable_type == LinearGaussianCPDType():
+            disc = [p for p in evidence if model.underlying_node_type(self._frame, p) == DiscreteFactorType()]
+            cont = [p for p in evidence if p not in disc]
+            if not disc:
+                r = self._bic_lineargaussian(self._frame, variable, evidence)
+                if r is None:
+                    return -np.inf
+                return float(r[0] - np.log(r[1]) * 0.5 * (len(evidence) + 2))
+            return float(self._bic_clg(variable, disc, cont))
+        if variable_type == DiscreteFactorType():
+            if any(model.underlying_node_type(self._frame, p) != DiscreteFactorType() for p in evidence):
+                raise ValueError("Local score for discrete variable " + variable + " cannot be calculated because the "
+                                 "parents/evidence contains non-discrete variables.")
+            return float(self._bic_discrete(variable, evidence))
+        raise ValueError("Bayesian network type \"" + str(model.type()) + "\" not valid for score BIC")
+
+    def __str__(self):
+        return "BIC"

@@ -324,3 +324,48 @@ def test_mle_linear_gaussian_like_the_reference_test(pbn):
     A = np.column_stack([np.ones(len(sub)), sub["a"].to_numpy()])
     beta, _, _, _ = np.linalg.lstsq(A, sub["b"].to_numpy(), rcond=None)
     assert np.allclose(p.beta, beta, rtol=1e-8)
+
+
+def _numpy_bic(data, variable, evidence):
+    """tests/learning/scores/bic_test.py:10-30."""
+    from scipy.stats import norm
+    nd = data[[variable] + evidence].dropna()
+    N, d = len(nd), len(evidence)
+    A = np.column_stack([np.ones(N)] + [nd[e].to_numpy() for e in evidence])
+    beta, res, _, _ = np.linalg.lstsq(A, nd[variable].to_numpy(), rcond=None)
+    var = res[0] / (N - d - 1)
+    means = A @ beta
+    return norm.logpdf(nd[variable].to_numpy(), means, np.sqrt(var)).sum() - np.log(N) * 0.5 * (d + 2)
+
+
+def test_bic_like_the_reference_test_and_gaussian_hc(pbn):
+    df = util_data.generate_normal_data(10000, 0)
+    gbn = pbn.GaussianNetwork(["a", "b", "c", "d"], [("a", "b"), ("a", "c"), ("a", "d"), ("b", "c"), ("b", "d"), ("c", "d")])
+    bic = pbn.BIC(df)
+    for v, e in [("a", []), ("b", ["a"]), ("c", ["a", "b"]), ("d", ["a", "b", "c"])]:
+        assert np.isclose(bic.local_score(gbn, v, e), _numpy_bic(df, v, e), rtol=1e-9)
+        assert bic.local_score(gbn, v) == bic.local_score(gbn, v, gbn.parents(v))
+    assert np.isclose(bic.local_score(gbn, "d", ["b", "c", "a"]), _numpy_bic(df, "d", ["a", "b", "c"]), rtol=1e-9)
+    assert np.isclose(bic.score(gbn), sum(_numpy_bic(df, v, gbn.parents(v)) for v in "abcd"), rtol=1e-9)
+    dfn = df.copy()
+    rng = np.random.default_rng(0)
+    for c in "abcd":
+        dfn.loc[rng.integers(0, len(df), 100), c] = np.nan
+    bn = pbn.BIC(dfn)
+    assert np.isclose(bn.local_score(gbn, "c", ["a", "b"]), _numpy_bic(dfn, "c", ["a", "b"]), rtol=1e-9)
+    # hillclimbing_test.py:8-60 with the GaussianNetwork defaults (score "bic", arc operators)
+    small = util_data.generate_normal_data(1000, 0)
+    start = pbn.GaussianNetwork(list(small.columns))
+    sb = pbn.BIC(small)
+    res = pbn.GreedyHillClimbing().estimate(pbn.ArcOperatorSet(), sb, start, max_iters=1)
+    assert res.num_arcs() == 1
+    added = res.arcs()[0]
+    delta = sb.score(res) - sb.score(start)
+    assert np.isclose(delta, sb.local_score(res, added[1], [added[0]]) - sb.local_score(res, added[1], []))
+    # BIC is score equivalent: blacklisting the arc adds its reverse
+    res2 = pbn.GreedyHillClimbing().estimate(pbn.ArcOperatorSet(), sb, start, max_iters=1, arc_blacklist=[added])
+    assert res2.arcs()[0] == added[::-1]
+    assert pbn.GreedyHillClimbing().estimate(pbn.ArcOperatorSet(), sb, start, epsilon=delta + 0.01).num_arcs() == 0
+    full = pbn.hc(small, bn_type=pbn.GaussianNetworkType())
+    assert type(full) is pbn.GaussianNetwork and full.num_arcs() >= 5
+    assert pbn.hc(small, bn_type=pbn.GaussianNetworkType(), score="bic").num_arcs() == full.num_arcs()
