@@ -249,8 +249,15 @@ class _FoldScorer:
                 out[pos] = results[key]
         return out
 
+    # several ranks: deal (item, fold) jobs instead of whole items (a hill-climbing step has only 20-40 candidates of
+    # very different cost).  Subclasses whose _run_items cannot score a fold range set this to False.
+    _fold_parallel = True
+
     def _score_native(self, code, items):
         rank, world = parallel.rank(), parallel.world_size()
+        nfolds = self.fold_end - self.fold_begin
+        if world > 1 and self._fold_parallel and nfolds > 1:
+            return self._score_native_by_fold(code, items, rank, world)
         # deal the items over the ranks, most expensive first (CKDE cost grows with the family size; LG is free)
         cost = [len(v) if f == _lib.FACTOR_CKDE else 0 for _, f, _, v in items]
         mine = parallel.deal(cost, rank, world) if world > 1 else list(range(len(items)))
@@ -263,11 +270,42 @@ class _FoldScorer:
             scores = parallel.all_reduce_sum(scores, self._ctx(code))
         return {items[i][0]: float(scores[i]) for i in range(len(items))}
 
+    def _score_native_by_fold(self, code, items, rank, world):
+        """(item, fold) jobs dealt over the ranks; every rank scores its jobs fold by fold (one pbn_cv_scores call per
+        fold), the [items x folds] matrix is summed over ranks (each entry written by exactly one rank) and the folds of
+        an item are added in fold order - the same additions as the single-GPU call."""
+        nfolds = self.fold_end - self.fold_begin
+        cost = []
+        for _, f, _, v in items:
+            cost.extend([len(v) if f == _lib.FACTOR_CKDE else 0] * nfolds)
+        mine = parallel.deal(cost, rank, world)
+        per_fold = {}
+        for job in mine:
+            per_fold.setdefault(job % nfolds, []).append(job // nfolds)
+        mat = np.zeros((len(items), nfolds))
+        for q in sorted(per_fold):
+            idx = per_fold[q]
+            f0 = self.fold_begin + q
+            mat[idx, q] = self._run_items(code, [items[i] for i in idx], f0, f0 + 1)
+            self.stats["device_items"] += len(idx)
+            self.stats["batches"] += 1
+        mat = parallel.all_reduce_sum(mat.ravel(), self._ctx(code)).reshape(len(items), nfolds)
+        out = {}
+        for i in range(len(items)):
+            total = 0.0
+            for q in range(nfolds):
+                total += float(mat[i, q])
+            out[items[i][0]] = total
+        return out
+
     def _ctx(self, code):
         return self._device(code)[0].tbl.ctx
 
-    def _run_items(self, code, items):
-        """One pbn_cv_scores call for `items` = [(key, factor, rule, variables)]; returns their scores."""
+    def _run_items(self, code, items, fold_begin=None, fold_end=None):
+        """One pbn_cv_scores call for `items` = [(key, factor, rule, variables)] over folds [fold_begin, fold_end)
+        (default: all folds of this scorer); returns their scores."""
+        fold_begin = self.fold_begin if fold_begin is None else fold_begin
+        fold_end = self.fold_end if fold_end is None else fold_end
         handle, index = self._device(code)
         arr = (CVItem * len(items))()
         for slot, (_, factor, rule, variables) in enumerate(items):
@@ -276,7 +314,7 @@ class _FoldScorer:
                 arr[slot].vars[q] = index[v]
         local = np.zeros(len(items))
         status = (ctypes.c_int * len(items))()
-        check(lib().pbn_cv_scores(handle.tbl.ctx.handle, handle.h, arr, len(items), self.fold_begin, self.fold_end,
+        check(lib().pbn_cv_scores(handle.tbl.ctx.handle, handle.h, arr, len(items), fold_begin, fold_end,
                                   local.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), status))
         bad = [s for s in status if s != _lib.PBN_OK]
         if bad:

@@ -38,6 +38,7 @@ idx, lim = oracle.cv_indices(np.arange(300), 5, 0)
 
 class CpuScorer(_FoldScorer):
     ran = []
+    _fold_parallel = False  # the oracle scores whole items; the (item, fold) dealing is covered on GPUs (tools/multi_gpu_check.py)
     def _ctx(self, code):
         return None
     def _run_items(self, code, items):
@@ -59,6 +60,31 @@ assert got == want, (got, want)
 n_mine = len(CpuScorer.ran)
 counts = parallel.all_reduce_sum(np.array([n_mine if rank == 0 else 0.0, n_mine if rank == 1 else 0.0]))
 assert counts.sum() == len(reqs) and abs(counts[0] - counts[1]) <= 1, counts
+# 3b. (item, fold) dealing: jobs of one item land on both ranks, the folds are added in fold order
+def fold_value(variables, f):
+    return 1.0 / (3.0 + len(variables) + 7.0 * f) + 0.001 * sum(ord(c) for v in variables for c in v)
+
+class FoldScorer(_FoldScorer):
+    calls = []
+    def _ctx(self, code):
+        return None
+    def _run_items(self, code, items, fold_begin=None, fold_end=None):
+        fb = self.fold_begin if fold_begin is None else fold_begin
+        fe = self.fold_end if fold_end is None else fold_end
+        FoldScorer.calls.append((fb, fe, len(items)))
+        return np.array([sum(fold_value(v, f) for f in range(fb, fe)) for _, _, _, v in items])
+
+fs = FoldScorer(pbn.DataFrame(data), idx, lim, 0, 5, pbn.Arguments())
+got = fs.score_batch(model, reqs)
+for (t, v, e), g in zip(reqs, got):
+    want_f = 0.0
+    for f in range(5):
+        want_f += fold_value([v] + e, f)
+    assert g == want_f, (v, e, g, want_f)
+assert all(fe - fb == 1 for fb, fe, _ in FoldScorer.calls) and len(FoldScorer.calls) <= 5
+jobs = sum(n for _, _, n in FoldScorer.calls)
+tot = parallel.all_reduce_sum(np.array([jobs if rank == 0 else 0.0, jobs if rank == 1 else 0.0]))
+assert tot.sum() == 5 * len(reqs) and abs(tot[0] - tot[1]) <= 1, tot
 # 4. hill climbing on top of the sharded engine makes the same decisions on every rank
 class ShardedScore(pbn.CVLikelihood):
     pass
