@@ -38,6 +38,52 @@ __device__ __forceinline__ void ucv_tile(const T* __restrict__ tp, int cnt, long
                 s1[r] = fma(e2, e2, s1[r]);
             }
         }
+    } else if constexpr (PBN_F32_PACKED && R % 2 == 0) {
+        // packed FP32 (FFMA2 / FADD2), two rows per instruction: see tile_f32_packed in pair_kernel.cuh
+        constexpr int H = R / 2;
+        f32x2_t nyi[H][D], f2[H], f1[H];
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+#pragma unroll
+            for (int c = 0; c < D; ++c) nyi[h][c] = pack_f32x2(-yi[2 * h][c], -yi[2 * h + 1][c]);
+            f2[h] = 0ull;
+            f1[h] = 0ull;
+        }
+#pragma unroll 4
+        for (int j = 0; j < cnt; ++j) {
+            float p[D];
+#pragma unroll
+            for (int c = 0; c < D; ++c) p[c] = tp[j * D + c];
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                f32x2_t sq = 0ull;
+#pragma unroll
+                for (int c = 0; c < D; ++c) {
+                    f32x2_t d2 = fadd2(pack_f32x2(p[c], p[c]), nyi[h][c]);
+                    sq = ffma2(d2, d2, sq);
+                }
+                float lo, hi;
+                unpack_f32x2(sq, lo, hi);
+                float e_lo = ex2_neg(lo), e_hi = ex2_neg(hi);
+                if (DIAG) {
+                    e_lo = (col0 + j < rowid[2 * h]) ? e_lo : 0.f;
+                    e_hi = (col0 + j < rowid[2 * h + 1]) ? e_hi : 0.f;
+                }
+                f32x2_t e2 = pack_f32x2(e_lo, e_hi);
+                f2[h] = fadd2(f2[h], e2);
+                f1[h] = ffma2(e2, e2, f1[h]);
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            float lo, hi;
+            unpack_f32x2(f2[h], lo, hi);
+            s2[2 * h] += (double)lo;
+            s2[2 * h + 1] += (double)hi;
+            unpack_f32x2(f1[h], lo, hi);
+            s1[2 * h] += (double)lo;
+            s1[2 * h + 1] += (double)hi;
+        }
     } else {
         float f2[R], f1[R];
 #pragma unroll
