@@ -495,6 +495,101 @@ __device__ __forceinline__ void tile_f32_packed(const float* __restrict__ tp, in
     }
 }
 
+__device__ __forceinline__ f32x2_t fsub2(f32x2_t a, f32x2_t b) {
+    f32x2_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2_t fmul2(f32x2_t a, f32x2_t b) {
+    f32x2_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
+// CDF mode of the packed f32 tile (see tile_f64 for the formula): everything per row is elementwise, so the exponent,
+// the tail polynomial and the products pack two rows per instruction; only the three MUFU calls (2 ex2, 1 rcp) and the
+// sign select are per lane.  Here yt - p is needed with its sign, so the training coordinate is subtracted (FADD2 with a
+// negated broadcast operand).
+template <int D, bool CKDE, int R>
+__device__ __forceinline__ void tile_f32_packed_cdf(const float* __restrict__ tp, int cnt, const float (&yt)[R][D],
+                                                    double (&sum_j)[R], double (&sum_m)[R], float inv_c) {
+    static_assert(R % 2 == 0, "packed f32 tile needs an even number of rows per thread");
+    constexpr int H = R / 2;
+    constexpr float c[kQDeg32 + 1] = PBN_Q32_COEFFS;
+    f32x2_t y2[H][D], facc_j[H], facc_m[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) y2[h][k] = pack_f32x2(yt[2 * h][k], yt[2 * h + 1][k]);
+        facc_j[h] = 0ull;
+        facc_m[h] = 0ull;
+    }
+    const f32x2_t one2 = pack_f32x2(1.f, 1.f);
+    const f32x2_t invc2 = pack_f32x2(inv_c, inv_c);
+    const f32x2_t qinv2 = pack_f32x2(static_cast<float>(kQInvC), static_cast<float>(kQInvC));
+    const f32x2_t qs2 = pack_f32x2(static_cast<float>(kQScale), static_cast<float>(kQScale));
+    const f32x2_t qh2 = pack_f32x2(static_cast<float>(kQShift), static_cast<float>(kQShift));
+#pragma unroll 2
+    for (int i = 0; i < cnt; ++i) {
+        f32x2_t p2[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            float v = tp[i * D + k];
+            p2[k] = pack_f32x2(v, v);
+        }
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            f32x2_t s2 = 0ull, w2 = one2, dl2 = 0ull;
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                f32x2_t d2 = fsub2(y2[h][k], p2[k]);
+                if (k == D - 1) dl2 = d2;
+                if (CKDE && k == D - 1) {  // marginal weight from the first D - 1 coordinates
+                    float lo, hi;
+                    unpack_f32x2(s2, lo, hi);
+                    w2 = pack_f32x2(ex2_neg(lo), ex2_neg(hi));
+                    facc_m[h] = fadd2(facc_m[h], w2);
+                }
+                s2 = ffma2(d2, d2, s2);
+            }
+            float slo, shi, dlo, dhi;
+            unpack_f32x2(s2, slo, shi);
+            unpack_f32x2(dl2, dlo, dhi);
+            const f32x2_t e2 = pack_f32x2(ex2_neg(slo), ex2_neg(shi));  // joint kernel value
+            // t = 1 / (1 + |z| / 4),  u = t * scale + shift,  g(u) by Horner,  q = e t g
+            const f32x2_t a2 = fmul2(pack_f32x2(fabsf(dlo), fabsf(dhi)), invc2);
+            float nlo, nhi;
+            unpack_f32x2(ffma2(a2, qinv2, one2), nlo, nhi);
+            float tlo, thi;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(tlo) : "f"(nlo));
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(thi) : "f"(nhi));
+            const f32x2_t t2 = pack_f32x2(tlo, thi);
+            const f32x2_t u2 = ffma2(t2, qs2, qh2);
+            f32x2_t g2 = pack_f32x2(c[kQDeg32], c[kQDeg32]);
+#pragma unroll
+            for (int k = kQDeg32 - 1; k >= 0; --k) g2 = ffma2(g2, u2, pack_f32x2(c[k], c[k]));
+            const f32x2_t q2 = fmul2(e2, fmul2(t2, g2));
+            const f32x2_t r2 = fsub2(w2, q2);
+            float qlo, qhi, rlo, rhi;
+            unpack_f32x2(q2, qlo, qhi);
+            unpack_f32x2(r2, rlo, rhi);
+            facc_j[h] = fadd2(facc_j[h], pack_f32x2(dlo < 0.f ? qlo : rlo, dhi < 0.f ? qhi : rhi));
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+        float lo, hi;
+        unpack_f32x2(facc_j[h], lo, hi);
+        sum_j[2 * h] += static_cast<double>(lo);
+        sum_j[2 * h + 1] += static_cast<double>(hi);
+        if (CKDE) {
+            unpack_f32x2(facc_m[h], lo, hi);
+            sum_m[2 * h] += static_cast<double>(lo);
+            sum_m[2 * h + 1] += static_cast<double>(hi);
+        }
+    }
+}
+
 // CDF = false: KDE / CKDE log-likelihood sums.  CDF = true: CKDE::cdf sums (see tile_f64); `inv_c` converts a whitened
 // (kernel-unit) coordinate difference into standard-normal units and is only read in that mode.
 template <typename T, int D, bool CKDE, bool CDF = false>
@@ -647,6 +742,8 @@ pair_kernel(const PairJob* __restrict__ jobs, int n_jobs, long long total_units,
         } else {
             if constexpr (PBN_F32_PACKED && !CDF && R % 2 == 0 && D >= PBN_F32_PACKED_MIN_D)
                 tile_f32_packed<D, CKDE, R>(tp, cnt, yt, sum_j, sum_m);
+            else if constexpr (PBN_F32_PACKED && CDF && R % 2 == 0)
+                tile_f32_packed_cdf<D, CKDE, R>(tp, cnt, yt, sum_j, sum_m, static_cast<float>(inv_c));
             else
                 tile_f32<D, CKDE, R, CDF>(tp, cnt, yt, sum_j, sum_m, static_cast<float>(inv_c));
         }
