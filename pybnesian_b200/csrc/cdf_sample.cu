@@ -65,7 +65,7 @@ struct TilePipe {
     const T* src;
     long long n;
     int d;
-    int t_next, t_end;  // producer state (thread 0)
+    int t_next;  // producer state (thread 0)
     uint32_t issued, consumed;
     __device__ __forceinline__ void issue() {
         int stage = issued % kWStages;
@@ -122,7 +122,6 @@ __global__ void __launch_bounds__(kWThreads) weight_kernel(const __grid_constant
     pipe.n = P.n;
     pipe.d = D;
     pipe.t_next = t0;
-    pipe.t_end = t1;
     pipe.issued = 0;
     pipe.consumed = 0;
     if (tid == 0)

@@ -9,13 +9,10 @@ template <int D, bool CKDE, bool CDF = false>
 static cudaError_t launch_one(const PairJob* jobs, int n_jobs, long long total_units, long long upb, int grid,
                               const double* tab, cudaStream_t stream, double inv_c = 0.0) {
     constexpr size_t smem = kStages * (pair_tile<PBN_T>(D) * D * sizeof(PBN_T) + pair_nrm_bytes<PBN_T>(D)) + 64 + exp_tab_smem_bytes<PBN_T>();
-    static bool configured = false;  // per instantiation; attribute is per device function
     auto kern = pair_kernel<PBN_T, D, CKDE, CDF>;
-    if (!configured || true) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    // set on every launch: the attribute is per device (and per context), and the call is a host-side table update
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
     kern<<<grid, kThreads, smem, stream>>>(jobs, n_jobs, total_units, upb, tab, inv_c);
     return cudaGetLastError();
 }

@@ -27,7 +27,6 @@ for dt in (("float64",) if QUICK else ("float64", "float32")):
         out[key] = {"s": t, "pairs_per_s": N * M / t, "mean_cdf": float(np.nanmean(c))}
         print(key, "%.4f s  %.3e pairs/s  mean %.6f" % (t, N * M / t, np.nanmean(c)), flush=True)
         if evidence:
-            ev = test.loc(evidence) if hasattr(test, "loc") else None
             evp = util_data.generate_normal_data(M, 1).astype(dt)[evidence]
             cpd.sample(M, evp, 0)
             ts = []
