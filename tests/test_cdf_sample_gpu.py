@@ -254,3 +254,29 @@ def test_bayesian_network_sample(pbn):
     assert abs(s["b"].mean() - (2.5 + 1.65 * 3)) < 0.3
     with pytest.raises(ValueError):
         model.sample(-1, 0)
+
+
+@pytest.mark.parametrize("dt", ["float64", "float32"])
+@pytest.mark.parametrize("d", [5, 6, 8])
+def test_cdf_and_sample_medium_families(pbn, dt, d):
+    """5-8 variables: the CDF mode of the pair kernel on top of the dot-product exponent form (float64, >= 4 evidence
+    columns), the packed float32 tile, and the sampler's weight kernels at the same widths."""
+    df = util_data.iid_normal(3000, d, seed=0).astype(dt)
+    test = util_data.iid_normal(300, d, seed=1).astype(dt)
+    names = list(df.columns)
+    df["x0"] = (df["x0"] + 0.6 * df["x1"] - 0.4 * df[names[-1]]).astype(dt)
+    test["x0"] = (test["x0"] + 0.6 * test["x1"] - 0.4 * test[names[-1]]).astype(dt)
+    cpd = pbn.CKDE("x0", names[1:])
+    cpd.fit(df)
+    X, T = df[names].to_numpy(), test[names].to_numpy()
+    H = oracle.bandwidth(X)
+    tol = TOL[dt]
+    assert np.allclose(cpd.cdf(test), oracle.ckde_cdf(X, T, H), rtol=tol, atol=tol)
+    want_l, _ = oracle.ckde_logl(X, T, H)
+    assert np.allclose(cpd.logl(test), want_l, rtol=tol, atol=tol)
+    arr, idx = cpd.sample(300, test[names[1:]], 4, _return_indices=True)
+    want, want_idx = oracle.ckde_sample(X, H, T[:, 1:], 300, 4)
+    mismatch = int(np.sum(idx != want_idx))
+    assert mismatch == 0 if dt == "float64" else mismatch <= 12
+    same = idx == want_idx
+    assert np.allclose(arr.to_numpy()[same], want[same], rtol=1e-12 if dt == "float64" else 1e-5, atol=1e-10 if dt == "float64" else 1e-4)
