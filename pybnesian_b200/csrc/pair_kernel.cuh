@@ -119,15 +119,16 @@ static_assert(kExpRep == 1 || kExpRep == 2 || kExpRep == 4 || kExpRep == 8 || kE
 static_assert(kExpDeg >= 2 && kExpDeg <= 4, "PBN_EXP_DEG");
 // train points per shared-memory tile: halved for wide f64 rows so that two CTAs (tiles + table) still
 // fit the 227 KB of an SM
+template <typename T> __host__ __device__ constexpr size_t exp_tab_smem_bytes() {
+    return sizeof(T) == 8 ? static_cast<size_t>(kExpTab) * kExpRep * sizeof(double) : 0;
+}
 template <typename T> __host__ __device__ constexpr int pair_tile(int D) {
-    return (sizeof(T) == 8 && D >= 7) ? PairCfg<T>::TILE / 2 : PairCfg<T>::TILE;
+    return (sizeof(T) == 8 && (D >= 7 || (D >= 5 && exp_tab_smem_bytes<T>() > 32 * 1024))) ? PairCfg<T>::TILE / 2
+                                                                                            : PairCfg<T>::TILE;
 }
 // per-stage bytes of the training-row norm tile (dot-product form, f64 only)
 template <typename T> __host__ __device__ constexpr uint32_t pair_nrm_bytes(int D) {
     return sizeof(T) == 8 ? static_cast<uint32_t>(pair_tile<T>(D) * sizeof(double)) : 0u;
-}
-template <typename T> __host__ __device__ constexpr size_t exp_tab_smem_bytes() {
-    return sizeof(T) == 8 ? static_cast<size_t>(kExpTab) * kExpRep * sizeof(double) : 0;
 }
 // P(g) ~ exp(a g), a = ln2/K, |g| <= 1/2: Taylor polynomial of degree kExpDeg + 1 with its leading term
 // replaced by its Chebyshev economisation on [-h, h], h = a/2 (error = next Taylor term / 2^deg):
@@ -214,11 +215,14 @@ constexpr double kDotTol = PBN_DOT_TOL;  // worst-case per-term cancellation err
 constexpr int kNMin = -1022 * kExpTab;
 // hi word of the double -(1022 * K): sign | (1023 + 9 + log2 K) << 20 | top mantissa bits of 1022/1024
 constexpr unsigned kHiLim = 0x80000000u | (static_cast<unsigned>(1023 + 9 + kExpTabBits) << 20) | 0xFF000u;
+// `nshift` evaluates 2^((t + nshift)/K) instead: the shift is added to the rounded exponent (tile_f64_dot keeps the
+// integer part of -|yt|^2 there); unsigned arithmetic, so only the shifted n has to fit 32 bits.
 template <bool SAFE>
-__device__ __forceinline__ double exp2_tab(double t, const double* __restrict__ tab, double& scaled) {
+__device__ __forceinline__ double exp2_tab(double t, const double* __restrict__ tab, double& scaled,
+                                           const int nshift = 0) {
     const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
     double tm = t + MAGIC;
-    int n = __double2loint(tm);
+    int n = static_cast<int>(static_cast<unsigned>(__double2loint(tm)) + static_cast<unsigned>(nshift));
     double nd = tm - MAGIC;
     double g = t - nd;
     double p;
@@ -316,9 +320,21 @@ __device__ __forceinline__ void tile_f64(const double* __restrict__ tp, int cnt,
 // |whitened coordinate|); the caller only takes this path when that WORST-CASE bound (both points at the edge of the
 // bounding box) is below kDotTol = 1e-11 relative per term - typical pairs are orders of magnitude better and the errors
 // have random sign, so sums stay far inside the 1e-10 target (tests/test_fullsize_gpu.py checks 1e-10 on 1M x 1M).
+//
+// PBN_F64_HOIST: the per-pair DADD `at + nb` is removed as well.  at = A + f with A = rint(at): the integer A is added to
+// the ROUNDED exponent on the integer side (one IADD on the ALU pipe: n = rint(acc) + A, the fraction g is unchanged),
+// and the fraction f is a per-test-row FACTOR 2^(f/K) of every term of the row, applied once to the finished sums
+// (pair_kernel's flush).  The exponent chain then starts from the training norm (the first DFMA takes nb as its
+// addend): DN DFMA per pair instead of 1 DADD + DN DFMA.  Measured on B200 (N = m = 300k, profiles/r1h_tuning.md): KDE
+// d=4 1.085e12 -> 1.141e12 pairs/s, d=8 8.29e11 -> 8.41e11.  Carrying A on the rounding constant instead (kExpMagic + A
+// in a register, no IADD) was 3% SLOWER than not hoisting at all: the two DADDs of the exp2 then read a register pair
+// where they had an immediate, and this kernel is sensitive to register-operand traffic, not to the FP64 count alone.
+#ifndef PBN_F64_HOIST
+#define PBN_F64_HOIST 1
+#endif
 template <int D, bool CKDE, int R, bool CDF>
 __device__ __forceinline__ void tile_f64_dot(const double* __restrict__ tp, const double* __restrict__ nb, int cnt,
-                                             const double (&yt)[R][D], const double (&at)[R],
+                                             const double (&yt)[R][D], const double (&at)[R], const int (&ati)[R],
                                              const double* __restrict__ tab, double (&sum_j)[R], double (&sum_m)[R],
                                              double inv_c) {
     constexpr int DN = CKDE ? D - 1 : D;
@@ -330,13 +346,19 @@ __device__ __forceinline__ void tile_f64_dot(const double* __restrict__ tp, cons
         const double b = nb[i];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
+#if PBN_F64_HOIST
+            const int ns = ati[r];  // rint(-|yt|^2)
+            double acc = b;
+#else
+            const int ns = 0;
             double acc = at[r] + b;
+#endif
             double w = 1.0, dl_last = 0.0;
 #pragma unroll
             for (int c = 0; c < DN; ++c) acc = fma(yt[r][c], p[c], acc);
             if (CKDE) {
                 double st;
-                double pm = exp2_tab<false>(acc, tab, st);
+                double pm = exp2_tab<false>(acc, tab, st, ns);
                 if (CDF) {
                     w = st * pm;
                     sum_m[r] += w;
@@ -348,7 +370,7 @@ __device__ __forceinline__ void tile_f64_dot(const double* __restrict__ tp, cons
                 acc = fma(-dl, dl, acc);
             }
             double st;
-            double pj = exp2_tab<false>(acc, tab, st);
+            double pj = exp2_tab<false>(acc, tab, st, ns);
             if (CDF && CKDE) {
                 double q = (st * pj) * normal_tail_tg(fabs(dl_last) * inv_c);
                 sum_j[r] += (dl_last < 0.0) ? q : (w - q);
@@ -658,6 +680,8 @@ pair_kernel(const PairJob* __restrict__ jobs, int n_jobs, long long total_units,
     int cj = jlo;
     T yt[R][D];
     double at[R];
+    int ati[R];
+    double row_scale[R];
     double sum_j[R], sum_m[R];
     long long cur_tt = -1;
     int cur_job = -1;
@@ -672,6 +696,12 @@ pair_kernel(const PairJob* __restrict__ jobs, int n_jobs, long long total_units,
         for (int r = 0; r < R; ++r) {
             long long row = cur_tt * TB + r * kThreads + tid;
             if (row < jb.m) {
+#if PBN_F64_HOIST
+                if (DOT && dot) {  // the fraction of -|yt|^2 that tile_f64_dot left out: one factor per test row
+                    sum_j[r] *= row_scale[r];
+                    if (CKDE) sum_m[r] *= row_scale[r];
+                }
+#endif
                 jb.part[static_cast<long long>(slot) * jb.m_pad + row] = sum_j[r];
                 if (CKDE) jb.part[(static_cast<long long>(jb.slots) + slot) * jb.m_pad + row] = sum_m[r];
             }
@@ -719,6 +749,11 @@ pair_kernel(const PairJob* __restrict__ jobs, int n_jobs, long long total_units,
                         for (int r = 0; r < R; ++r) {
                             long long row = tt * TB + r * kThreads + tid;
                             at[r] = row < jb.m ? tn[row] : 0.0;
+#if PBN_F64_HOIST
+                            const double ai = rint(at[r]);  // |at| < 2^31 (the `safe` test above)
+                            row_scale[r] = exp((at[r] - ai) * kExpA);
+                            ati[r] = static_cast<int>(ai);
+#endif
 #pragma unroll
                             for (int c = 0; c < DN; ++c) yt[r][c] *= T(2);
                         }
@@ -734,7 +769,7 @@ pair_kernel(const PairJob* __restrict__ jobs, int n_jobs, long long total_units,
 
         if constexpr (sizeof(T) == 8) {
             if (DOT && dot)
-                tile_f64_dot<D, CKDE, R, CDF>(tp, nrm_buf + static_cast<size_t>(stage) * TILE, cnt, yt, at, tab, sum_j, sum_m, inv_c);
+                tile_f64_dot<D, CKDE, R, CDF>(tp, nrm_buf + static_cast<size_t>(stage) * TILE, cnt, yt, at, ati, tab, sum_j, sum_m, inv_c);
             else if (safe)
                 tile_f64<D, CKDE, true, R, CDF>(tp, cnt, yt, tab, sum_j, sum_m, inv_c);
             else

@@ -9,6 +9,7 @@ template <int D, bool CKDE, bool CDF = false>
 static cudaError_t launch_one(const PairJob* jobs, int n_jobs, long long total_units, long long upb, int grid,
                               const double* tab, cudaStream_t stream, double inv_c = 0.0) {
     constexpr size_t smem = kStages * (pair_tile<PBN_T>(D) * D * sizeof(PBN_T) + pair_nrm_bytes<PBN_T>(D)) + 64 + exp_tab_smem_bytes<PBN_T>();
+    static_assert(smem <= 113 * 1024 || PairCfg<PBN_T>::MIN_CTAS < 2, "two CTAs per SM must fit in shared memory");
     auto kern = pair_kernel<PBN_T, D, CKDE, CDF>;
     // set on every launch: the attribute is per device (and per context), and the call is a host-side table update
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
