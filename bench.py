@@ -294,8 +294,8 @@ def main():
     # (joint d=4, marginal d=3) => mean (26 + 24)/2 = 25 per pair-eval.
     i_survey = (2 * 4 + 18 + 2 * 3 + 18) / 2.0
     # This kernel's own count per pair-eval: fused pass shares the d differences/FMAs, table exp2
-    # costs 3 DADD + 3 DFMA + 1 DFMA(accumulate): (2*4 + 2*7)/2 = 11.
-    i_own = (2 * 4 + 2 * 7) / 2.0
+    # costs 3 DADD + 2 DFMA (degree-2 polynomial, K = 4096) + 1 DFMA(accumulate): (2*4 + 2*6)/2 = 10.
+    i_own = (2 * 4 + 2 * 6) / 2.0
     achieved = kern_pairs / (kern_ms * 1e-3) if kern_ms > 0 else None
     peak = sms * lanes * f_hz / i_survey
     # DRAM bytes of one launch of this exact configuration, from a committed ncu capture

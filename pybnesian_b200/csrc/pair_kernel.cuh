@@ -9,10 +9,10 @@
 //
 // Inputs are *whitened* rows (see whiten_kernel in runtime.cu):  y = c * L^-1 (x - mu)
 // with c chosen so that the exponent is already in table / log2 units:
-//   f64:  t = -sum_c (yt_c - yi_c)^2  ==  K * log2(e) * (-1/2 s)   (s = Mahalanobis^2, K = 2048)
+//   f64:  t = -sum_c (yt_c - yi_c)^2  ==  K * log2(e) * (-1/2 s)   (s = Mahalanobis^2, K = 4096)
 //         exp(-s/2) = 2^(t/K) = 2^k * T[j] * P(g),  n = rint(t), k = n>>11, j = n&2047,
-//         g = t - n in [-1/2, 1/2], P a degree-3 polynomial (max rel. err 3.4e-16).
-//         Cost: 3 DADD + 3 DFMA + 1 DFMA (accumulate) on the FP64 pipe.
+//         g = t - n in [-1/2, 1/2], P a degree-2 polynomial (max rel. err 2.5e-14 per term, four orders inside
+//         the 1e-10 parity bar).  Cost: 3 DADD + 2 DFMA + 1 DFMA (accumulate) on the FP64 pipe.
 //   f32:  t = -sum_c (..)^2 == log2(e) * (-1/2 s);  exp(-s/2) = ex2.approx(t) (1 MUFU).
 // Sums are accumulated unshifted (every term <= 1); rows whose sum is too small for
 // that to be accurate are re-run with a per-row shift by the caller (runtime.cu).
@@ -81,16 +81,18 @@ template <typename T> struct PairCfg;
 #ifndef PBN_F64_DOT
 #define PBN_F64_DOT 1
 #endif
-// the dot-product form is used from this many norm coordinates on (measured on B200, N = m = 300k, R = 3:
-// KDE d=4 +7%, d=8 +18%; no gain for DN <= 3, where the extra norm loads cost what the saved DFMAs buy)
+// the dot-product form is used from this many norm coordinates on.  Round 1f measured no gain below DN = 4 (the extra
+// norm loads cost what the saved DFMAs bought while the shared-memory pipe was saturated by table-gather conflicts);
+// with the exponent floor (pair_floor) taking those conflicts away the FP64 count decides again: B200, N = m = 300k,
+// CKDE d=4 (DN = 3) 1.437e12 -> 1.516e12 pair-evals/s, KDE d=2 1.365e12 -> 1.489e12 (profiles/r1h_tuning.md).
 #ifndef PBN_F64_DOT_MIN_DN
-#define PBN_F64_DOT_MIN_DN 4
+#define PBN_F64_DOT_MIN_DN 2
 #endif
 #ifndef PBN_EXP_BITS
-#define PBN_EXP_BITS 11
+#define PBN_EXP_BITS 12
 #endif
 #ifndef PBN_EXP_DEG
-#define PBN_EXP_DEG 3
+#define PBN_EXP_DEG 2
 #endif
 #ifndef PBN_EXP_REP
 #define PBN_EXP_REP 1
@@ -110,7 +112,8 @@ template <> struct PairCfg<float>  { static constexpr int R = PBN_F32_R; static 
 // measured for one shared copy), but on B200 it bought nothing: the single-copy kernel reports the
 // shared-memory pipe 98.5% busy (profiles/r1b_ncu_pair_f64_ckde_d4.txt) yet runs at the same speed as
 // the conflict-free variant (profiles/r1c_tuning.md) - the replays hide behind the FP64 pipe, and the
-// extra address arithmetic costs issue slots the DFMA stream needs.  Default: one copy, K = 2048.
+// extra address arithmetic costs issue slots the DFMA stream needs (re-measured in round 1h with the current kernel:
+// K = 512 x 16 copies -5%, profiles/r1h_tuning.md).  Default: one copy, K = 4096 (32 KB), degree 2.
 constexpr int kExpTabBits = PBN_EXP_BITS;
 constexpr int kExpTab = 1 << kExpTabBits;
 constexpr int kExpRep = PBN_EXP_REP;
@@ -133,7 +136,8 @@ template <typename T> __host__ __device__ constexpr uint32_t pair_nrm_bytes(int 
 // P(g) ~ exp(a g), a = ln2/K, |g| <= 1/2: Taylor polynomial of degree kExpDeg + 1 with its leading term
 // replaced by its Chebyshev economisation on [-h, h], h = a/2 (error = next Taylor term / 2^deg):
 //   K =  512, degree 3: 1.1e-15      K = 2048, degree 3: 4.3e-18      K = 256, degree 4 (plain Taylor): 3.8e-17
-//   K = 2048, degree 2: 2.0e-13      K = 1024, degree 2: 1.6e-12      (experimental, PBN_EXP_DEG=2)
+//   K = 2048, degree 2: 2.0e-13      K = 4096, degree 2: 2.5e-14 (default)      K = 8192, degree 2: 3.1e-15
+// Degree 2 saves one DFMA per exp2: +1.5% (CKDE d=4) .. +3% (KDE d=2) over K = 2048 / degree 3 on B200.
 constexpr double kExpA = 0.693147180559945309417232121458 / kExpTab;
 constexpr double kExpH2 = 0.25 * kExpA * kExpA;  // h^2
 constexpr double kExpC0 = kExpDeg == 3 ? 1.0 - kExpH2 * kExpH2 / 192.0 : 1.0;
@@ -217,9 +221,11 @@ constexpr int kNMin = -1022 * kExpTab;
 constexpr unsigned kHiLim = 0x80000000u | (static_cast<unsigned>(1023 + 9 + kExpTabBits) << 20) | 0xFF000u;
 // `nshift` evaluates 2^((t + nshift)/K) instead: the shift is added to the rounded exponent (tile_f64_dot keeps the
 // integer part of -|yt|^2 there); unsigned arithmetic, so only the shifted n has to fit 32 bits.
+// `nmin` (a multiple of K, >= kNMin) is the floor of the rounded exponent: terms below 2^(nmin/K) are evaluated AS
+// 2^(nmin/K) and all read table entry 0 (see pair_floor).
 template <bool SAFE>
 __device__ __forceinline__ double exp2_tab(double t, const double* __restrict__ tab, double& scaled,
-                                           const int nshift = 0) {
+                                           const int nshift = 0, const int nmin = kNMin) {
     const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
     double tm = t + MAGIC;
     int n = static_cast<int>(static_cast<unsigned>(__double2loint(tm)) + static_cast<unsigned>(nshift));
@@ -242,8 +248,9 @@ __device__ __forceinline__ double exp2_tab(double t, const double* __restrict__ 
         // kHiLim is the hi word of -(1022 * K)
         unsigned hi = static_cast<unsigned>(__double2hiint(t));
         n = (hi > kHiLim) ? kNMin : n;
+        n = max(n, nmin);
     } else {
-        n = max(n, kNMin);
+        n = max(n, nmin);
     }
 #if PBN_EXP_INT == 1
     // integer glue on the ALU pipe (SHF / LOP3 / IADD3) instead of the FMA pipe (IMAD.SHL / IMAD): the FP64 stream
@@ -261,6 +268,26 @@ __device__ __forceinline__ double exp2_tab(double t, const double* __restrict__ 
     return p;
 }
 
+// Floor of the rounded exponent for the terms still to be added to a running (unshifted, non-negative) sum:
+//   floor = K * (exponent(sum) - kFloorBits), never below kNMin, kNMin while the sum is still zero / subnormal.
+// A term below 2^(floor/K) is below 2^-kFloorBits of the sum it is added to; evaluating it as 2^(floor/K) changes the
+// finished sum by less than N 2^-kFloorBits relative (N = 2^24 training rows: 1.4e-17), far below the rounding of the
+// sum itself.  Why bother: the floor is a multiple of K, so every such lane reads table entry 0 - ONE shared-memory
+// address per warp instead of a random one.  The table gather is what saturates the shared-memory pipe (ncu r1h: LSU
+// wavefronts 99% of peak, 6.1 wavefronts per 8-byte gather against 2 without bank conflicts, FP64 pipe waiting at 73%),
+// and for a KDE with a rule-of-thumb bandwidth most (test, train) pairs are that far apart, so the conflicts go with them.
+// Costs nothing per pair (the clamp instruction was there already, with the constant kNMin).
+#ifndef PBN_F64_FLOOR_BITS
+#define PBN_F64_FLOOR_BITS 80
+#endif
+constexpr int kFloorBits = PBN_F64_FLOOR_BITS;  // 0 disables
+__device__ __forceinline__ int pair_floor(double sum) {
+    if (kFloorBits == 0) return kNMin;
+    const int e = __double2hiint(sum) >> 20;  // sum >= 0 (or NaN, whose terms no longer matter)
+    const int f = (e - 1023 - kFloorBits) * kExpTab;
+    return (e <= 0 || e >= 2047) ? kNMin : max(f, kNMin);
+}
+
 // Fills the interleaved shared-memory copies of the table from the K-entry global table.
 __device__ __forceinline__ void exp_tab_fill(double* __restrict__ tab_s, const double* __restrict__ tab_g, int tid,
                                              int nthreads) {
@@ -276,6 +303,13 @@ template <int D, bool CKDE, bool SAFE, int R, bool CDF>
 __device__ __forceinline__ void tile_f64(const double* __restrict__ tp, int cnt, const double (&yt)[R][D],
                                          const double* __restrict__ tab, double (&sum_j)[R], double (&sum_m)[R],
                                          double inv_c) {
+    // exponent floors of this tile from the sums so far (log-likelihood sums only: a cdf sum may be far below its weights)
+    int fl_j[R], fl_m[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        fl_j[r] = CDF ? kNMin : pair_floor(sum_j[r]);
+        fl_m[r] = (CDF || !CKDE) ? kNMin : pair_floor(sum_m[r]);
+    }
 #pragma unroll kF64Unroll
     for (int i = 0; i < cnt; ++i) {
         double p[D];
@@ -292,7 +326,7 @@ __device__ __forceinline__ void tile_f64(const double* __restrict__ tp, int cnt,
                 if (CDF && c == D - 1) dl_last = dl;
                 if (CKDE && c == D - 2) {
                     double st;
-                    double pm = exp2_tab<SAFE>(acc, tab, st);
+                    double pm = exp2_tab<SAFE>(acc, tab, st, 0, fl_m[r]);
                     if (CDF) {
                         w = st * pm;
                         sum_m[r] += w;
@@ -302,7 +336,7 @@ __device__ __forceinline__ void tile_f64(const double* __restrict__ tp, int cnt,
                 }
             }
             double st;
-            double pj = exp2_tab<SAFE>(acc, tab, st);
+            double pj = exp2_tab<SAFE>(acc, tab, st, 0, fl_j[r]);
             if (CDF) {
                 double q = (st * pj) * normal_tail_tg(fabs(dl_last) * inv_c);
                 sum_j[r] += (dl_last < 0.0) ? q : (w - q);
@@ -338,6 +372,12 @@ __device__ __forceinline__ void tile_f64_dot(const double* __restrict__ tp, cons
                                              const double* __restrict__ tab, double (&sum_j)[R], double (&sum_m)[R],
                                              double inv_c) {
     constexpr int DN = CKDE ? D - 1 : D;
+    int fl_j[R], fl_m[R];  // see tile_f64
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        fl_j[r] = CDF ? kNMin : pair_floor(sum_j[r]);
+        fl_m[r] = (CDF || !CKDE) ? kNMin : pair_floor(sum_m[r]);
+    }
 #pragma unroll kF64Unroll
     for (int i = 0; i < cnt; ++i) {
         double p[D];
@@ -358,7 +398,7 @@ __device__ __forceinline__ void tile_f64_dot(const double* __restrict__ tp, cons
             for (int c = 0; c < DN; ++c) acc = fma(yt[r][c], p[c], acc);
             if (CKDE) {
                 double st;
-                double pm = exp2_tab<false>(acc, tab, st, ns);
+                double pm = exp2_tab<false>(acc, tab, st, ns, fl_m[r]);
                 if (CDF) {
                     w = st * pm;
                     sum_m[r] += w;
@@ -370,7 +410,7 @@ __device__ __forceinline__ void tile_f64_dot(const double* __restrict__ tp, cons
                 acc = fma(-dl, dl, acc);
             }
             double st;
-            double pj = exp2_tab<false>(acc, tab, st, ns);
+            double pj = exp2_tab<false>(acc, tab, st, ns, fl_j[r]);
             if (CDF && CKDE) {
                 double q = (st * pj) * normal_tail_tg(fabs(dl_last) * inv_c);
                 sum_j[r] += (dl_last < 0.0) ? q : (w - q);
