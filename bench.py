@@ -293,9 +293,10 @@ def main():
     # FP64-pipe instructions per pair-eval I(d) = 2d + 18; CKDE run as two passes
     # (joint d=4, marginal d=3) => mean (26 + 24)/2 = 25 per pair-eval.
     i_survey = (2 * 4 + 18 + 2 * 3 + 18) / 2.0
-    # This kernel's own count per pair-eval: fused pass shares the d differences/FMAs, table exp2
-    # costs 3 DADD + 2 DFMA (degree-2 polynomial, K = 4096) + 1 DFMA(accumulate): (2*4 + 2*6)/2 = 10.
-    i_own = (2 * 4 + 2 * 6) / 2.0
+    # This kernel's own count per (train, test) row pair, which is 2 pair-evals: marginal exponent in dot-product form
+    # with the test-row norm hoisted (3 DFMA), table exp2 (3 DADD + 2 DFMA, degree-2 polynomial on K = 4096) + 1 DFMA to
+    # accumulate, last coordinate in difference form (1 DADD + 1 DFMA), second exp2 + accumulate: 3 + 6 + 2 + 6 = 17.
+    i_own = 17 / 2.0
     achieved = kern_pairs / (kern_ms * 1e-3) if kern_ms > 0 else None
     peak = sms * lanes * f_hz / i_survey
     # DRAM bytes of one launch of this exact configuration, from a committed ncu capture

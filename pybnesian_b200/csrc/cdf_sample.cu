@@ -636,7 +636,7 @@ int pbn_ckde_cdf(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const in
     if (fast) {
         // CDF mode of the fused pair kernel: same stream-K schedule and partial-sum slots as pbn_logl_impl
         const int TILE = f64 ? pbn::pair_tile_f64(d) : pbn::pair_tile_f32(d);
-        const int TB = f64 ? pbn::pair_tb_f64() : pbn::pair_tb_f32();
+        const int TB = f64 ? pbn::pair_tb_f64() : pbn::pair_tb_f32();  // CDF mode: PairCfg rows for every shape
         int n_test_tiles = (int)((m + TB - 1) / TB);
         int n_train_tiles = (int)((k->n + TILE - 1) / TILE);
         long long U = (long long)n_test_tiles * n_train_tiles;

@@ -606,7 +606,7 @@ int score_ckde_group(pbn_ctx* ctx, pbn_cv* cv, const pbn_cv_item* items, const s
     const size_t es = elem_size(tbl->dtype);
     const bool ckde = d >= 2;
     const int TILE = f64 ? pbn::pair_tile_f64(d) : pbn::pair_tile_f32(d);
-    const int TB = f64 ? pbn::pair_tb_f64() : pbn::pair_tb_f32();
+    const int TB = f64 ? pbn::pair_tb_for_f64(d, ckde) : pbn::pair_tb_for_f32(d, ckde);
     const int nfold = f1 - f0;
     const double unit = unit_scale(tbl->dtype);
     const double cscale = sqrt(0.5 * unit);

@@ -147,6 +147,9 @@ cudaError_t launch_cdf_f32(int D, const PairJob* jobs, int n_jobs, long long tot
                            const double* tab, double inv_c, cudaStream_t stream);
 int pair_tile_f64(int D);
 int pair_tile_f32(int D);
-int pair_tb_f64();
+int pair_tb_f64();  // UCV kernel and the CDF mode of the pair kernel (rows per thread of PairCfg)
 int pair_tb_f32();
+// test rows per tile of pair_kernel<T, D, CKDE> (the rows per thread depend on the kernel shape, pair_rows)
+int pair_tb_for_f64(int D, bool ckde);
+int pair_tb_for_f32(int D, bool ckde);
 }  // namespace pbn

@@ -84,9 +84,10 @@ template <typename T> struct PairCfg;
 // the dot-product form is used from this many norm coordinates on.  Round 1f measured no gain below DN = 4 (the extra
 // norm loads cost what the saved DFMAs bought while the shared-memory pipe was saturated by table-gather conflicts);
 // with the exponent floor (pair_floor) taking those conflicts away the FP64 count decides again: B200, N = m = 300k,
-// CKDE d=4 (DN = 3) 1.437e12 -> 1.516e12 pair-evals/s, KDE d=2 1.365e12 -> 1.489e12 (profiles/r1h_tuning.md).
+// CKDE d=4 (DN = 3) 1.437e12 -> 1.516e12 pair-evals/s, KDE d=2 1.365e12 -> 1.489e12, KDE d=1 1.615e12 -> 1.685e12
+// (profiles/r1h_tuning.md).
 #ifndef PBN_F64_DOT_MIN_DN
-#define PBN_F64_DOT_MIN_DN 2
+#define PBN_F64_DOT_MIN_DN 1
 #endif
 #ifndef PBN_EXP_BITS
 #define PBN_EXP_BITS 12
@@ -103,8 +104,19 @@ template <typename T> struct PairCfg;
 #ifndef PBN_F64_UNROLL
 #define PBN_F64_UNROLL 4
 #endif
+// test rows per thread and training points per unrolled step, by kernel shape (B200, N = m = 300k, profiles/r1h_tuning.md):
+// f64 KDE (no marginal sum) d <= 4 runs 4-5% faster with 4 rows per thread, the CKDE kernels 3% slower (registers);
+// 8 points per step pay for d <= 2 only (KDE d=2 +5%, CKDE d=4 -3%, KDE d=8 -3%).
+template <typename T> __host__ __device__ constexpr int pair_rows(int D, bool ckde);
 template <> struct PairCfg<double> { static constexpr int R = PBN_F64_R; static constexpr int TILE = PBN_F64_TILE; static constexpr int MIN_CTAS = PBN_F64_MINCTAS; };
 template <> struct PairCfg<float>  { static constexpr int R = PBN_F32_R; static constexpr int TILE = PBN_F32_TILE; static constexpr int MIN_CTAS = PBN_F32_MINCTAS; };
+
+template <typename T> __host__ __device__ constexpr int pair_rows(int D, bool ckde) {
+    return (sizeof(T) == 8 && PBN_F64_R == 3 && !ckde && D <= 4) ? 4 : PairCfg<T>::R;
+}
+__host__ __device__ constexpr int pair_unroll_f64(int D, bool ckde) {
+    return (PBN_F64_UNROLL == 4 && !ckde && D <= 2) ? 8 : PBN_F64_UNROLL;
+}
 
 // exp2 table of the f64 path: T[j] = 2^(j/K), K = 2^PBN_EXP_BITS, held in shared memory in kExpRep
 // interleaved copies (copy r of entry j at index j*kExpRep + r; a thread reads copy lane mod kExpRep).
@@ -303,6 +315,7 @@ template <int D, bool CKDE, bool SAFE, int R, bool CDF>
 __device__ __forceinline__ void tile_f64(const double* __restrict__ tp, int cnt, const double (&yt)[R][D],
                                          const double* __restrict__ tab, double (&sum_j)[R], double (&sum_m)[R],
                                          double inv_c) {
+    constexpr int U = pair_unroll_f64(D, CKDE);
     // exponent floors of this tile from the sums so far (log-likelihood sums only: a cdf sum may be far below its weights)
     int fl_j[R], fl_m[R];
 #pragma unroll
@@ -310,7 +323,7 @@ __device__ __forceinline__ void tile_f64(const double* __restrict__ tp, int cnt,
         fl_j[r] = CDF ? kNMin : pair_floor(sum_j[r]);
         fl_m[r] = (CDF || !CKDE) ? kNMin : pair_floor(sum_m[r]);
     }
-#pragma unroll kF64Unroll
+#pragma unroll U
     for (int i = 0; i < cnt; ++i) {
         double p[D];
 #pragma unroll
@@ -372,13 +385,14 @@ __device__ __forceinline__ void tile_f64_dot(const double* __restrict__ tp, cons
                                              const double* __restrict__ tab, double (&sum_j)[R], double (&sum_m)[R],
                                              double inv_c) {
     constexpr int DN = CKDE ? D - 1 : D;
+    constexpr int U = pair_unroll_f64(D, CKDE);
     int fl_j[R], fl_m[R];  // see tile_f64
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         fl_j[r] = CDF ? kNMin : pair_floor(sum_j[r]);
         fl_m[r] = (CDF || !CKDE) ? kNMin : pair_floor(sum_m[r]);
     }
-#pragma unroll kF64Unroll
+#pragma unroll U
     for (int i = 0; i < cnt; ++i) {
         double p[D];
 #pragma unroll
@@ -658,13 +672,14 @@ template <typename T, int D, bool CKDE, bool CDF = false>
 __global__ void __launch_bounds__(kThreads, PairCfg<T>::MIN_CTAS)
 pair_kernel(const PairJob* __restrict__ jobs, int n_jobs, long long total_units, long long upb,
             const double* __restrict__ exp_tab_g, double inv_c) {
-    constexpr int R = PairCfg<T>::R;
-    constexpr int TILE = pair_tile<T>(D);
+    constexpr int R = CDF ? PairCfg<T>::R : pair_rows<T>(D, CKDE);
     constexpr int TB = kThreads * R;  // test rows per tile
+    constexpr int TILE = pair_tile<T>(D);
     constexpr uint32_t TILE_BYTES = TILE * D * sizeof(T);
     constexpr uint32_t NRM_BYTES = pair_nrm_bytes<T>(D);  // per stage; 0 for f32
     constexpr int DN = CKDE ? D - 1 : D;
-    constexpr bool DOT = PBN_F64_DOT && sizeof(T) == 8 && DN >= PBN_F64_DOT_MIN_DN;
+    // (the evidence-free CDF kernel, D = 1, has no dot-product form: its only coordinate is the conditioned one)
+    constexpr bool DOT = PBN_F64_DOT && sizeof(T) == 8 && DN >= PBN_F64_DOT_MIN_DN && !(CDF && !CKDE);
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T* tile_buf = reinterpret_cast<T*>(smem_raw);  // [kStages][TILE*D]

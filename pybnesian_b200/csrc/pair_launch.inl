@@ -50,5 +50,6 @@ cudaError_t PBN_CDF_LAUNCH_NAME(int D, const PairJob* jobs, int n_jobs, long lon
 
 int PBN_TILE_NAME(int D) { return pair_tile<PBN_T>(D); }
 int PBN_TB_NAME() { return kThreads * PairCfg<PBN_T>::R; }
+int PBN_TB_FOR_NAME(int D, bool ckde) { return kThreads * pair_rows<PBN_T>(D, ckde); }
 
 }  // namespace pbn

@@ -594,7 +594,7 @@ int pbn_logl_impl(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const i
     const bool f64 = k->dtype == PBN_F64;
     const size_t es = elem_size(k->dtype);
     const int TILE = f64 ? pbn::pair_tile_f64(d) : pbn::pair_tile_f32(d);
-    const int TB = f64 ? pbn::pair_tb_f64() : pbn::pair_tb_f32();
+    const int TB = f64 ? pbn::pair_tb_for_f64(d, k->ckde) : pbn::pair_tb_for_f32(d, k->ckde);
     const bool fast = d <= 8;
 
     void* ytest = nullptr;

@@ -192,7 +192,7 @@ int pbn_kde_logl_multi(pbn_ctx* ctx, const pbn_kde* const* kdes, int n_jobs, con
     const bool ckde = first->ckde;
     const size_t es = elem_size(first->dtype);
     const int TILE = f64 ? pbn::pair_tile_f64(d) : pbn::pair_tile_f32(d);
-    const int TB = f64 ? pbn::pair_tb_f64() : pbn::pair_tb_f32();
+    const int TB = f64 ? pbn::pair_tb_for_f64(d, ckde) : pbn::pair_tb_for_f32(d, ckde);
     const double unit = unit_scale(first->dtype);
 
     std::vector<int> live;  // jobs with a fitted KDE and at least one row

@@ -17,6 +17,11 @@ __device__ __forceinline__ void ucv_tile(const T* __restrict__ tp, int cnt, long
                                          const long long (&rowid)[R], const double* __restrict__ tab,
                                          double (&s2)[R], double (&s1)[R]) {
     if constexpr (sizeof(T) == 8) {
+        // exponent floor from this row's running sum of exp(-s/4) (pair_floor in pair_kernel.cuh): a floored term is below
+        // 2^-80 of a partial sum of S2, and its square below 2^-160 N^2 of the largest term of S1
+        int fl[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) fl[r] = pair_floor(s2[r]);
 #pragma unroll 2
         for (int j = 0; j < cnt; ++j) {
             double p[D];
@@ -31,7 +36,7 @@ __device__ __forceinline__ void ucv_tile(const T* __restrict__ tp, int cnt, long
                     acc = fma(-dl, dl, acc);
                 }
                 double st;
-                double pg = exp2_tab<SAFE>(acc, tab, st);
+                double pg = exp2_tab<SAFE>(acc, tab, st, 0, fl[r]);
                 double e2 = st * pg;
                 if (DIAG) e2 = (col0 + j < rowid[r]) ? e2 : 0.0;
                 s2[r] += e2;

@@ -345,3 +345,42 @@ def test_non_finite_test_values_propagate(pbn):
     assert np.isfinite(got[0]) and np.isfinite(got[3])
     for i in (1, 2):
         assert not np.isfinite(got[i]) and not np.isfinite(want[i])
+
+
+@pytest.mark.parametrize("order", ["near_first", "far_first", "shuffled"])
+@pytest.mark.parametrize("evidence", [[], ["a"], ["a", "c", "d"]])
+def test_exponent_floor_is_invisible(pbn, order, evidence):
+    """The f64 kernel clamps the rounded exponent of a term to a floor derived from the row's running sum
+    (pair_kernel.cuh: pair_floor), so that far pairs read one table entry.  Two clusters 25 sigma apart make most terms of
+    every row fall below any such floor; the training order decides whether the floors are built from the near cluster
+    (large sums early), from the far one (sums of ~1e-200 for many tiles, then terms 200 orders larger) or mixed.  The
+    result must not depend on it and must meet the 1e-10 bar against the oracle in every order."""
+    rng = np.random.default_rng(11)
+    n_half = 30_000
+    near = util_data.generate_normal_data(n_half, seed=0)
+    far = util_data.generate_normal_data(n_half, seed=2) + 25.0
+    train = pd.concat([near, far] if order != "far_first" else [far, near], ignore_index=True)
+    if order == "shuffled":
+        train = train.iloc[rng.permutation(len(train))].reset_index(drop=True)
+    # test rows: both clusters, the gap between them, and a few outliers beyond
+    test = pd.concat([util_data.generate_normal_data(600, seed=1), util_data.generate_normal_data(600, seed=3) + 25.0,
+                      util_data.generate_normal_data(200, seed=4) + 12.5, util_data.generate_normal_data(100, seed=5) * 3.0],
+                     ignore_index=True)
+    cols = ["b"] + evidence
+    cpd = pbn.CKDE("b", evidence) if evidence else pbn.KDE(["b"])
+    cpd.fit(train)
+    X, T = train[cols].to_numpy(), test[cols].to_numpy()
+    H = oracle.bandwidth(X)
+    # checker: the long-double evaluation.  For the outlying rows the joint and marginal log-likelihoods are large and
+    # nearly cancel, and the reference arithmetic itself (oracle.ckde_logl) is only good to ~1e-13 of THEIR magnitude
+    # (3e-10 of the difference on this data), so the 1e-10 bar is taken relative to the terms of the difference.
+    joint = oracle.kde_logl_ld(X, T, H)
+    marg = oracle.kde_logl_ld(X[:, 1:], T[:, 1:], H[1:, 1:]) if evidence else np.zeros_like(joint)
+    want = joint - marg
+    scale = np.maximum(np.maximum(np.abs(joint), np.abs(marg)), np.abs(want))
+    got = cpd.logl(test)
+    assert np.all(np.isfinite(want))
+    assert np.max(np.abs(got - want) / scale) < RTOL64
+    assert abs(cpd.slogl(test) - want.sum()) <= RTOL64 * abs(want.sum())
+    ref, _ = (oracle.ckde_logl if evidence else oracle.kde_logl)(X, T, H)
+    assert np.max(np.abs(got - ref) / scale) < RTOL64
