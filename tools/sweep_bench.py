@@ -53,9 +53,9 @@ def main():
                 ctx.set_timing(False)
                 if dt == "float64":
                     peak_survey = sms * 64 * f_hz / (2 * d + 18)
-                    # difference form: d sub + d FMA + 7 (table exp2 + accumulate); dot-product form from d >= 4
-                    # (pair_kernel.cuh: tile_f64_dot): 1 add + d FMA + 7
-                    peak_own = sms * 64 * f_hz / ((d + 8) if d >= 4 else (2 * d + 7))
+                    # dot-product form with the hoisted test-row norm (pair_kernel.cuh: tile_f64_dot): d FMA + 6
+                    # (table exp2 with a degree-2 polynomial: 3 DADD + 2 DFMA, + 1 DFMA to accumulate)
+                    peak_own = sms * 64 * f_hz / (d + 6)
                 else:
                     # FP32 pipe: d sub + d FMA + 1 add lane-ops per pair at 128 lanes/clk/SM; MUFU.EX2 16/clk/SM
                     peak_survey = min(sms * 128 * f_hz / (2 * d + 2), sms * 16 * f_hz)
