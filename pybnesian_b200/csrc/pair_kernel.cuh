@@ -851,6 +851,7 @@ struct UcvJob {
     const long long* prefix;   // prefix[tt] = first unit of row tile tt, prefix[n_row_tiles] = total
     int n_row_tiles;
     const float* bound;        // max |whitened coordinate|
+    const double* nrm;         // f64 only, may be null: -sum_c y_c^2 per row (dot-product form, see ucv_tile_dot)
     double* partial;           // [grid][2]
     long long unit_begin, unit_end;  // slice of units handled by this launch (multi-GPU split)
 };

@@ -22,6 +22,7 @@ struct pbn_ucv {
     double mu[PBN_MAX_DIM];
     void* y;            // whitened rows (re-filled per score call)
     float* d_bound;
+    double* nrm;        // f64, d <= 8 only (else null): -sum_c y_c^2 per row, re-filled with y
     long long* d_prefix;
     int n_row_tiles;
     long long total_units;
@@ -41,7 +42,7 @@ static int ucv_sums(pbn_ucv* s, const double* Lchol /*col-major lower*/, long lo
     double c = sqrt(0.25 * unit_scale(s->dtype));
     for (int i = 0; i < d * d; ++i) W[i] = c * Winv[i];
     PBN_CUDA_TRY(cudaMemsetAsync(s->d_bound, 0, sizeof(float), st));
-    PBN_TRY(whiten_raw_launch(ctx, s->tbl, s->cols, d, s->rows, W.data(), s->mu, s->y, s->d_bound));
+    PBN_TRY(whiten_raw_launch(ctx, s->tbl, s->cols, d, s->rows, W.data(), s->mu, s->y, s->d_bound, s->nrm, d));
     long long ub = s->total_units * part / nparts, ue = s->total_units * (part + 1) / nparts;
     long long U = ue - ub;
     *S2 = 0;
@@ -56,6 +57,7 @@ static int ucv_sums(pbn_ucv* s, const double* Lchol /*col-major lower*/, long lo
     job.prefix = s->d_prefix;
     job.n_row_tiles = s->n_row_tiles;
     job.bound = s->d_bound;
+    job.nrm = s->nrm;
     job.partial = s->d_partial;
     job.unit_begin = ub;
     job.unit_end = ue;
@@ -269,8 +271,9 @@ int pbn_ucv_create(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, p
     size_t es = elem_size(s->dtype);
     size_t ybytes = (((size_t)((n + TILE - 1) / TILE * TILE + 16) * d * es) + 255) / 256 * 256;
     cudaStream_t st = ctx->stream;
-    cudaError_t e = cudaMallocAsync(&s->y, ybytes + 256, st);
-    if (e == cudaSuccess) e = cudaMemsetAsync(s->y, 0, ybytes + 256, st);
+    const size_t nbytes = (f64 && d <= 8) ? (((size_t)((n + TILE - 1) / TILE * TILE + 16) * sizeof(double)) + 255) / 256 * 256 : 0;
+    cudaError_t e = cudaMallocAsync(&s->y, ybytes + 256 + nbytes, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(s->y, 0, ybytes + 256 + nbytes, st);
     if (e == cudaSuccess) e = cudaMallocAsync(&s->d_prefix, prefix.size() * sizeof(long long), st);
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(s->d_prefix, prefix.data(), prefix.size() * sizeof(long long), cudaMemcpyHostToDevice, st);
@@ -284,6 +287,7 @@ int pbn_ucv_create(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, p
         PBN_CUDA_TRY(e);
     }
     s->d_bound = reinterpret_cast<float*>(static_cast<char*>(s->y) + ybytes);
+    s->nrm = nbytes ? reinterpret_cast<double*>(static_cast<char*>(s->y) + ybytes + 256) : nullptr;
     *out = s;
     return PBN_OK;
 }

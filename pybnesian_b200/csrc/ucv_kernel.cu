@@ -118,6 +118,38 @@ __device__ __forceinline__ void ucv_tile(const T* __restrict__ tp, int cnt, long
     }
 }
 
+// Dot-product form of the f64 tile (tile_f64_dot in pair_kernel.cuh): yi2 holds 2 y_i, the training norm nb is the addend
+// of the first DFMA, the integer part of the row's own norm is added to the rounded exponent (ati) and its fraction is a
+// per-row factor applied by the caller (scale on S2, scale^2 on S1).  D DFMA + 8 FP64 instructions per pair instead of 2 D + 8.
+template <int D, bool DIAG, int R>
+__device__ __forceinline__ void ucv_tile_dot(const double* __restrict__ tp, const double* __restrict__ nb, int cnt,
+                                             long long col0, const double (&yi2)[R][D], const int (&ati)[R],
+                                             const long long (&rowid)[R], const double* __restrict__ tab,
+                                             double (&s2)[R], double (&s1)[R]) {
+    int fl[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) fl[r] = pair_floor(s2[r]);
+#pragma unroll 2
+    for (int j = 0; j < cnt; ++j) {
+        double p[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) p[c] = tp[j * D + c];
+        const double b = nb[j];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            double acc = b;
+#pragma unroll
+            for (int c = 0; c < D; ++c) acc = fma(yi2[r][c], p[c], acc);
+            double st;
+            double pg = exp2_tab<false>(acc, tab, st, ati[r], fl[r]);
+            double e2 = st * pg;
+            if (DIAG) e2 = (col0 + j < rowid[r]) ? e2 : 0.0;
+            s2[r] += e2;
+            s1[r] = fma(e2, e2, s1[r]);
+        }
+    }
+}
+
 template <typename T, int D>
 __global__ void __launch_bounds__(kThreads, 2)
 ucv_kernel(UcvJob job, long long upb, const double* __restrict__ exp_tab_g) {
@@ -125,19 +157,32 @@ ucv_kernel(UcvJob job, long long upb, const double* __restrict__ exp_tab_g) {
     constexpr int TILE = pair_tile<T>(D);
     constexpr int TB = kThreads * R;
     constexpr uint32_t TILE_BYTES = TILE * D * sizeof(T);
+    constexpr uint32_t NRM_BYTES = pair_nrm_bytes<T>(D);  // per stage; 0 for f32
+    constexpr bool DOT = PBN_F64_DOT && sizeof(T) == 8;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T* tile_buf = reinterpret_cast<T*>(smem_raw);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + kStages * TILE_BYTES);
-    double* tab = reinterpret_cast<double*>(smem_raw + kStages * TILE_BYTES + 64);
+    double* nrm_buf = reinterpret_cast<double*>(smem_raw + kStages * TILE_BYTES);  // [kStages][TILE]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + kStages * (TILE_BYTES + NRM_BYTES));
+    double* tab = reinterpret_cast<double*>(smem_raw + kStages * (TILE_BYTES + NRM_BYTES) + 64);
     __shared__ double red[2][kThreads / 32];
 
     const int tid = threadIdx.x;
     const long long u0 = job.unit_begin + static_cast<long long>(blockIdx.x) * upb;
     long long u1 = u0 + upb;
     if (u1 > job.unit_end) u1 = job.unit_end;
-    double s2[R], s1[R];
+    double s2[R], s1[R], scale[R];  // sums of the current row tile; scale: see ucv_tile_dot (1 in the difference form)
+    double tot2 = 0, tot1 = 0;      // finished row tiles of this CTA
 #pragma unroll
-    for (int r = 0; r < R; ++r) { s2[r] = 0; s1[r] = 0; }
+    for (int r = 0; r < R; ++r) { s2[r] = 0; s1[r] = 0; scale[r] = 1.0; }
+    auto fold = [&]() {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            tot2 = fma(s2[r], scale[r], tot2);
+            tot1 = fma(s1[r], scale[r] * scale[r], tot1);
+            s2[r] = 0;
+            s1[r] = 0;
+        }
+    };
 
     if (u0 < u1) {
         if (sizeof(T) == 8) exp_tab_fill(tab, exp_tab_g, tid, kThreads);
@@ -147,10 +192,14 @@ ucv_kernel(UcvJob job, long long upb, const double* __restrict__ exp_tab_g) {
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncthreads();
-        bool safe = true;
+        bool safe = true, dot = false;
         if (sizeof(T) == 8) {
             float a = job.bound ? *job.bound : INFINITY;
             safe = !(static_cast<float>(D) * 4.f * a * a < 2.0e9f);
+            if (DOT) {  // same cancellation bound as pair_kernel (tile_f64_dot)
+                float crit = sqrtf(static_cast<float>(D + 1)) * 2.f * D * a * a;
+                dot = job.nrm && crit < static_cast<float>(kDotTol * 9007199254740992.0 / kExpA) && !safe;
+            }
         }
         // row tile of the first unit
         int lo = 0, hi = job.n_row_tiles - 1;
@@ -167,9 +216,12 @@ ucv_kernel(UcvJob job, long long upb, const double* __restrict__ exp_tab_g) {
             long long cnt = job.n - start;
             if (cnt > TILE) cnt = TILE;
             uint32_t bytes = static_cast<uint32_t>(((cnt * D * sizeof(T)) + 15) & ~15ull);
-            mbar_expect_tx(&full_bar[stage], bytes);
+            uint32_t nbytes = 0;
+            if (DOT && dot) nbytes = static_cast<uint32_t>((cnt * sizeof(double) + 15) & ~15ull);
+            mbar_expect_tx(&full_bar[stage], bytes + nbytes);
             tma_bulk_g2s(tile_buf + static_cast<size_t>(stage) * TILE * D,
                          reinterpret_cast<const T*>(job.y) + start * D, bytes, &full_bar[stage]);
+            if (nbytes) tma_bulk_g2s(nrm_buf + static_cast<size_t>(stage) * TILE, job.nrm + start, nbytes, &full_bar[stage]);
             ++pu;
         };
         if (tid == 0)
@@ -177,6 +229,7 @@ ucv_kernel(UcvJob job, long long upb, const double* __restrict__ exp_tab_g) {
 
         int ctt = lo, cur_tt = -1;
         T yi[R][D];
+        int ati[R];
         long long rowid[R];
         for (long long u = u0; u < u1; ++u) {
             const int stage = static_cast<int>((u - u0) % kStages);
@@ -184,6 +237,7 @@ ucv_kernel(UcvJob job, long long upb, const double* __restrict__ exp_tab_g) {
             while (job.prefix[ctt + 1] <= u) ++ctt;
             const long long nt = u - job.prefix[ctt];
             if (ctt != cur_tt) {
+                fold();
                 cur_tt = ctt;
                 const T* yp = reinterpret_cast<const T*>(job.y);
 #pragma unroll
@@ -193,6 +247,17 @@ ucv_kernel(UcvJob job, long long upb, const double* __restrict__ exp_tab_g) {
                     rowid[r] = ok ? row : -1;  // invalid rows pair with nothing (j < -1 never holds)
 #pragma unroll
                     for (int c = 0; c < D; ++c) yi[r][c] = ok ? yp[row * D + c] : T(0);
+                    ati[r] = 0;
+                    if constexpr (DOT) {
+                        if (dot) {
+                            const double at = ok ? job.nrm[row] : 0.0;
+                            const double ai = rint(at);  // |at| < 2^31 (the `safe` test above)
+                            scale[r] = exp((at - ai) * kExpA);
+                            ati[r] = static_cast<int>(ai);
+#pragma unroll
+                            for (int c = 0; c < D; ++c) yi[r][c] *= T(2);
+                        }
+                    }
                 }
             }
             const long long col0 = nt * TILE;
@@ -203,7 +268,15 @@ ucv_kernel(UcvJob job, long long upb, const double* __restrict__ exp_tab_g) {
             const bool full = (col0 + cnt <= row_lo) && (row_lo + TB <= job.n);
             mbar_wait(&full_bar[stage], parity);
             const T* __restrict__ tp = tile_buf + static_cast<size_t>(stage) * TILE * D;
-            if (full) {
+            if constexpr (DOT) {
+                if (dot) {
+                    const double* nb = nrm_buf + static_cast<size_t>(stage) * TILE;
+                    if (full) ucv_tile_dot<D, false, R>(tp, nb, cnt, col0, yi, ati, rowid, tab, s2, s1);
+                    else ucv_tile_dot<D, true, R>(tp, nb, cnt, col0, yi, ati, rowid, tab, s2, s1);
+                }
+            }
+            if (DOT && dot) {
+            } else if (full) {
                 if (safe) ucv_tile<T, D, false, true, R>(tp, cnt, col0, yi, rowid, tab, s2, s1);
                 else ucv_tile<T, D, false, false, R>(tp, cnt, col0, yi, rowid, tab, s2, s1);
             } else {
@@ -215,9 +288,8 @@ ucv_kernel(UcvJob job, long long upb, const double* __restrict__ exp_tab_g) {
         }
     }
     // deterministic CTA reduction
-    double a = 0, b = 0;
-#pragma unroll
-    for (int r = 0; r < R; ++r) { a += s2[r]; b += s1[r]; }
+    fold();
+    double a = tot2, b = tot1;
     for (int o = 16; o > 0; o >>= 1) {
         a += __shfl_down_sync(0xffffffffu, a, o);
         b += __shfl_down_sync(0xffffffffu, b, o);
@@ -234,7 +306,7 @@ ucv_kernel(UcvJob job, long long upb, const double* __restrict__ exp_tab_g) {
 
 template <typename T, int D>
 static cudaError_t launch_ucv_one(const UcvJob& job, long long upb, int grid, const double* tab, cudaStream_t stream) {
-    constexpr size_t smem = kStages * pair_tile<T>(D) * D * sizeof(T) + 64 + exp_tab_smem_bytes<T>();
+    constexpr size_t smem = kStages * (pair_tile<T>(D) * D * sizeof(T) + pair_nrm_bytes<T>(D)) + 64 + exp_tab_smem_bytes<T>();
     auto kern = ucv_kernel<T, D>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
