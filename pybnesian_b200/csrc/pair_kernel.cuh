@@ -105,14 +105,15 @@ template <typename T> struct PairCfg;
 #define PBN_F64_UNROLL 4
 #endif
 // test rows per thread and training points per unrolled step, by kernel shape (B200, N = m = 300k, profiles/r1h_tuning.md):
-// f64 KDE (no marginal sum) d <= 4 runs 4-5% faster with 4 rows per thread, the CKDE kernels 3% slower (registers);
+// f64 KDE (no marginal sum) d <= 5 runs 4-5% faster with 4 rows per thread (d = 6: -2%), the CKDE kernels 1-3% slower
+// (registers; CKDE d=2 +1.6%, not worth a special case);
 // 8 points per step pay for d <= 2 only (KDE d=2 +5%, CKDE d=4 -3%, KDE d=8 -3%).
 template <typename T> __host__ __device__ constexpr int pair_rows(int D, bool ckde);
 template <> struct PairCfg<double> { static constexpr int R = PBN_F64_R; static constexpr int TILE = PBN_F64_TILE; static constexpr int MIN_CTAS = PBN_F64_MINCTAS; };
 template <> struct PairCfg<float>  { static constexpr int R = PBN_F32_R; static constexpr int TILE = PBN_F32_TILE; static constexpr int MIN_CTAS = PBN_F32_MINCTAS; };
 
 template <typename T> __host__ __device__ constexpr int pair_rows(int D, bool ckde) {
-    return (sizeof(T) == 8 && PBN_F64_R == 3 && !ckde && D <= 4) ? 4 : PairCfg<T>::R;
+    return (sizeof(T) == 8 && PBN_F64_R == 3 && !ckde && D <= 5) ? 4 : PairCfg<T>::R;
 }
 __host__ __device__ constexpr int pair_unroll_f64(int D, bool ckde) {
     return (PBN_F64_UNROLL == 4 && !ckde && D <= 2) ? 8 : PBN_F64_UNROLL;

@@ -30,6 +30,8 @@ if __name__ == "__main__":
         shapes += [("ckde", 4, "float64"), ("kde", 1, "float64"), ("kde", 2, "float64"), ("kde", 4, "float64"), ("kde", 8, "float64")]
     if which in ("all", "f32"):
         shapes += [("ckde", 4, "float32"), ("kde", 1, "float32"), ("kde", 2, "float32"), ("kde", 4, "float32"), ("kde", 8, "float32")]
+    if os.environ.get("TUNE_SHAPES"):  # e.g. "ckde:2:float64,kde:5:float64"
+        shapes = [(k, int(d), dt) for k, d, dt in (x.split(":") for x in os.environ["TUNE_SHAPES"].split(","))]
     out = {}
     for kind, d, dt in shapes:
         v, s = run(kind, d, n, dt)
