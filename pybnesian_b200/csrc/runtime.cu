@@ -797,7 +797,7 @@ int pbn_ctx_create(int device, pbn_ctx** out) {
     c->stream = c->own_stream;
     std::vector<double> tab(pbn::kExpTab);
     for (int j = 0; j < pbn::kExpTab; ++j) {
-        // T'[j]: 2^(j/256) with (j << 12) subtracted from the high word (see exp2_tab)
+        // T'[j]: 2^(j/K) with (j << (20 - log2 K)) subtracted from the high word (see exp2_tab)
         double v = (double)exp2l((long double)j / pbn::kExpTab);
         uint64_t bits;
         memcpy(&bits, &v, 8);

@@ -1,0 +1,103 @@
+"""CPU checks of the arithmetic the f64 pair kernel's exp2 relies on (pybnesian_b200/csrc/pair_kernel.cuh), restated in
+numpy with the constants read from the header: the accuracy of the table + polynomial split, the hoisted test-row norm of
+the dot-product form (tile_f64_dot) and the exponent floor (pair_floor).  No GPU, no oracle: these pin the error bounds
+DESIGN.md quotes, so that a change of PBN_EXP_BITS / PBN_EXP_DEG / PBN_F64_FLOOR_BITS that breaks them fails here."""
+import os
+import re
+
+import numpy as np
+
+HDR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "pybnesian_b200", "csrc", "pair_kernel.cuh")
+
+
+def _define(name):
+    m = re.search(r"#ifndef %s\s*\n#define %s\s+(\S+)" % (name, name), open(HDR).read())
+    assert m, name
+    return int(m.group(1))
+
+
+BITS, DEG, FLOOR = _define("PBN_EXP_BITS"), _define("PBN_EXP_DEG"), _define("PBN_F64_FLOOR_BITS")
+K = 1 << BITS
+A = np.log(2.0) / K
+H2 = 0.25 * A * A
+C0 = 1.0 - H2 * H2 / 192.0 if DEG == 3 else 1.0
+C1 = A * (1.0 + H2 / 8.0) if DEG == 2 else A
+C2 = A * A * (0.5 + H2 / 24.0) if DEG == 3 else 0.5 * A * A
+C3 = A ** 3 / 6.0
+NMIN = -1022 * K
+
+
+def poly(g):
+    p = C3 * g + C2 if DEG == 3 else np.full_like(g, C2)
+    return (p * g + C1) * g + C0
+
+
+def exp2_tab(t, nshift=0, nmin=NMIN):
+    """2^((t + nshift)/K) the way exp2_tab computes it: n = rint(t) + nshift clamped to nmin, g = t - rint(t)."""
+    nd = np.rint(t)
+    n = np.maximum(nd.astype(np.int64) + nshift, nmin)
+    return np.ldexp(np.exp2((n % K) / K), (n // K).astype(np.int64)) * poly(t - nd)
+
+
+def test_polynomial_error_is_what_the_docs_say():
+    g = np.linspace(-0.5, 0.5, 200001)
+    err = np.max(np.abs(poly(g) / np.exp(A * g) - 1.0))
+    assert DEG in (2, 3)
+    assert err < (3e-14 if DEG == 2 else 1e-15) * (4096.0 / K) ** (DEG + 1) + 3e-16  # 2.5e-14 at K = 4096, degree 2
+
+
+def test_table_split_matches_exp2():
+    rng = np.random.default_rng(0)
+    t = -rng.uniform(0, 900 * K, 200000)
+    got, want = exp2_tab(t), np.exp2(t / K)
+    assert np.max(np.abs(got / want - 1.0)) < 4e-14
+
+
+def test_hoisted_row_norm_is_an_integer_shift_times_a_row_factor():
+    """tile_f64_dot: exponent = at + (b + sum 2 yt p).  at = A_int + f; A_int joins the rounded exponent, 2^(f/K) scales
+    the finished sum: same value as evaluating the full exponent, term by term."""
+    rng = np.random.default_rng(1)
+    at = -rng.uniform(0, 3e5)
+    rest = rng.uniform(-2e5, 3e5, 100000)  # b + dot product; at + rest <= 0 for a real pair, keep those
+    rest = rest[at + rest <= 0]
+    ai = np.rint(at)
+    hoisted = exp2_tab(rest, nshift=int(ai)) * np.exp((at - ai) * A)
+    direct = np.exp2((at + rest) / K)
+    assert np.max(np.abs(hoisted / direct - 1.0)) < 5e-14
+    assert abs(hoisted.sum() / direct.sum() - 1.0) < 1e-14
+
+
+def _floor(s):
+    if FLOOR == 0 or s <= 0.0:
+        return NMIN
+    e = int(np.floor(np.log2(s)))  # exponent field of the running sum
+    return max((e - FLOOR) * K, NMIN)
+
+
+def _floored_sum(t, tile):
+    """Sum of 2^(t_i/K) in tiles of `tile` terms with the floor refreshed from the running sum before each tile."""
+    s = 0.0
+    for i in range(0, len(t), tile):
+        s += float(exp2_tab(t[i:i + tile], nmin=_floor(s)).sum())
+    return s
+
+
+def test_exponent_floor_changes_nothing_visible():
+    rng = np.random.default_rng(2)
+    n, tile = 200_000, 512
+    near = -rng.uniform(0, 40 * K, n // 20)          # the terms that make up the sum
+    far = -rng.uniform(60 * K, 1000 * K, n - len(near))  # the bulk: far pairs
+    for order in ("near_first", "far_first", "shuffled"):
+        t = np.concatenate([near, far] if order == "near_first" else [far, near])
+        if order == "shuffled":
+            t = rng.permutation(t)
+        exact = float(np.exp2(t / K).sum())
+        got = _floored_sum(t, tile)
+        plain = _floored_sum(t, len(t))  # one tile: floor never above kNMin
+        assert abs(got / exact - 1.0) < 1e-13
+        assert abs(got - plain) <= n * 2.0 ** -FLOOR * exact + 4 * np.finfo(float).eps * exact
+    # every floored lane reads table entry 0: the floor is a multiple of K
+    assert _floor(3.7) % K == 0 and _floor(1e-200) % K == 0
+    # a tiny row (all terms ~ 2^-600) keeps its relative accuracy: the floor follows the running sum down
+    tiny = -rng.uniform(600 * K, 640 * K, 50_000)
+    assert abs(_floored_sum(tiny, tile) / float(np.exp2(tiny / K).sum()) - 1.0) < 1e-13
