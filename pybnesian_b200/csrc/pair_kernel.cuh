@@ -374,7 +374,7 @@ __device__ __forceinline__ void tile_f64(const double* __restrict__ tp, int cnt,
 // and the fraction f is a per-test-row FACTOR 2^(f/K) of every term of the row, applied once to the finished sums
 // (pair_kernel's flush).  The exponent chain then starts from the training norm (the first DFMA takes nb as its
 // addend): DN DFMA per pair instead of 1 DADD + DN DFMA.  Measured on B200 (N = m = 300k, profiles/r1h_tuning.md): KDE
-// d=4 1.085e12 -> 1.141e12 pairs/s, d=8 8.29e11 -> 8.41e11.  Carrying A on the rounding constant instead (kExpMagic + A
+// d=4 1.085e12 -> 1.141e12 pairs/s, d=8 8.29e11 -> 8.41e11.  Carrying A on the rounding constant instead (1.5 * 2^52 + A
 // in a register, no IADD) was 3% SLOWER than not hoisting at all: the two DADDs of the exp2 then read a register pair
 // where they had an immediate, and this kernel is sensitive to register-operand traffic, not to the FP64 count alone.
 #ifndef PBN_F64_HOIST
