@@ -199,3 +199,28 @@ def test_singular_covariance():
         oracle.bandwidth(X)
     with pytest.raises(oracle.SingularCovariance):
         oracle.bandwidth(X[:2])
+
+
+FLOOR_GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "floor_golden.npz"))
+
+
+@pytest.mark.parametrize("dt", ["float64", "float32"])
+@pytest.mark.parametrize("order", ["near_first", "far_first", "shuffled"])
+@pytest.mark.parametrize("variables", [["b"], ["b", "a"], ["b", "a", "c", "d"]])
+def test_oracle_bit_exact_on_two_cluster_golden(dt, order, variables):
+    """Two clusters 25 sigma apart, test rows in both, between and beyond (tests/golden/make_golden_floor.py): almost every
+    kernel term of a row is negligible and the joint / marginal log-likelihoods of the outlying rows nearly cancel.  The
+    restatement must still reproduce the reference kernels bit for bit, in every training-row order."""
+    train, test = util_data.two_cluster_frames(order)
+    X, T = train[variables].to_numpy().astype(dt), test[variables].to_numpy().astype(dt)
+    H = oracle.bandwidth(X)
+    key = "%s_%s_%s" % (dt, order, "".join(variables))
+    logl, _ = oracle.kde_logl(X, T, H)
+    assert np.array_equal(logl, FLOOR_GOLD["ref_kde_logl_" + key], equal_nan=True)
+    if len(variables) > 1:
+        cl, _ = oracle.ckde_logl(X, T, H)
+        assert np.array_equal(cl, FLOOR_GOLD["ref_ckde_logl_" + key], equal_nan=True)
+        if dt == "float64":  # and the long-double value, to the accuracy the reference arithmetic has on these rows
+            ld = oracle.kde_logl_ld(X, T, H) - oracle.kde_logl_ld(X[:, 1:], T[:, 1:], H[1:, 1:])
+            scale = np.maximum(np.abs(oracle.kde_logl_ld(X, T, H)), 1.0)
+            assert np.max(np.abs(cl - ld) / scale) < 1e-11

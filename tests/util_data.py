@@ -46,3 +46,18 @@ def generate_hybrid_data(size, seed=0):
         else:
             d[sel] = b0 + b1 * c[sel] + np.random.normal(0, sd, size=sel.sum())
     return pd.DataFrame({"A": pd.Series(a, dtype="category"), "B": pd.Series(b, dtype="category"), "C": c, "D": d})
+
+
+def two_cluster_frames(order, n_half=300, m_sizes=(12, 12, 6, 6)):
+    """Training set of two clusters 25 sigma apart in the given row order ("near_first", "far_first", "shuffled") and test
+    rows in both clusters, between them and beyond (tests/golden/make_golden_floor.py, tests/test_oracle.py)."""
+    rng = np.random.default_rng(11)
+    near = generate_normal_data(n_half, seed=0)
+    far = generate_normal_data(n_half, seed=2) + 25.0
+    train = pd.concat([near, far] if order != "far_first" else [far, near], ignore_index=True)
+    if order == "shuffled":
+        train = train.iloc[rng.permutation(len(train))].reset_index(drop=True)
+    test = pd.concat([generate_normal_data(m_sizes[0], seed=1), generate_normal_data(m_sizes[1], seed=3) + 25.0,
+                      generate_normal_data(m_sizes[2], seed=4) + 12.5, generate_normal_data(m_sizes[3], seed=5) * 3.0],
+                     ignore_index=True)
+    return train, test
