@@ -18,3 +18,8 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:pair
 timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:pair_kernel -s 3 -c 1 --csv \
     --log-file gpurun_out/traffic.csv python bench.py --steps 1 --warmup 3 --no-cpu --e2e-steps 1 > gpurun_out/ncu_traffic.log 2>&1
 ls -la gpurun_out
+# per-shape pair-kernel throughput (N = m = 300k), UCV objective, config 4
+timeout 200 python tools/tune_bench.py all > gpurun_out/tune_default.log 2>&1
+python tools/tune_summary.py gpurun_out/tune_default.log
+timeout 100 python tools/ucv_bench.py > gpurun_out/ucv_200k.log 2>&1; tail -3 gpurun_out/ucv_200k.log
+timeout 200 python tools/hc_bench.py --json gpurun_out/hc_config4.json > gpurun_out/hc_config4.log 2>&1; tail -c 300 gpurun_out/hc_config4.log
