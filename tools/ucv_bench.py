@@ -1,4 +1,5 @@
-"""BASELINE.json configs[2]: UCV objective and UCV().bandwidth on N rows, d = 4, both dtypes.\nusage: python tools/ucv_bench.py [n_rows]"""
+"""BASELINE.json configs[2]: UCV objective and UCV().bandwidth on N rows, d = 4, both dtypes.
+usage: python tools/ucv_bench.py [n_rows]"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
