@@ -2,7 +2,8 @@
 (test tile x training tile) units of BASELINE configs[1] lies entirely below the exponent floor (pair_floor in
 pair_kernel.cuh) and could be skipped from the tiles' bounding boxes alone?
 
-    python tools/skip_model.py [n_rows] [floor_bits]
+    python tools/skip_model.py [n_rows] [floor_bits]            config 2: CKDE d = 4 (joint and marginal)
+    python tools/skip_model.py kde N d [floor_bits] [n_test]    KDE of d i.i.d. normal columns (config 5 / CV-fold shapes)
 
 Not part of the product or the tests; DESIGN.md section 9 quotes its output."""
 import os, sys
@@ -11,12 +12,22 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 import oracle, util_data
 
-N = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
-BITS = float(sys.argv[2]) if len(sys.argv) > 2 else 80.0
-TB, TILE = 768, 512
-cols = ["d", "a", "b", "c"]
-X = util_data.generate_normal_data(N, seed=0)[cols].to_numpy()
-T = util_data.generate_normal_data(N, seed=1)[cols].to_numpy()
+KDE_MODE = len(sys.argv) > 1 and sys.argv[1] == "kde"
+args = sys.argv[2:] if KDE_MODE else sys.argv[1:]
+N = int(args[0]) if len(args) > 0 else 1_000_000
+if KDE_MODE:
+    D = int(args[1])
+    BITS = float(args[2]) if len(args) > 2 else 80.0
+    M = int(args[3]) if len(args) > 3 else N
+    TB, TILE = (1024 if D <= 5 else 768), (512 if D <= 6 else 256)  # pair_rows / pair_tile of the f64 KDE kernels
+    X = util_data.iid_normal(N, D, 0, "float64").to_numpy()
+    T = util_data.iid_normal(M, D, 1, "float64").to_numpy()
+else:
+    BITS = float(args[1]) if len(args) > 1 else 80.0
+    TB, TILE = 768, 512
+    cols = ["d", "a", "b", "c"]
+    X = util_data.generate_normal_data(N, seed=0)[cols].to_numpy()
+    T = util_data.generate_normal_data(N, seed=1)[cols].to_numpy()
 H = oracle.bandwidth(X)
 
 
@@ -52,7 +63,7 @@ def model(name, Hm, Xc, Tc, order):
         Y, Z = Y[np.argsort(morton((Y - lo) / (hi - lo)))], Z[np.argsort(morton((Z - lo) / (hi - lo)))]
     # log2 of the row sums of a sample of test rows (exact, against all training rows) -> floor of a test tile
     rng = np.random.default_rng(0)
-    samp = rng.choice(len(Z), 200, replace=False)
+    samp = rng.choice(len(Z), min(200, len(Z)), replace=False)
     l2 = []
     for z in Z[samp]:
         e = -0.5 * ((Y - z) ** 2).sum(1) * np.log2(np.e)
@@ -72,5 +83,8 @@ def model(name, Hm, Xc, Tc, order):
 
 
 for order in ("none", "coord0", "morton"):
-    aj, tj = model("joint d=4", H, X, T, order)
-    am, tm = model("marg d=3", H[1:, 1:], X[:, 1:], T[:, 1:], order)
+    if KDE_MODE:
+        model("KDE d=%d" % D, H, X, T, order)
+    else:
+        model("joint d=4", H, X, T, order)
+        model("marg d=3", H[1:, 1:], X[:, 1:], T[:, 1:], order)
