@@ -18,6 +18,10 @@ log-likelihood scalar.
             libpbn_cuda on the launching stream) against the FP64 FMA roofline of SURVEY.md §8(d)
   cpu_baseline  the CPU oracle (port of the reference arithmetic; the reference itself cannot be
             built here) on a bounded sample of the same workload, all host threads
+  strong_scaling  ONE 1M x 1M job sharded over the ranks by the product's own parallel.py, checked against
+            the single-GPU result inside the run
+  hc_cv / hc_cv_s_per_iter  the second half of BASELINE.json's metric: hill climbing with CVLikelihood on
+            configs[3], candidates dealt over the ranks
 
 `--impl reference` times only that CPU arm.
 """
@@ -101,50 +105,73 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": max(power) if power else None}
 
 
-def cpu_arm(n_train, sample_rows, steps, warmup):
-    """Times the CPU oracle (reference arithmetic, OpenMP over test rows) on `sample_rows`
-    test rows against the full training set.  Returns (pair-evals/s, threads, ms/step, check)."""
+def cpu_arm(n_train, sample_rows, steps, warmup, budget_s=None):
+    """Times the CPU oracle (reference arithmetic, OpenMP over test rows, -O3 -march=native timing build compiled on
+    this host) on `sample_rows` test rows against the full training set, on ALL host threads (torchrun exports
+    OMP_NUM_THREADS=1 to its workers; that is undone here).  With `budget_s` the sample is cut (never below 64 rows)
+    so that warmup + steps passes fit the budget on this host's cores.
+    Returns (pair-evals/s, threads, ms/step, slogl of the sample, rows used)."""
     import oracle
+    threads = oracle.use_all_threads()
     tr = gen(n_train, 0)[VARIABLES].to_numpy()
-    te = gen(max(sample_rows, 1), 1)[VARIABLES].to_numpy()
+    te_all = gen(max(sample_rows, 64), 1)[VARIABLES].to_numpy()
     H = oracle.bandwidth(tr)
+    oracle.ckde_logl(tr, te_all[:threads], H, fast=True)          # builds / loads the timing library, first touch
+    threads = oracle.use_all_threads()
+    t0 = time.perf_counter()
+    probe = min(len(te_all), max(64, 2 * threads))
+    oracle.ckde_logl(tr, te_all[:probe], H, fast=True)
+    rate_rows = probe / (time.perf_counter() - t0)                 # test rows per second on this host
+    rows = sample_rows
+    if budget_s:
+        rows = int(min(sample_rows, max(64, rate_rows * budget_s / max(1, steps + warmup))))
+    te = te_all[:rows]
     for _ in range(warmup):
-        oracle.ckde_logl(tr, te[: max(8, sample_rows // 16)], H)
+        oracle.ckde_logl(tr, te, H, fast=True)
     times = []
+    s = 0.0
     for _ in range(steps):
         t0 = time.perf_counter()
-        _, s = oracle.ckde_logl(tr, te, H)
+        _, s = oracle.ckde_logl(tr, te, H, fast=True)
         times.append(time.perf_counter() - t0)
     t = float(np.mean(times))
-    return 2.0 * n_train * sample_rows / t, oracle.num_threads(), 1e3 * t, s
+    return 2.0 * n_train * rows / t, threads, 1e3 * t, s, rows
+
+
+CPU_NOTE = ("oracle/ port of the reference arithmetic (per-pair forward substitution + two-pass LSE), -O3 -march=native, "
+            "OpenMP over test rows on all host threads; the reference's OpenCL host path cannot be built in this image "
+            "(no CL/cl.h, no ICD, no NLopt/Boost/Arrow 17) and its kernels through oracle/_ref run ~1000x slower than "
+            "the port (work-group emulation), so timing them would measure the shim")
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, args.steps)
-    # ~1e8 pair-evals/s on 8 cores: 192 rows x 1M x 2 = 3.8e8 pair-evals ~ 4 s per step
-    rows = args.cpu_rows or 192
-    val, threads, ms, _ = cpu_arm(args.n_train, rows, steps, min(args.warmup, 1))
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    # 4096 test rows (SURVEY 8d) when the host is fast enough for warmup + steps passes to end within ~150 s
+    rows_cap = args.cpu_rows or 4096
+    val, threads, ms, _, rows = cpu_arm(args.n_train, rows_cap, steps, warmup, budget_s=args.cpu_budget)
     sample = "%d of %d test rows per step against all %d training rows" % (rows, args.n_test, args.n_train)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
-                         "note": "oracle/ port of the reference arithmetic; the reference's OpenCL path cannot be "
-                                 "built in this image (no CL/cl.h, no ICD, no NLopt/Boost)"},
+                         "build": "-O3 -march=native -fopenmp", "note": CPU_NOTE},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
 def workload_config(args):
-    return {"workload": "configs[1]: CKDE('d'|'a','b','c') slogl, float64, %d train x %d test rows per GPU, "
-                        "NormalReferenceRule bandwidth, generate_normal_data seeds 0/1" % (args.n_train, args.n_test),
-            "n_train": args.n_train, "n_test_per_gpu": args.n_test, "d_joint": 4, "d_marginal": 3,
-            "parallelism": "test rows sharded over %d GPU(s), training set replicated" % args.gpus,
+    strong = getattr(args, "scaling", "weak") == "strong"
+    return {"workload": "configs[1]: CKDE('d'|'a','b','c') slogl, float64, %d train x %d test rows %s, "
+                        "NormalReferenceRule bandwidth, generate_normal_data seeds 0/1"
+                        % (args.n_train, args.n_test, "in ONE job" if strong else "per GPU"),
+            "n_train": args.n_train, ("n_test" if strong else "n_test_per_gpu"): args.n_test, "d_joint": 4, "d_marginal": 3,
+            "parallelism": ("one frame of test rows sharded over %d GPU(s) by pybnesian_b200.parallel, training set replicated"
+                            if strong else "every one of %d GPU(s) scores its own test rows, training set replicated") % args.gpus,
             "l2": "flushed between timed steps (256 MiB memset); train set (32 MB) is L2 resident by design"}
 
 
@@ -157,7 +184,12 @@ def main():
     ap.add_argument("--n-train", type=int, default=1_000_000)
     ap.add_argument("--n-test", type=int, default=1_000_000)
     ap.add_argument("--cpu-rows", type=int, default=0, help="test rows of the CPU-baseline sample")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-budget", type=float, default=150.0, help="seconds the reference arm may spend in total")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 10)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every rank scores its own n_test rows (headline); strong: ONE n_train x n_test job "
+                         "sharded over the ranks by pybnesian_b200.parallel is the headline instead")
+    ap.add_argument("--no-extras", action="store_true", help="skip the strong-scaling and hill-climbing side measurements")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
 
@@ -183,8 +215,9 @@ def main():
     from pybnesian_b200 import _lib, parallel
     import ctypes
 
-    # weak scaling: every rank owns ITS OWN 1M test rows (a different seed per rank) and calls the
-    # single-GPU entry points on them; the API-level sharding of one shared frame (parallel.py) is off
+    strong = args.scaling == "strong"
+    # weak scaling (headline): every rank owns ITS OWN n_test rows (a different seed per rank) and calls the
+    # single-GPU entry points on them.  strong scaling: ONE frame, sharded by the product's own parallel.py.
     parallel.enable(False)
 
     ctx = pbn.default_context()
@@ -195,7 +228,7 @@ def main():
     steps, warmup = args.steps, max(args.warmup, 3)
     n_train, n_test = args.n_train, args.n_test
     train_df = gen(n_train, 0)
-    test_df = gen(n_test, 1 + rank)  # each rank scores its own shard of test rows
+    test_df = gen(n_test, 1 if strong else 1 + rank)  # weak: each rank scores its own shard of test rows
     train = pbn.DataFrame(train_df)
     test = pbn.DataFrame(test_df)
 
@@ -205,10 +238,11 @@ def main():
     out = torch.zeros(1, dtype=torch.float64, device="cuda")
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
     L = _lib.lib()
+    b_sh, e_sh = parallel.shard_range(n_test, rank, world) if strong else (0, n_test)
 
     def step():
         _lib.check(L.pbn_kde_logl_device(ctx.handle, cpd._handle.handle, test_tbl.handle, _lib.int_array(test_cols),
-                                         test_tbl.rows(), None, ctypes.c_void_p(out.data_ptr())))
+                                         test_tbl.rows(b_sh, e_sh), None, ctypes.c_void_p(out.data_ptr())))
         if world > 1:
             dist.all_reduce(out)
 
@@ -216,6 +250,12 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def reduce_max(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     for _ in range(warmup):
         step()
@@ -238,18 +278,15 @@ def main():
     c1 = ctx.counters()
     ctx.set_timing(False)
     step_ms = [a.elapsed_time(b) for a, b in ev]
-    total_ms = float(sum(step_ms))
     kern_ms, kern_launches, kern_pairs = ctx.pair_kernel_time(reset=True)
     slogl_total = float(out.item())
-
-    tmax = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    total_ms = float(tmax.item())
-    pairs_per_step_per_gpu = 2.0 * n_train * n_test
-    value = pairs_per_step_per_gpu * world * steps / (total_ms * 1e-3)
+    total_ms = reduce_max(float(sum(step_ms)))
+    pairs_per_step_job = 2.0 * n_train * n_test * (1 if strong else world)
+    value = pairs_per_step_job * steps / (total_ms * 1e-3)
 
     # ---- e2e: public API with host buffers (pinned), H2D + D2H inside the timed region ----
+    e2e_steps = args.e2e_steps or min(steps, 10)
+    parallel.enable(strong)   # strong: CKDE.slogl shards the frame itself (and all-reduces the scalar)
     pinned = {c: torch.from_numpy(test_df[c].to_numpy()).pin_memory() for c in VARIABLES}
     host_rb = pa.RecordBatch.from_arrays([pa.array(pinned[c].numpy()) for c in VARIABLES], names=VARIABLES)
     cpd.slogl(host_rb)  # warm
@@ -257,24 +294,28 @@ def main():
     e0 = ctx.counters()
     t0 = time.perf_counter()
     e2e_sum = torch.zeros(1, dtype=torch.float64, device="cuda")
-    for _ in range(args.e2e_steps):
+    for _ in range(e2e_steps):
         s_e2e = cpd.slogl(host_rb)
-        if world > 1:   # the job's result is the sum over the ranks' shards
+        if world > 1 and not strong:   # weak: the job's result is the sum over the ranks' own frames
             e2e_sum[0] = s_e2e
             dist.all_reduce(e2e_sum)
     ctx.synchronize()
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    e2e_s = reduce_max(time.perf_counter() - t0)
     e1 = ctx.counters()
-    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = pairs_per_step_per_gpu * world * args.e2e_steps / float(te.item())
-    e2e = {"value": e2e_value, "unit": UNIT,
-           "h2d_bytes_per_step": (e1["h2d_bytes"] - e0["h2d_bytes"]) // args.e2e_steps,
-           "d2h_bytes_per_step": (e1["d2h_bytes"] - e0["d2h_bytes"]) // args.e2e_steps,
-           "api": "CKDE.slogl(pyarrow.RecordBatch over pinned host buffers)", "steps": args.e2e_steps,
+    parallel.enable(False)
+    e2e = {"value": pairs_per_step_job * e2e_steps / e2e_s, "unit": UNIT,
+           "h2d_bytes_per_step": (e1["h2d_bytes"] - e0["h2d_bytes"]) // e2e_steps,
+           "d2h_bytes_per_step": (e1["d2h_bytes"] - e0["d2h_bytes"]) // e2e_steps,
+           "api": "CKDE.slogl(pyarrow.RecordBatch over pinned host buffers)", "steps": e2e_steps,
            "timer": "host wall clock around the blocking API call, max over ranks"}
+
+    # ---- side measurements (every rank takes part; rank 0 reports) ----
+    extras = {}
+    if not args.no_extras:
+        extras["strong_scaling"] = strong_scaling_leg(args, ctx, cpd, world, rank, barrier, reduce_max, pbn, parallel)
+        extras["hc_cv"] = hc_leg(world)
+        barrier()
 
     if rank != 0:
         if world > 1:
@@ -290,59 +331,123 @@ def main():
         pass
     f_hz = (clocks.get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0) * 1e6
     sms, lanes = ctx.sm_count, 64
-    # FP64-pipe instructions per pair-eval I(d) = 2d + 18; CKDE run as two passes
-    # (joint d=4, marginal d=3) => mean (26 + 24)/2 = 25 per pair-eval.
-    i_survey = (2 * 4 + 18 + 2 * 3 + 18) / 2.0
-    # This kernel's own count per (train, test) row pair, which is 2 pair-evals: marginal exponent in dot-product form
-    # with the test-row norm hoisted (3 DFMA), table exp2 (3 DADD + 2 DFMA, degree-2 polynomial on K = 4096) + 1 DFMA to
-    # accumulate, last coordinate in difference form (1 DADD + 1 DFMA), second exp2 + accumulate: 3 + 6 + 2 + 6 = 17.
+    # FP64-pipe instructions this kernel issues per (train, test) row pair, which is 2 pair-evals (joint + marginal):
+    # marginal exponent in dot-product form with the test-row norm hoisted (3 DFMA), table exp2 (3 DADD + 2 DFMA,
+    # degree-2 polynomial on K = 4096) + 1 DFMA to accumulate, last coordinate in difference form (1 DADD + 1 DFMA),
+    # second exp2 + accumulate: 3 + 6 + 2 + 6 = 17 (SASS: profiles/r2_sass_pair_f64_ckde_d4.txt).  The roofline is
+    # the FP64 pipe at that count; `frac` is therefore the FP64-pipe utilisation and is cross-checked by ncu's
+    # sm__inst_executed_pipe_fp64 (profiles/r2_ncu_pair_f64_ckde_d4.txt).
     i_own = 17 / 2.0
+    # SURVEY.md 8(d) models a two-pass kernel with a 16-instruction polynomial exp: I(d) = 2d + 18 per pair-eval,
+    # (26 + 24) / 2 = 25 for joint d=4 + marginal d=3.  This kernel needs a third of that, so the ratio against the
+    # SURVEY model exceeds 1; it is reported on the side, never as the utilisation.
+    i_survey = (2 * 4 + 18 + 2 * 3 + 18) / 2.0
     achieved = kern_pairs / (kern_ms * 1e-3) if kern_ms > 0 else None
-    peak = sms * lanes * f_hz / i_survey
+    peak = sms * lanes * f_hz / i_own
     # DRAM bytes of one launch of this exact configuration, from a committed ncu capture
     # (tools/gpu_check.sh -> tools/traffic_json.py -> profiles/pair_kernel_traffic.json); null when none matches
     traffic, traffic_src = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "pair_kernel_traffic.json")) as f:
             for rec in json.load(f):
-                if rec.get("n_train") == n_train and rec.get("n_test") == n_test and rec.get("kernel") == "pair_kernel<double, 4, 1, 0>":
+                if rec.get("n_train") == n_train and rec.get("n_test") == (e_sh - b_sh) and rec.get("kernel") == "pair_kernel<double, 4, 1, 0>":
                     traffic = rec["dram_bytes_read"] + rec["dram_bytes_write"]
                     traffic_src = rec.get("source")
     except Exception:
         pass
+    alg_bytes = 8.0 * 4 * (n_train + (e_sh - b_sh)) + 8.0 * (e_sh - b_sh)
     roofline = {
         "bound": "fp64_fma", "kernel": "pbn::pair_kernel<double,4,CKDE>", "achieved": achieved, "peak": peak,
         "unit": UNIT, "frac": (achieved / peak) if achieved else None, "traffic": traffic,
         "traffic_source": traffic_src,
         "peak_def": "SMs(%d) x 64 FP64 lanes x %.0f MHz (median SM clock sampled in the timed region) / %.1f FP64-pipe "
-                    "instr per pair-eval (SURVEY.md 8d two-pass count; a fused pass may exceed 1.0)" % (sms, f_hz / 1e6, i_survey),
-        "own_count": {"fp64_instr_per_pair_eval": i_own, "peak": sms * lanes * f_hz / i_own,
-                      "frac": (achieved / (sms * lanes * f_hz / i_own)) if achieved else None},
+                    "instructions the kernel issues per pair-eval (17 per train x test row pair, SASS-counted): frac is "
+                    "the FP64-pipe utilisation" % (sms, f_hz / 1e6, i_own),
+        "fp64_instr_per_pair_eval": i_own,
+        "frac_vs_survey_model": (achieved / (sms * lanes * f_hz / i_survey)) if achieved else None,
+        "survey_model": "SURVEY.md 8(d) two-pass count, %.0f FP64 instr per pair-eval; a fused table-exp2 pass undercuts "
+                        "it, so this ratio is > 1 and is NOT a utilisation" % i_survey,
         "kernel_ms_per_launch": kern_ms / max(kern_launches, 1), "launches_timed": kern_launches,
         "kernel_share_of_step": kern_ms / (sum(step_ms)) if step_ms else None,
         "hbm_peak_gbs_measured": peaks.get("hbm_gbs"),
-        "algorithmic_bytes_per_pair_eval": (8.0 * 4 * (n_train + n_test) + 8.0 * n_test) / (2.0 * n_train * n_test),
+        "algorithmic_bytes_per_launch": alg_bytes,
+        "algorithmic_bytes_per_pair_eval": alg_bytes / (2.0 * n_train * (e_sh - b_sh)),
+        "traffic_note": "DRAM traffic above the algorithmic bytes is the partial-sum slots the stream-K decomposition "
+                        "writes and finalize re-reads plus the row norms of the dot-product form; DRAM is < 0.01% utilised",
     }
 
     cpu_baseline = None
     if not args.no_cpu:
-        rows = args.cpu_rows or 768
-        v, threads, ms, _ = cpu_arm(n_train, rows, 1, 1)
-        cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                        "sample": "%d of %d test rows against all %d training rows (%.1f s)" % (rows, n_test, n_train, ms / 1e3)}
+        v, threads, ms, _, rows = cpu_arm(n_train, args.cpu_rows or 4096, 1, 1, budget_s=30.0)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "build": "-O3 -march=native -fopenmp",
+                        "sample": "%d of %d test rows against all %d training rows (%.1f s)" % (rows, n_test, n_train, ms / 1e3),
+                        "note": CPU_NOTE}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
-        "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": workload_config(args),
         "clocks": clocks, "e2e": e2e, "gpu_launches": c1["launches"] - c0["launches"],
         "roofline": roofline, "cpu_baseline": cpu_baseline,
         "check": {"slogl_sum_over_ranks": slogl_total, "slogl_e2e_rank0": s_e2e,
                   "fallback_rows_last_call": ctx.last_fallback_rows(), "wall_s_timed_loop": wall},
     }
+    if extras:
+        line["strong_scaling"] = extras["strong_scaling"]
+        line["hc_cv"] = extras["hc_cv"]
+        line["hc_cv_s_per_iter"] = extras["hc_cv"].get("hc_cv_s_per_iter_mean")
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def strong_scaling_leg(args, ctx, cpd, world, rank, barrier, reduce_max, pbn, parallel):
+    """ONE n_train x n_test job (the same frame on every rank) through the PRODUCT's sharding, `CKDE.slogl` with
+    pybnesian_b200.parallel enabled: contiguous test-row shards against the replicated training set, one all-reduced
+    double.  The sharded result is checked against the single-GPU evaluation of the same frame inside the run."""
+    frame = pbn.DataFrame(gen(args.n_test, 1))
+    frame.device_table(VARIABLES)               # resident before the timed region, like `value`
+    parallel.enable(False)
+    s_single = cpd.slogl(frame)                 # every rank: whole frame on its own GPU
+    parallel.enable(True)
+    s_sharded = cpd.slogl(frame)                # warm-up of the sharded path, and the value that is checked
+    barrier()
+    n = 3
+    t0 = time.perf_counter()
+    for _ in range(n):
+        s_sharded = cpd.slogl(frame)
+    ctx.synchronize()
+    dt = reduce_max(time.perf_counter() - t0)
+    parallel.enable(False)
+    rel = abs(s_sharded - s_single) / abs(s_single)
+    assert rel < 1e-12, ("sharded slogl differs from the single-GPU one", s_sharded, s_single)
+    return {"value": 2.0 * args.n_train * args.n_test * n / dt, "unit": UNIT, "ms_per_step": 1e3 * dt / n, "steps": n,
+            "n_gpus": world, "workload": "one %d x %d CKDE slogl sharded by pybnesian_b200.parallel" % (args.n_train, args.n_test),
+            "slogl_sharded": s_sharded, "slogl_single_gpu": s_single, "rel_diff": rel,
+            "timer": "host wall clock around the blocking API calls, max over ranks"}
+
+
+def hc_leg(world):
+    """Second half of BASELINE.json's metric: HC-CV seconds per iteration on configs[3] (20 nodes, 100k rows, k=10,
+    max_indegree 4); with N ranks the (candidate, fold) jobs are dealt over the GPUs by pybnesian_b200.parallel."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import hashlib
+    import hc_bench
+    from pybnesian_b200 import parallel
+    parallel.enable(world > 1)
+    try:
+        r = hc_bench.run(100_000, 20, 0, 4)
+    finally:
+        parallel.enable(False)
+    ops = r.pop("operators")
+    keep = ("rows", "nodes", "k", "max_indegree", "iterations", "hc_cv_s_per_iter_mean", "hc_cv_s_per_iter_max",
+            "cache_scores_s", "cv_create_s", "kernel_warmup_s", "total_s", "pair_evals_per_s_in_kernel", "gpu_launches",
+            "final_arcs", "ckde_nodes", "final_score")
+    out = {k: r.get(k) for k in keep}
+    out["n_gpus"] = world
+    out["operators_sha1"] = hashlib.sha1("\n".join(ops).encode()).hexdigest()   # same sequence at every N
+    out["first_operators"] = ops[:3]
+    return out
 
 
 if __name__ == "__main__":

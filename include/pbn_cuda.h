@@ -84,7 +84,6 @@ int pbn_ctx_pair_kernel_time(pbn_ctx* ctx, double* total_ms, int64_t* n_launches
  * the table stays resident until freed. */
 int pbn_table_upload(pbn_ctx* ctx, const void* const* col_ptrs, int ncols, int64_t nrows, int dtype,
                      pbn_table** out);
-/* Same, from pageable or pinned host memory already laid out column-major (one block). */
 int pbn_table_free(pbn_table* tbl);
 int64_t pbn_table_rows(const pbn_table* tbl);
 int pbn_table_cols(const pbn_table* tbl);

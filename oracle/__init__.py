@@ -69,6 +69,46 @@ def num_threads():
     return lib().orc_num_threads()
 
 
+def use_all_threads():
+    """All host threads for the OpenMP loops of the oracle (torchrun sets OMP_NUM_THREADS=1 for its workers, which
+    made the round-1 reference arm single-threaded at N >= 2).  Returns the thread count now in use."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    for L in (lib(), _fast_lib):
+        if L is not None:
+            L.orc_set_num_threads(_c_int(n))
+    return num_threads()
+
+
+# Timing build of the same source: -O3 -march=native (SURVEY.md 8d / BASELINE.md 3), compiled ON the machine that
+# runs it (a -march=native object must not travel between hosts) into oracle/_fast/ (git- and gpurun-ignored).
+# The parity build above stays -O2 -ffp-contract=off: it is the one pinned bit for bit to the reference kernels.
+_fast_lib = None
+
+
+def fast_lib():
+    global _fast_lib
+    if _fast_lib is None:
+        import hashlib
+        tag = "generic"
+        try:
+            with open("/proc/cpuinfo") as f:
+                flags = [ln for ln in f if ln.startswith("flags") or ln.startswith("model name")][:2]
+            tag = hashlib.sha1("".join(flags).encode()).hexdigest()[:12]
+        except OSError:
+            pass
+        out_dir = os.path.join(_HERE, "_fast")
+        path = os.path.join(out_dir, "liboracle_fast_%s.so" % tag)
+        src = os.path.join(_HERE, "pbn_oracle.cpp")
+        if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+            os.makedirs(out_dir, exist_ok=True)
+            cxx = "/usr/bin/g++" if os.access("/usr/bin/g++", os.X_OK) else "g++"
+            subprocess.check_call([cxx, "-O3", "-march=native", "-std=c++17", "-fPIC", "-fopenmp", "-w", "-shared",
+                                   "-o", path, src])
+        _fast_lib = ctypes.CDLL(path)
+        _fast_lib.orc_num_threads.restype = _c_int
+    return _fast_lib
+
+
 def cov(X):
     X = _fmat(X)
     n, d = X.shape
@@ -122,9 +162,10 @@ def kde_logl(train, test, H):
     return _logl_call(lib().orc_kde_logl, train, test, H)
 
 
-def ckde_logl(train, test, Hjoint):
-    """(logl[m], slogl) of CKDE(col 0 | cols 1..): joint - marginal with H[1:,1:]."""
-    return _logl_call(lib().orc_ckde_logl, train, test, Hjoint)
+def ckde_logl(train, test, Hjoint, fast=False):
+    """(logl[m], slogl) of CKDE(col 0 | cols 1..): joint - marginal with H[1:,1:].  `fast` runs the -O3 -march=native
+    timing build (bench.py's CPU arms); parity checks use the default build."""
+    return _logl_call((fast_lib() if fast else lib()).orc_ckde_logl, train, test, Hjoint)
 
 
 def kde_logl_ld(train, test, H):

@@ -898,6 +898,15 @@ int orc_num_threads() {
 #endif
 }
 
+// torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU-baseline legs of bench.py ask for all host threads back
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_cov(const void* X, int64_t n, int d, int dtype, double* cov_out) {
     if (dtype == 0) {
         std::vector<double> c;

@@ -75,13 +75,14 @@ struct GramParams {
     const int64_t* limits;  // device, k + 1
     const double* centre;   // device, C
     double* partial;
+    int pair0;              // first tile pair of this launch (the host loops over chunks of pairs)
 };
 
 template <typename T>
 __global__ void fold_gram_kernel(GramParams P) {
     __shared__ double sh[32];
     // decode the tile pair
-    int pair = blockIdx.y, ta = 0;
+    int pair = P.pair0 + blockIdx.y, ta = 0;
     while (pair >= P.ntiles - ta) { pair -= P.ntiles - ta; ++ta; }
     int tb = ta + pair;
     const int fold = blockIdx.z;
@@ -473,7 +474,10 @@ int pbn_cv_create(pbn_ctx* ctx, const pbn_table* tbl, const int32_t* indices, in
         int64_t* d_lim = nullptr;
         double* d_centre = nullptr;
         double* d_part = nullptr;
-        size_t np = (size_t)k * npairs * fb * 24;
+        // tile pairs are processed in chunks: grid.y stays far below the 65535 launch limit and the partial buffer
+        // (device and host) is bounded however many columns the frame has
+        const int chunk = std::min(npairs, 2048);
+        size_t np = (size_t)k * chunk * fb * 24;
         CV_TRY(cudaMallocAsync(&d_lim, (k + 1) * sizeof(int64_t), st));
         CV_TRY(cudaMallocAsync(&d_centre, C * sizeof(double), st));
         CV_TRY(cudaMallocAsync(&d_part, np * sizeof(double), st));
@@ -487,15 +491,28 @@ int pbn_cv_create(pbn_ctx* ctx, const pbn_table* tbl, const int32_t* indices, in
         P.limits = d_lim;
         P.centre = d_centre;
         P.partial = d_part;
-        dim3 grid(fb, npairs, k);
-        if (f64) fold_gram_kernel<double><<<grid, 256, 0, st>>>(P);
-        else fold_gram_kernel<float><<<grid, 256, 0, st>>>(P);
-        ctx->launches++;
-        CV_TRY(cudaGetLastError());
         std::vector<double> h(np);
-        CV_TRY(cudaMemcpyAsync(h.data(), d_part, np * sizeof(double), cudaMemcpyDeviceToHost, st));
-        CV_TRY(cudaStreamSynchronize(st));
-        ctx->d2h += (int64_t)np * 8;
+        std::vector<double> hsum((size_t)k * npairs * 24);  // block partials added in block order
+        for (int pair0 = 0; pair0 < npairs; pair0 += chunk) {
+            const int np_here = std::min(chunk, npairs - pair0);
+            P.pair0 = pair0;
+            dim3 grid(fb, np_here, k);
+            if (f64) fold_gram_kernel<double><<<grid, 256, 0, st>>>(P);
+            else fold_gram_kernel<float><<<grid, 256, 0, st>>>(P);
+            ctx->launches++;
+            CV_TRY(cudaGetLastError());
+            const size_t cnt = (size_t)k * np_here * fb * 24;
+            CV_TRY(cudaMemcpyAsync(h.data(), d_part, cnt * sizeof(double), cudaMemcpyDeviceToHost, st));
+            CV_TRY(cudaStreamSynchronize(st));
+            ctx->d2h += (int64_t)cnt * 8;
+            for (int f = 0; f < k; ++f)
+                for (int pl = 0; pl < np_here; ++pl)
+                    for (int q = 0; q < 24; ++q) {
+                        double s = 0;
+                        for (int b = 0; b < fb; ++b) s += h[(((size_t)f * np_here + pl) * fb + b) * 24 + q];
+                        hsum[((size_t)f * npairs + pair0 + pl) * 24 + q] = s;
+                    }
+        }
         CV_TRY(cudaFreeAsync(d_lim, st));
         CV_TRY(cudaFreeAsync(d_centre, st));
         CV_TRY(cudaFreeAsync(d_part, st));
@@ -506,11 +523,7 @@ int pbn_cv_create(pbn_ctx* ctx, const pbn_table* tbl, const int32_t* indices, in
             for (int ta = 0; ta < ntiles; ++ta)
                 for (int tb = ta; tb < ntiles; ++tb, ++pair) {
                     double acc[24];
-                    for (int q = 0; q < 24; ++q) {
-                        double s = 0;
-                        for (int b = 0; b < fb; ++b) s += h[(((size_t)f * npairs + pair) * fb + b) * 24 + q];
-                        acc[q] = s;
-                    }
+                    for (int q = 0; q < 24; ++q) acc[q] = hsum[((size_t)f * npairs + pair) * 24 + q];
                     for (int a = 0; a < 4; ++a)
                         for (int b = 0; b < 4; ++b) {
                             int ca = ta * 4 + a, cb = tb * 4 + b;

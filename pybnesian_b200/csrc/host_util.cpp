@@ -26,7 +26,10 @@ extern "C" {
 // CrossValidationProperties (dataset/crossvalidation_adaptator.hpp:15-67)
 int pbn_cv_split(int32_t* indices, int64_t n, int k, uint32_t seed, int32_t* limits) {
     if (!indices || !limits) return pbn_set_error(PBN_ERR_ARG, "null argument");
-    if (k <= 1 || k > n)
+    // the reference checks k against df->num_rows() (all rows, nulls included) before the null rows are dropped
+    // (crossvalidation_adaptator.hpp:24-29), so k may exceed the number of VALID rows passed here and the trailing
+    // folds are then empty; that check is the caller's (dataset.py), only k <= 1 is rejected here
+    if (k <= 1 || n < 0)
         return pbn_set_error(PBN_ERR_ARG, "Cannot split " + std::to_string(n) + " instances into " + std::to_string(k) +
                                               " folds.");
     std::vector<int> v(indices, indices + n);

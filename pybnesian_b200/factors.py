@@ -407,12 +407,13 @@ class CKDE(Factor):
         # all-reduce (each element written by exactly one rank), as _run_logl does
         b, e = parallel.shard_range(m) if parallel.active() else (0, m)
         out = np.zeros(m)
-        if e > b:
-            shard = out[b:e]
-            check(lib().pbn_ckde_cdf(tbl.ctx.handle, self._handle.handle, tbl.handle, int_array(cols), tbl.rows(b, e),
-                                     shard.ctypes.data_as(ctypes.POINTER(ctypes.c_double))))
+        with parallel.guard() as g:
+            if e > b:
+                shard = out[b:e]
+                check(lib().pbn_ckde_cdf(tbl.ctx.handle, self._handle.handle, tbl.handle, int_array(cols), tbl.rows(b, e),
+                                         shard.ctypes.data_as(ctypes.POINTER(ctypes.c_double))))
         if parallel.active():
-            out = parallel.all_reduce_sum(out, tbl.ctx)
+            out = parallel.all_reduce_sum(out, tbl.ctx, error=g.error)
         if mask is not None:
             full = np.full(frame.num_rows, np.nan)
             full[mask] = out

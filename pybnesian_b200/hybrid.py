@@ -674,10 +674,13 @@ class HCKDE(DiscreteAdaptator):
         dp = ctypes.POINTER(ctypes.c_double)
         vals = np.empty(total) if want_logl else None
         sums = np.zeros(F)
-        check(lib().pbn_kde_logl_multi(grouped.tbl.ctx.handle, handles, F, grouped.tbl.handle, int_array(grouped.cols), rows,
-                                       vals.ctypes.data_as(dp) if want_logl else None,
-                                       None if want_logl else sums.ctypes.data_as(dp)))
+        with parallel.guard() as g:
+            check(lib().pbn_kde_logl_multi(grouped.tbl.ctx.handle, handles, F, grouped.tbl.handle, int_array(grouped.cols), rows,
+                                           vals.ctypes.data_as(dp) if want_logl else None,
+                                           None if want_logl else sums.ctypes.data_as(dp)))
         if parallel.active():
+            if g.error is not None:
+                parallel.all_reduce_sum(np.zeros(1), grouped.tbl.ctx, error=g.error)
             if want_logl:
                 full = np.zeros(grouped.tbl.nrows)
                 pos = 0

@@ -136,9 +136,10 @@ class UCVScorer:
         if parallel.active():
             # each rank sums its slice of the pair-tile schedule; 2 doubles are all-reduced
             s2, s1 = ctypes.c_double(), ctypes.c_double()
-            check(lib().pbn_ucv_pair_sums(self._handle, _dp(H), is_diag, parallel.rank(), parallel.world_size(),
-                                          ctypes.byref(s2), ctypes.byref(s1)))
-            tot = parallel.all_reduce_sum(np.array([s2.value, s1.value]), self._tbl.ctx)
+            with parallel.guard() as g:
+                check(lib().pbn_ucv_pair_sums(self._handle, _dp(H), is_diag, parallel.rank(), parallel.world_size(),
+                                              ctypes.byref(s2), ctypes.byref(s1)))
+            tot = parallel.all_reduce_sum(np.array([s2.value, s1.value]), self._tbl.ctx, error=g.error)
             check(lib().pbn_ucv_score_from_sums(self._handle, _dp(H), is_diag, float(tot[0]), float(tot[1]), ctypes.byref(out)))
         else:
             check(lib().pbn_ucv_score(self._handle, _dp(H), is_diag, ctypes.byref(out)))
@@ -240,16 +241,17 @@ def _run_logl(fitted, frame, variables, want_logl, want_slogl):
     b, e = parallel.shard_range(m) if parallel.active() else (0, m)
     out = np.zeros(m) if want_logl else None
     s = ctypes.c_double(0.0)
-    if e > b or not parallel.active():
-        shard = out[b:e] if want_logl else None
-        check(lib().pbn_kde_logl(tbl.ctx.handle, fitted.handle, tbl.handle, int_array(cols), tbl.rows(b, e),
-                                 _dp(shard) if want_logl else None, ctypes.byref(s) if want_slogl else None))
+    with parallel.guard() as g:  # a failing rank still enters the collective; every rank raises after it
+        if e > b or not parallel.active():
+            shard = out[b:e] if want_logl else None
+            check(lib().pbn_kde_logl(tbl.ctx.handle, fitted.handle, tbl.handle, int_array(cols), tbl.rows(b, e),
+                                     _dp(shard) if want_logl else None, ctypes.byref(s) if want_slogl else None))
     total = s.value
     if parallel.active():
         if want_slogl:
-            total = float(parallel.all_reduce_sum(np.array([s.value]), tbl.ctx)[0])
+            total = float(parallel.all_reduce_sum(np.array([s.value]), tbl.ctx, error=g.error)[0])
         if want_logl:
-            out = parallel.all_reduce_sum(out, tbl.ctx)
+            out = parallel.all_reduce_sum(out, tbl.ctx, error=g.error)
     if want_logl and mask is not None:
         full = np.full(frame.num_rows, np.nan)
         full[mask] = out

@@ -49,22 +49,77 @@ def local_device():
     return int(os.environ.get("PBN_CUDA_DEVICE", os.environ.get("LOCAL_RANK", "0")))
 
 
-def all_reduce_sum(values, ctx=None):
-    """Element-wise sum over ranks of a float64 numpy vector (returned as a new array)."""
+class guard:
+    """Collects an exception raised by this rank's share of a sharded call so that the rank still enters the
+    collective that follows; `all_reduce_sum(..., error=g.error)` then raises on EVERY rank (the reference raises
+    cleanly from its single process; a rank that raised before the collective would leave the others waiting for
+    the NCCL timeout).
+
+        with parallel.guard() as g:
+            ... local work that may raise ...
+        total = parallel.all_reduce_sum(values, ctx, error=g.error)
+    """
+
+    def __init__(self):
+        self.error = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, exc_type, exc, tb):
+        if exc is not None and isinstance(exc, Exception) and active():
+            self.error = exc
+            return True  # swallowed here, re-raised on every rank after the collective
+        return False
+
+
+_ERR_BYTES = 1024
+
+
+def _raise_everywhere(error, dist, dev):
+    """Called on every rank once the reduced error flag is non-zero: the lowest failing rank broadcasts
+    (exception class name, message); every rank raises that exception (its own object on the source rank)."""
+    import torch
+    w, r = dist.get_world_size(_group), dist.get_rank(_group)
+    src = torch.tensor([r if error is not None else w], dtype=torch.int64, device=dev)
+    dist.all_reduce(src, op=dist.ReduceOp.MIN, group=_group)
+    src = int(src.item())
+    buf = torch.zeros(_ERR_BYTES, dtype=torch.uint8, device=dev)
+    if r == src:
+        raw = (type(error).__name__ + "\n" + str(error)).encode("utf-8", "replace")[:_ERR_BYTES]
+        buf[: len(raw)] = torch.tensor(list(raw), dtype=torch.uint8, device=dev)
+    dist.broadcast(buf, src=dist.get_global_rank(_group, src) if _group is not None else src, group=_group)
+    if r == src:
+        raise error
+    name, _, msg = bytes(buf.cpu().tolist()).rstrip(b"\0").decode("utf-8", "replace").partition("\n")
+    from ._lib import SingularCovarianceData
+    cls = {"SingularCovarianceData": SingularCovarianceData, "ValueError": ValueError, "TypeError": TypeError,
+           "IndexError": IndexError, "KeyError": KeyError}.get(name, RuntimeError)
+    raise cls(msg + " [raised on rank %d]" % src)
+
+
+def all_reduce_sum(values, ctx=None, error=None):
+    """Element-wise sum over ranks of a float64 numpy vector (returned as a new array).  `error` is the exception this
+    rank caught while producing `values` (see `guard`), or None; a flag travels with the vector and, if any rank
+    failed, every rank raises after the collective."""
     values = np.ascontiguousarray(values, dtype=np.float64)
     if not active():
+        if error is not None:
+            raise error
         return values
     import torch
     dist = _dist()
     backend = dist.get_backend(_group)
-    t = torch.from_numpy(values.copy())
+    t = torch.from_numpy(np.append(values.ravel(), 1.0 if error is not None else 0.0))
+    dev = torch.device("cpu")
     if backend == "nccl":
         dev = torch.device("cuda", ctx.device if ctx is not None else local_device())
         t = t.to(dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=_group)
-        return t.cpu().numpy()
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=_group)
-    return t.numpy()
+    t = t.cpu().numpy()
+    if t[-1] != 0.0:
+        _raise_everywhere(error, dist, dev)
+    return t[:-1].reshape(values.shape)
 
 
 def deal(costs, r=None, w=None):

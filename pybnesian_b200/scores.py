@@ -262,12 +262,13 @@ class _FoldScorer:
         cost = [len(v) if f == _lib.FACTOR_CKDE else 0 for _, f, _, v in items]
         mine = parallel.deal(cost, rank, world) if world > 1 else list(range(len(items)))
         scores = np.zeros(len(items))
-        if mine:
-            scores[mine] = self._run_items(code, [items[i] for i in mine])
-            self.stats["device_items"] += len(mine)
-            self.stats["batches"] += 1
+        with parallel.guard() as g:  # e.g. SingularCovarianceData of an item only this rank was dealt
+            if mine:
+                scores[mine] = self._run_items(code, [items[i] for i in mine])
+                self.stats["device_items"] += len(mine)
+                self.stats["batches"] += 1
         if world > 1:
-            scores = parallel.all_reduce_sum(scores, self._ctx(code))
+            scores = parallel.all_reduce_sum(scores, self._ctx(code), error=g.error)
         return {items[i][0]: float(scores[i]) for i in range(len(items))}
 
     def _score_native_by_fold(self, code, items, rank, world):
@@ -283,13 +284,14 @@ class _FoldScorer:
         for job in mine:
             per_fold.setdefault(job % nfolds, []).append(job // nfolds)
         mat = np.zeros((len(items), nfolds))
-        for q in sorted(per_fold):
-            idx = per_fold[q]
-            f0 = self.fold_begin + q
-            mat[idx, q] = self._run_items(code, [items[i] for i in idx], f0, f0 + 1)
-            self.stats["device_items"] += len(idx)
-            self.stats["batches"] += 1
-        mat = parallel.all_reduce_sum(mat.ravel(), self._ctx(code)).reshape(len(items), nfolds)
+        with parallel.guard() as g:
+            for q in sorted(per_fold):
+                idx = per_fold[q]
+                f0 = self.fold_begin + q
+                mat[idx, q] = self._run_items(code, [items[i] for i in idx], f0, f0 + 1)
+                self.stats["device_items"] += len(idx)
+                self.stats["batches"] += 1
+        mat = parallel.all_reduce_sum(mat.ravel(), self._ctx(code), error=g.error).reshape(len(items), nfolds)
         out = {}
         for i in range(len(items)):
             total = 0.0

@@ -1,0 +1,160 @@
+"""Parity at the sizes BASELINE.json's configs 3, 4 and 5 are stated for ("untested configs"):
+
+* config 3 - the UCV objective at N = 50 000 (inside the reference's uint32-safe range) against the
+  oracle, and at N = 200 000 (2e10 pairs, the 64-bit tile prefix of ucv_kernel.cu) through an identity that a second,
+  independent kernel evaluates:  sum_{i<j} e^{-s_ij/2} = (sum_t sum_i e^{-s_ti/2} - N) / 2,  the double sum being what
+  KDE.logl computes on the training rows themselves (same bandwidth for e^{-s/2}, bandwidth 2H for e^{-s/4});
+* config 5 - i.i.d. N(0, I_d), 1M x 1M, d in {1, 4, 8}, float64 AND float32: a 512-row sub-sample against the oracle
+  plus additivity over test shards and over a partition of the training rows;
+* config 4 - (CKDE family, fold) scores on the 100 000-row, 20-column hill-climbing data against the oracle's
+  fit + slogl of that one fold.
+
+Reference: kde/UCV.cpp:296-358, kde/KDE.hpp:592-640, learning/scores/cv_likelihood.cpp:11-25.
+Tolerances: float64 1e-10 relative, float32 1e-4 relative (BASELINE.json north_star), stated per assertion.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import oracle
+import util_data
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+VARS = ["a", "b", "c", "d"]
+
+
+@pytest.fixture(scope="module")
+def pbn():
+    import pybnesian_b200 as pbn
+    oracle.use_all_threads()
+    return pbn
+
+
+# ---- config 3 ------------------------------------------------------------------------------------------------------
+def test_ucv_objective_50k_against_oracle(pbn):
+    n = 50_000
+    df = util_data.generate_normal_data(n, 0)
+    X = df[VARS].to_numpy()
+    H = oracle.bandwidth(X)
+    sc = pbn.UCVScorer(df, VARS)
+    assert sc.num_pairs() == n * (n - 1) // 2
+    want = oracle.ucv_score_unconstrained(X, H)
+    got = sc.score_unconstrained(H)
+    assert abs(got - want) <= 1e-10 * abs(want), (got, want)
+    hd = 0.5 * np.diag(H)
+    want = oracle.ucv_score_diagonal(X, hd)
+    got = sc.score_diagonal(hd)
+    assert abs(got - want) <= 1e-10 * abs(want), (got, want)
+
+
+def _double_sum_from_logl(pbn, df, variables, H):
+    """sum_t sum_i exp(-s_ti / 2) over all ordered pairs of the rows of df (i = t included), from KDE.logl."""
+    k = pbn.KDE(variables)
+    k.fit(df)
+    k.bandwidth = H
+    logl = k.logl(df)
+    return float(np.exp(logl - k.lognorm_const()).sum())
+
+
+@pytest.mark.parametrize("n,variables", [(200_000, VARS), (120_001, ["c", "a"])])
+def test_ucv_pair_sums_200k_two_kernels_agree(pbn, n, variables):
+    """N > 92 682 is where the reference's uint32 pair offsets overflow and where this library switches to a 64-bit tile
+    prefix; the oracle needs minutes there, so the UCV kernel is checked against the logl pair kernel."""
+    df = util_data.generate_normal_data(n, 0)
+    frame = pbn.DataFrame(df)
+    H = np.asarray(pbn.NormalReferenceRule().bandwidth(frame, variables))
+    sc = pbn.UCVScorer(frame, variables)
+    assert sc.num_pairs() == n * (n - 1) // 2 and sc.num_pairs() > 2 ** 32
+    s_quarter, s_half = sc.pair_sums(H)
+    want_half = (_double_sum_from_logl(pbn, frame, variables, H) - n) / 2.0
+    want_quarter = (_double_sum_from_logl(pbn, frame, variables, 2.0 * H) - n) / 2.0
+    assert abs(s_half - want_half) <= 1e-10 * want_half, (s_half, want_half)
+    assert abs(s_quarter - want_quarter) <= 1e-10 * want_quarter, (s_quarter, want_quarter)
+    # and the objective assembled from those sums is the score the selector minimises
+    d = len(variables)
+    L = np.linalg.cholesky(H)
+    c1 = -np.log(np.diag(L)).sum() - 0.5 * d * np.log(2 * np.pi)
+    c2 = c1 - 0.5 * d * np.log(2.0)
+    want = np.exp(c2) + (2.0 / n) * np.exp(c2) * want_quarter - (4.0 / (n - 1)) * np.exp(c1) * want_half
+    got = sc.score_unconstrained(H)
+    assert abs(got - want) <= 1e-9 * abs(want), (got, want)   # the three terms cancel to ~1/10 of their size
+
+
+# ---- config 5 ------------------------------------------------------------------------------------------------------
+N5 = 1_000_000
+
+
+@pytest.mark.parametrize("dtype,tol", [("float64", 1e-10), ("float32", 1e-4)])
+@pytest.mark.parametrize("d", [1, 4, 8])
+def test_config5_iid_1m_subsample_and_additivity(pbn, d, dtype, tol):
+    train = util_data.iid_normal(N5, d, 0, dtype)
+    test = util_data.iid_normal(N5, d, 1, dtype)
+    cols = list(train.columns)
+    ftrain, ftest = pbn.DataFrame(train), pbn.DataFrame(test)
+    k = pbn.KDE(cols)
+    k.fit(ftrain)
+    logl = k.logl(ftest)
+    assert np.all(np.isfinite(logl))
+    X = train.to_numpy()
+    H = oracle.bandwidth(X)
+    assert np.allclose(k.bandwidth, H, rtol=1e-11 if dtype == "float64" else 2e-5, atol=0)
+    rows = np.random.default_rng(d).choice(N5, 512, replace=False)
+    # the extreme rows of the test set are where unshifted float sums are smallest: always part of the sample
+    r2 = (test.to_numpy().astype(np.float64) ** 2).sum(axis=1)
+    rows[:8] = np.argsort(r2)[-8:]
+    want, _ = oracle.kde_logl(X, test.to_numpy()[rows], k.bandwidth)
+    rel = np.abs(logl[rows] - want) / np.abs(want)
+    assert rel.max() < tol, (d, dtype, rel.max(), rows[np.argmax(rel)])
+    # slogl = sum of logl, and additive over test shards (size-independent)
+    total = k.slogl(ftest)
+    assert abs(total - logl.sum()) <= 1e-12 * abs(total)
+    cut = 333_337
+    parts = k.slogl(pbn.DataFrame(test.iloc[:cut])) + k.slogl(pbn.DataFrame(test.iloc[cut:]))
+    assert abs(total - parts) <= 1e-12 * abs(total)
+    # the kernel sum is additive over a partition of the training rows
+    sub = pbn.DataFrame(test.iloc[:50_000])
+    full = logl[:50_000]
+    cut = 400_003
+    pieces = []
+    for chunk in (train.iloc[:cut], train.iloc[cut:]):
+        kk = pbn.KDE(cols)
+        kk.fit(pbn.DataFrame(chunk))
+        kk.bandwidth = k.bandwidth
+        pieces.append(kk.logl(sub) + np.log(len(chunk)))
+    combined = np.logaddexp(pieces[0], pieces[1]) - np.log(N5)
+    # float32: every per-tile float partial sum rounds at 2^-24 relative; the two splits round differently
+    assert np.max(np.abs(combined - full) / np.abs(full)) < (1e-10 if dtype == "float64" else 2e-6)
+
+
+# ---- config 4 ------------------------------------------------------------------------------------------------------
+def test_config4_100k_fold_scores_against_oracle(pbn):
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import hc_bench
+    from pybnesian_b200 import _lib
+    data, _ = hc_bench.config4_data(100_000, 20, 0)
+    score = pbn.CVLikelihood(data, 10, 0)
+    idx, lim = oracle.cv_indices(np.arange(len(data)), 10, 0)
+    assert np.array_equal(score._scorer.indices, idx) and np.array_equal(score._scorer.limits, lim)
+    cases = [(["x3", "x1"], 0), (["x5", "x2", "x4"], 4), (["x7", "x0", "x3", "x6"], 9), (["x12"], 5),
+             (["x19", "x4", "x11", "x15", "x17"], 2)]
+    for variables, f in cases:
+        items = [(None, _lib.FACTOR_CKDE, _lib.BW_NORMAL_REFERENCE, variables)]
+        got = float(score._scorer._run_items(_lib.PBN_F64, items, f, f + 1)[0])
+        X = data[variables].to_numpy()
+        te = X[idx[lim[f]:lim[f + 1]]]
+        tr = X[np.concatenate([idx[:lim[f]], idx[lim[f + 1]:]])]
+        H = oracle.bandwidth(tr)
+        _, want = (oracle.ckde_logl if len(variables) > 1 else oracle.kde_logl)(tr, te, H)
+        assert abs(got - want) <= 1e-10 * abs(want), (variables, f, got, want)
+    # a whole local score is the in-order sum of its fold scores
+    variables = ["x5", "x2", "x4"]
+    items = [(None, _lib.FACTOR_CKDE, _lib.BW_NORMAL_REFERENCE, variables)]
+    folds = [float(score._scorer._run_items(_lib.PBN_F64, items, f, f + 1)[0]) for f in range(10)]
+    total = 0.0
+    for v in folds:
+        total += v
+    got = score.local_score_node_type(pbn.SemiparametricBN(list(data.columns)), pbn.CKDEType(), "x5", ["x2", "x4"])
+    assert abs(got - total) <= 1e-13 * abs(total)

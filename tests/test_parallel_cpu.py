@@ -85,6 +85,29 @@ assert all(fe - fb == 1 for fb, fe, _ in FoldScorer.calls) and len(FoldScorer.ca
 jobs = sum(n for _, _, n in FoldScorer.calls)
 tot = parallel.all_reduce_sum(np.array([jobs if rank == 0 else 0.0, jobs if rank == 1 else 0.0]))
 assert tot.sum() == 5 * len(reqs) and abs(tot[0] - tot[1]) <= 1, tot
+# 3c. a failure on ONE rank (an item only it was dealt) raises on EVERY rank after the collective - no rank is left
+# waiting in the all-reduce (ADVICE round 1: the reference raises cleanly from its single process)
+class FailingScorer(FoldScorer):
+    def _run_items(self, code, items, fold_begin=None, fold_end=None):
+        if rank == 1:
+            raise _lib.SingularCovarianceData("Covariance matrix for variables [a, b] is not positive-definite.")
+        return super()._run_items(code, items, fold_begin, fold_end)
+
+bad = FailingScorer(pbn.DataFrame(data), idx, lim, 0, 5, pbn.Arguments())
+try:
+    bad.score_batch(model, reqs)
+    raise AssertionError("no exception on rank %d" % rank)
+except _lib.SingularCovarianceData as ex:
+    assert "not positive-definite" in str(ex), str(ex)
+with parallel.guard() as g:
+    if rank == 0:
+        raise ValueError("boom")
+try:
+    parallel.all_reduce_sum(np.zeros(3), error=g.error)
+    raise AssertionError("no exception on rank %d" % rank)
+except ValueError as ex:
+    assert "boom" in str(ex)
+assert parallel.all_reduce_sum(np.ones(2)).tolist() == [2.0, 2.0]   # the group is still usable afterwards
 # 4. hill climbing on top of the sharded engine makes the same decisions on every rank
 class ShardedScore(pbn.CVLikelihood):
     pass
