@@ -137,8 +137,13 @@ int pbn_kde_logl(pbn_ctx* ctx, const pbn_kde* kde, const pbn_table* test, const 
 int pbn_kde_logl_device(pbn_ctx* ctx, const pbn_kde* kde, const pbn_table* test, const int* cols, pbn_rows rows,
                         double* d_out_logl, double* d_out_slogl);
 /* Number of test rows of the last logl call on this context that needed the shifted
- * (max-subtracted) re-evaluation because their unshifted kernel sum underflowed. */
+ * (max-subtracted) re-evaluation because their unshifted kernel sum underflowed: a second,
+ * device-scheduled pass of the tiled pair kernel with a per-row exponent shift - what
+ * OpenCLConfig::logsumexp_cols_offset (opencl/opencl_config.hpp:517-536) does for every row. */
 int pbn_ctx_last_fallback_rows(pbn_ctx* ctx, int64_t* out);
+/* ... and how many of those the shifted pass could not evaluate either (farther than 2^31
+ * kernel units from every training row, non-finite coordinates): one CTA per row. */
+int pbn_ctx_last_row_kernel_rows(pbn_ctx* ctx, int64_t* out);
 
 /* kde::UCVScorer (kde/UCV.hpp:12-45): constructed once per (data, variables); every score call
  * evaluates all N(N-1)/2 pairs in ONE launch (64-bit pair indexing; the reference's 32-bit chunk

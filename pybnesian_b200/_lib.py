@@ -20,7 +20,7 @@ EXPORTS = [
     "pbn_ctx_stream", "pbn_ctx_synchronize", "pbn_ctx_sm_count", "pbn_ctx_counters", "pbn_table_upload",
     "pbn_table_free", "pbn_table_rows", "pbn_table_cols", "pbn_table_download", "pbn_table_moments", "pbn_bandwidth",
     "pbn_diag_bandwidth", "pbn_kde_fit", "pbn_ckde_fit", "pbn_product_kde_fit", "pbn_kde_free", "pbn_kde_num_instances", "pbn_kde_lognorm",
-    "pbn_kde_logl", "pbn_kde_logl_device", "pbn_ctx_last_fallback_rows", "pbn_device_alloc", "pbn_device_free",
+    "pbn_kde_logl", "pbn_kde_logl_device", "pbn_ctx_last_fallback_rows", "pbn_ctx_last_row_kernel_rows", "pbn_device_alloc", "pbn_device_free",
     "pbn_device_read", "pbn_ctx_set_timing", "pbn_ctx_pair_kernel_time", "pbn_ucv_create", "pbn_ucv_free",
     "pbn_ucv_score", "pbn_ucv_pair_sums", "pbn_ucv_pairs", "pbn_ucv_bandwidth",
     "pbn_ucv_score_from_sums", "pbn_lg_fit", "pbn_lg_logl", "pbn_cv_split", "pbn_holdout_split", "pbn_cv_create", "pbn_cv_free", "pbn_cv_table",
@@ -100,6 +100,7 @@ def lib():
         L.pbn_kde_logl.argtypes = [vp, vp, vp, ip, Rows, dp, dp]
         L.pbn_kde_logl_device.argtypes = [vp, vp, vp, ip, Rows, vp, vp]
         L.pbn_ctx_last_fallback_rows.argtypes = [vp, ctypes.POINTER(i64)]
+        L.pbn_ctx_last_row_kernel_rows.argtypes = [vp, ctypes.POINTER(i64)]
         L.pbn_device_alloc.argtypes = [vp, i64, ctypes.POINTER(vp)]
         L.pbn_device_free.argtypes = [vp, vp]
         L.pbn_device_read.argtypes = [vp, vp, i64, vp]
@@ -207,6 +208,11 @@ class Context:
     def last_fallback_rows(self):
         v = ctypes.c_int64()
         check(lib().pbn_ctx_last_fallback_rows(self.handle, ctypes.byref(v)))
+        return v.value
+
+    def last_row_kernel_rows(self):
+        v = ctypes.c_int64()
+        check(lib().pbn_ctx_last_row_kernel_rows(self.handle, ctypes.byref(v)))
         return v.value
 
 

@@ -3,7 +3,7 @@
 // namespace by each translation unit.
 #pragma once
 
-constexpr int kMaxFast = 8;  // the pair kernel is instantiated for d = 1..8
+constexpr int kMaxFast = pbn::kMaxFastD;  // the pair kernel is instantiated for d = 1..10
 
 __device__ __forceinline__ double block_sum(double v, double* sh) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);

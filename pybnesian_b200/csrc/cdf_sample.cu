@@ -446,7 +446,7 @@ cudaError_t launch_weight_one(const WParams& P, dim3 grid, cudaStream_t st) {
 template <typename T, int MODE>
 cudaError_t launch_weight(const WParams& P, dim3 grid, cudaStream_t st) {
     if constexpr (MODE == 0) {
-        // families of up to 8 variables take the CDF mode of the fused pair kernel (pair_kernel.cuh)
+        // families of up to kMaxFastD (10) variables take the CDF mode of the fused pair kernel (pair_kernel.cuh)
         return launch_weight_one<T, 0, MODE>(P, grid, st);
     } else {
         switch (P.d) {
@@ -614,7 +614,7 @@ int pbn_ckde_cdf(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const in
     const bool f64 = k->dtype == PBN_F64;
     const size_t es = elem_size(k->dtype);
     const double inv_c = 1.0 / sqrt(0.5 * unit_scale(k->dtype));
-    const bool fast = d <= 8;
+    const bool fast = d <= pbn::kMaxFastD;
 
     void* ytest = nullptr;
     size_t ytbytes = ((size_t)m * d * es + 255) / 256 * 256;
@@ -636,7 +636,7 @@ int pbn_ckde_cdf(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const in
     if (fast) {
         // CDF mode of the fused pair kernel: same stream-K schedule and partial-sum slots as pbn_logl_impl
         const int TILE = f64 ? pbn::pair_tile_f64(d) : pbn::pair_tile_f32(d);
-        const int TB = f64 ? pbn::pair_tb_f64() : pbn::pair_tb_f32();  // CDF mode: PairCfg rows for every shape
+        const int TB = f64 ? pbn::pair_tb_cdf_f64(d) : pbn::pair_tb_cdf_f32(d);  // CDF mode: pair_rows_cdf
         int n_test_tiles = (int)((m + TB - 1) / TB);
         int n_train_tiles = (int)((k->n + TILE - 1) / TILE);
         long long U = (long long)n_test_tiles * n_train_tiles;

@@ -199,6 +199,8 @@ cudaError_t launch_whiten_batch(int d, const WhitenJob* jobs, int n_jobs, long l
         case 6: whiten_batch_kernel<T, 6><<<grid, 256, 0, st>>>(jobs, n); break;
         case 7: whiten_batch_kernel<T, 7><<<grid, 256, 0, st>>>(jobs, n); break;
         case 8: whiten_batch_kernel<T, 8><<<grid, 256, 0, st>>>(jobs, n); break;
+        case 9: whiten_batch_kernel<T, 9><<<grid, 256, 0, st>>>(jobs, n); break;
+        case 10: whiten_batch_kernel<T, 10><<<grid, 256, 0, st>>>(jobs, n); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
@@ -610,7 +612,7 @@ int fold_bandwidth(const pbn_cv* cv, int f, const int* vars, int d, int rule, in
     return PBN_OK;
 }
 
-// scores the CKDE items `sel` (all with the same number of variables d <= 8) over folds [f0, f1)
+// scores the CKDE items `sel` (all with the same number of variables d <= kMaxFast) over folds [f0, f1)
 int score_ckde_group(pbn_ctx* ctx, pbn_cv* cv, const pbn_cv_item* items, const std::vector<int>& sel, int d, int f0, int f1,
                      double* scores, int* status, std::string* first_error) {
     cudaStream_t st = ctx->stream;
@@ -876,7 +878,7 @@ extern "C" int pbn_cv_scores(pbn_ctx* ctx, pbn_cv* cv, const pbn_cv_item* items,
     for (int d = 1; d <= kMaxFast; ++d)
         if (!groups[d].empty())
             PBN_TRY(score_ckde_group(ctx, cv, items, groups[d], d, fold_begin, fold_end, scores, stat, &first_error));
-    // wide CKDEs (d > 8): one fit + slogl per fold through the single-model entry points
+    // wide CKDEs (d > kMaxFast = 10): one fit + slogl per fold through the single-model entry points
     for (int i : slow) {
         const pbn_cv_item& it = items[i];
         const int d = it.n_vars;

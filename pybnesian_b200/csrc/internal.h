@@ -44,7 +44,8 @@ struct pbn_ctx {
     int sm_count = 0;
     double* d_exp_tab = nullptr;  // T'[j] = 2^(j/K) with (j << (20 - log2 K)) taken off the high word, j = 0..K-1 (pair_kernel.cuh)
     int64_t launches = 0, h2d = 0, d2h = 0;
-    int64_t last_fallback_rows = 0;
+    int64_t last_fallback_rows = 0;     // rows of the last logl call that took the shifted second pass
+    int64_t last_row_kernel_rows = 0;   // ... of which the per-row kernel had to finish (farther than 2^31 kernel units)
     // optional device timing of the pair kernel (CUDA events on the launching stream)
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;
@@ -70,7 +71,7 @@ struct pbn_kde {
     int64_t n;
     void* y;  // whitened training rows AoS [n_pad][d]
     float* d_bound;  // device scalar: max |whitened training coordinate|
-    double* nrm;     // f64, d <= 8 only (else null): -sum_{c<dn} y_c^2 per training row, dn = d-1 if ckde else d
+    double* nrm;     // f64, d <= kMaxFastD only (else null): -sum_{c<dn} y_c^2 per training row, dn = d-1 if ckde else d
     double W[PBN_MAX_DIM * PBN_MAX_DIM];  // row-major lower-triangular whitening matrix (incl. unit scale)
     double mu[PBN_MAX_DIM];
     int perm[PBN_MAX_DIM];  // internal column k = caller column perm[k]
@@ -141,6 +142,10 @@ cudaError_t launch_pair_f64(int D, bool ckde, const PairJob* jobs, int n_jobs, l
                             int grid, const double* tab, cudaStream_t stream);
 cudaError_t launch_pair_f32(int D, bool ckde, const PairJob* jobs, int n_jobs, long long total_units, long long upb,
                             int grid, const double* tab, cudaStream_t stream);
+cudaError_t launch_pair_shift_f64(int D, bool ckde, const PairJob* job, const long long* dyn, int grid, const double* tab,
+                                  cudaStream_t stream);
+cudaError_t launch_pair_shift_f32(int D, bool ckde, const PairJob* job, const long long* dyn, int grid, const double* tab,
+                                  cudaStream_t stream);
 cudaError_t launch_cdf_f64(int D, const PairJob* jobs, int n_jobs, long long total_units, long long upb, int grid,
                            const double* tab, double inv_c, cudaStream_t stream);
 cudaError_t launch_cdf_f32(int D, const PairJob* jobs, int n_jobs, long long total_units, long long upb, int grid,
@@ -152,4 +157,6 @@ int pair_tb_f32();
 // test rows per tile of pair_kernel<T, D, CKDE> (the rows per thread depend on the kernel shape, pair_rows)
 int pair_tb_for_f64(int D, bool ckde);
 int pair_tb_for_f32(int D, bool ckde);
+int pair_tb_cdf_f64(int D);  // CDF mode of pair_kernel
+int pair_tb_cdf_f32(int D);
 }  // namespace pbn

@@ -29,6 +29,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "normcdf_coeffs.h"
 
 namespace pbn {
@@ -49,9 +51,18 @@ struct PairJob {
     int n_test_tiles;
     int slots;
     int pad_;
+    // shifted second pass only (pair_kernel<..., SHIFT = true>, see runtime.cu: rows whose unshifted sums underflowed):
+    // per test row, the smallest squared distance to a training row in kernel units (joint / marginal coordinates);
+    // every term of that row is evaluated as 2^((t + shift)/K) (f64) or 2^(t + shift) (f32), so its largest term is ~1
+    const float* shift_j;
+    const float* shift_m;
+    const int* test_rows;  // row r of the job is row test_rows[r] of `test`
 };
 
 constexpr int kThreads = 256;
+// the pair kernel (log-likelihood and CDF modes) is instantiated for 1..kMaxFastD variables: north_star's family
+// sizes (d = 1..10); wider families take the generic row kernels
+constexpr int kMaxFastD = 10;
 #ifndef PBN_F64_UNROLL
 #define PBN_F64_UNROLL 4
 #endif
@@ -113,7 +124,12 @@ template <> struct PairCfg<double> { static constexpr int R = PBN_F64_R; static 
 template <> struct PairCfg<float>  { static constexpr int R = PBN_F32_R; static constexpr int TILE = PBN_F32_TILE; static constexpr int MIN_CTAS = PBN_F32_MINCTAS; };
 
 template <typename T> __host__ __device__ constexpr int pair_rows(int D, bool ckde) {
-    return (sizeof(T) == 8 && PBN_F64_R == 3 && !ckde && D <= 5) ? 4 : PairCfg<T>::R;
+    // f64, d = 9, 10: two rows per thread (3 x 10 doubles of test rows + the training point do not fit 128 registers)
+    return (sizeof(T) == 8 && D >= 9) ? 2 : (sizeof(T) == 8 && PBN_F64_R == 3 && !ckde && D <= 5) ? 4 : PairCfg<T>::R;
+}
+// rows per thread of the CDF mode (and of the UCV kernel, which stops at d = 8)
+template <typename T> __host__ __device__ constexpr int pair_rows_cdf(int D) {
+    return (sizeof(T) == 8 && D >= 9) ? 2 : PairCfg<T>::R;
 }
 __host__ __device__ constexpr int pair_unroll_f64(int D, bool ckde) {
     return (PBN_F64_UNROLL == 4 && !ckde && D <= 2) ? 8 : PBN_F64_UNROLL;
@@ -236,7 +252,10 @@ constexpr unsigned kHiLim = 0x80000000u | (static_cast<unsigned>(1023 + 9 + kExp
 // integer part of -|yt|^2 there); unsigned arithmetic, so only the shifted n has to fit 32 bits.
 // `nmin` (a multiple of K, >= kNMin) is the floor of the rounded exponent: terms below 2^(nmin/K) are evaluated AS
 // 2^(nmin/K) and all read table entry 0 (see pair_floor).
-template <bool SAFE>
+// hi word of the double -2^31: with WIDE the SAFE clamp only rejects |t| >= 2^31 (the rounded exponent no longer fits the
+// integer side), because a positive `nshift` brings far smaller t back into range (shifted second pass)
+constexpr unsigned kHiLim31 = 0x80000000u | (static_cast<unsigned>(1023 + 31) << 20);
+template <bool SAFE, bool WIDE = false>
 __device__ __forceinline__ double exp2_tab(double t, const double* __restrict__ tab, double& scaled,
                                            const int nshift = 0, const int nmin = kNMin) {
     const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
@@ -260,7 +279,7 @@ __device__ __forceinline__ double exp2_tab(double t, const double* __restrict__ 
         // hi word of a negative double grows (as unsigned) with its magnitude;
         // kHiLim is the hi word of -(1022 * K)
         unsigned hi = static_cast<unsigned>(__double2hiint(t));
-        n = (hi > kHiLim) ? kNMin : n;
+        n = (hi > (WIDE ? kHiLim31 : kHiLim)) ? kNMin : n;
         n = max(n, nmin);
     } else {
         n = max(n, nmin);
@@ -358,6 +377,83 @@ __device__ __forceinline__ void tile_f64(const double* __restrict__ tp, int cnt,
                 sum_j[r] = fma(st, pj, sum_j[r]);
             }
         }
+    }
+}
+
+// Shifted form of tile_f64 for the second pass over rows whose unshifted sums underflowed (test rows tens of bandwidths
+// away from every training row): the per-row integers sh_j / sh_m (~ the row's smallest squared distance, see
+// rowmin_kernel in runtime.cu) are added to the rounded exponent, so the row's largest term is ~1 and the sums are as
+// accurate as anywhere else.  This is what the reference's max-shifted logsumexp_cols_offset does for every row
+// (opencl/opencl_config.hpp:517-536), at tile speed instead of one CTA per row.
+template <int D, bool CKDE, int R>
+__device__ __forceinline__ void tile_f64_shift(const double* __restrict__ tp, int cnt, const double (&yt)[R][D],
+                                               const int (&sh_j)[R], const int (&sh_m)[R], const double* __restrict__ tab,
+                                               double (&sum_j)[R], double (&sum_m)[R]) {
+    int fl_j[R], fl_m[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        fl_j[r] = pair_floor(sum_j[r]);
+        fl_m[r] = CKDE ? pair_floor(sum_m[r]) : kNMin;
+    }
+#pragma unroll 2
+    for (int i = 0; i < cnt; ++i) {
+        double p[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) p[c] = tp[i * D + c];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            double acc = 0.0;
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+                double dl = yt[r][c] - p[c];
+                acc = fma(-dl, dl, acc);
+                if (CKDE && c == D - 2) {
+                    double st;
+                    double pm = exp2_tab<true, true>(acc, tab, st, sh_m[r], fl_m[r]);
+                    sum_m[r] = fma(st, pm, sum_m[r]);
+                }
+            }
+            double st;
+            double pj = exp2_tab<true, true>(acc, tab, st, sh_j[r], fl_j[r]);
+            sum_j[r] = fma(st, pj, sum_j[r]);
+        }
+    }
+}
+
+template <int D, bool CKDE, int R>
+__device__ __forceinline__ void tile_f32_shift(const float* __restrict__ tp, int cnt, const float (&yt)[R][D],
+                                               const float (&sh_j)[R], const float (&sh_m)[R], double (&sum_j)[R],
+                                               double (&sum_m)[R]) {
+    float facc_j[R], facc_m[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) { facc_j[r] = 0.f; facc_m[r] = 0.f; }
+#pragma unroll 2
+    for (int i = 0; i < cnt; ++i) {
+        float p[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) p[c] = tp[i * D + c];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+                float dl = yt[r][c] - p[c];
+                acc = fmaf(-dl, dl, acc);
+                if (CKDE && c == D - 2) {
+                    float e;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(acc + sh_m[r]));
+                    facc_m[r] += e;
+                }
+            }
+            float e;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(acc + sh_j[r]));
+            facc_j[r] += e;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        sum_j[r] += static_cast<double>(facc_j[r]);
+        if (CKDE) sum_m[r] += static_cast<double>(facc_m[r]);
     }
 }
 
@@ -669,18 +765,24 @@ __device__ __forceinline__ void tile_f32_packed_cdf(const float* __restrict__ tp
 
 // CDF = false: KDE / CKDE log-likelihood sums.  CDF = true: CKDE::cdf sums (see tile_f64); `inv_c` converts a whitened
 // (kernel-unit) coordinate difference into standard-normal units and is only read in that mode.
-template <typename T, int D, bool CKDE, bool CDF = false>
+// SHIFT = true: the shifted second pass (tile_f64_shift / tile_f32_shift) over ONE job whose size is only known on the
+// device: `dyn` = {total_units, upb} written by shift_prep_kernel (runtime.cu) replaces the by-value arguments.
+template <typename T, int D, bool CKDE, bool CDF = false, bool SHIFT = false>
 __global__ void __launch_bounds__(kThreads, PairCfg<T>::MIN_CTAS)
 pair_kernel(const PairJob* __restrict__ jobs, int n_jobs, long long total_units, long long upb,
-            const double* __restrict__ exp_tab_g, double inv_c) {
-    constexpr int R = CDF ? PairCfg<T>::R : pair_rows<T>(D, CKDE);
+            const double* __restrict__ exp_tab_g, double inv_c, const long long* __restrict__ dyn = nullptr) {
+    if (SHIFT) {
+        total_units = dyn[0];
+        upb = dyn[1];
+    }
+    constexpr int R = CDF ? pair_rows_cdf<T>(D) : pair_rows<T>(D, CKDE);
     constexpr int TB = kThreads * R;  // test rows per tile
     constexpr int TILE = pair_tile<T>(D);
     constexpr uint32_t TILE_BYTES = TILE * D * sizeof(T);
     constexpr uint32_t NRM_BYTES = pair_nrm_bytes<T>(D);  // per stage; 0 for f32
     constexpr int DN = CKDE ? D - 1 : D;
     // (the evidence-free CDF kernel, D = 1, has no dot-product form: its only coordinate is the conditioned one)
-    constexpr bool DOT = PBN_F64_DOT && sizeof(T) == 8 && DN >= PBN_F64_DOT_MIN_DN && !(CDF && !CKDE);
+    constexpr bool DOT = !SHIFT && PBN_F64_DOT && sizeof(T) == 8 && DN >= PBN_F64_DOT_MIN_DN && !(CDF && !CKDE);
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T* tile_buf = reinterpret_cast<T*>(smem_raw);  // [kStages][TILE*D]
@@ -739,6 +841,7 @@ pair_kernel(const PairJob* __restrict__ jobs, int n_jobs, long long total_units,
     int ati[R];
     double row_scale[R];
     double sum_j[R], sum_m[R];
+    typename std::conditional<sizeof(T) == 8, int, float>::type shj[SHIFT ? R : 1], shm[SHIFT ? R : 1];
     long long cur_tt = -1;
     int cur_job = -1;
     bool safe = true, dot = false;
@@ -781,12 +884,26 @@ pair_kernel(const PairJob* __restrict__ jobs, int n_jobs, long long total_units,
             for (int r = 0; r < R; ++r) {
                 long long row = tt * TB + r * kThreads + tid;
                 bool ok = row < jb.m;
+                const long long src = (SHIFT && ok) ? static_cast<long long>(jb.test_rows[row]) : row;
 #pragma unroll
-                for (int c = 0; c < D; ++c) yt[r][c] = ok ? tp[row * D + c] : T(0);
+                for (int c = 0; c < D; ++c) yt[r][c] = ok ? tp[src * D + c] : T(0);
                 sum_j[r] = 0.0;
                 sum_m[r] = 0.0;
+                if constexpr (SHIFT) {
+                    // shifts >= 2^31 kernel units cannot be carried on the integer side: such a row keeps a zero sum
+                    // and falls through to the per-row kernel
+                    const float sj = ok ? jb.shift_j[row] : 0.f;
+                    const float sm = (ok && CKDE) ? jb.shift_m[row] : 0.f;
+                    if constexpr (sizeof(T) == 8) {
+                        shj[r] = sj < 2.0e9f ? static_cast<int>(rintf(sj)) : 0;
+                        shm[r] = sm < 2.0e9f ? static_cast<int>(rintf(sm)) : 0;
+                    } else {
+                        shj[r] = sj;
+                        shm[r] = sm;
+                    }
+                }
             }
-            if (sizeof(T) == 8) {
+            if (sizeof(T) == 8 && !SHIFT) {
                 // |t| <= D * (max|y_train| + max|y_test|)^2 must stay below 2^31 for the
                 // integer-only clamp of the fast exp2 variant
                 float a = jb.bound_train ? *jb.bound_train : INFINITY;
@@ -823,7 +940,11 @@ pair_kernel(const PairJob* __restrict__ jobs, int n_jobs, long long total_units,
         mbar_wait(&full_bar[stage], parity);
         const T* __restrict__ tp = tile_buf + static_cast<size_t>(stage) * TILE * D;
 
-        if constexpr (sizeof(T) == 8) {
+        if constexpr (SHIFT && sizeof(T) == 8) {
+            tile_f64_shift<D, CKDE, R>(tp, cnt, yt, shj, shm, tab, sum_j, sum_m);
+        } else if constexpr (SHIFT) {
+            tile_f32_shift<D, CKDE, R>(tp, cnt, yt, shj, shm, sum_j, sum_m);
+        } else if constexpr (sizeof(T) == 8) {
             if (DOT && dot)
                 tile_f64_dot<D, CKDE, R, CDF>(tp, nrm_buf + static_cast<size_t>(stage) * TILE, cnt, yt, at, ati, tab, sum_j, sum_m, inv_c);
             else if (safe)

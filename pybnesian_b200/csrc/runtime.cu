@@ -244,7 +244,7 @@ struct FinalizeParams {
     double u2ln;         // kernel exponent unit -> natural log
     double thresh;       // sums below this are re-evaluated with a shift
     double* out;         // [m]
-    int* flagged;        // [m] row ids needing the shifted path
+    unsigned char* mask; // [m], zeroed by the caller: 1 = the row needs the shifted path
     int* n_flagged;
 };
 
@@ -266,8 +266,8 @@ __global__ void finalize_kernel(FinalizeParams P) {
     // NaN sums (NaN inputs) are not "underflow": propagate them
     if (sj != sj || (P.ckde && sm != sm)) bad = false;
     if (bad) {
-        int slot = atomicAdd(P.n_flagged, 1);
-        P.flagged[slot] = (int)row;
+        atomicAdd(P.n_flagged, 1);
+        P.mask[row] = 1;
         return;
     }
     double v = P.lognorm_joint + log(sj);
@@ -275,8 +275,185 @@ __global__ void finalize_kernel(FinalizeParams P) {
     P.out[row] = v;
 }
 
+// ------------------------------------------------------------------------------------
+// shifted second pass over the rows finalize_kernel flagged (their unshifted sums underflowed: test rows tens of
+// bandwidths away from every training row).  Everything is sized and scheduled ON THE DEVICE from the flagged count, so
+// the common case (no flagged row) costs five empty launches and no host synchronisation:
+//   compact_flagged_kernel  mask -> ascending list of row ids (deterministic order), shifts reset to +inf
+//   shift_prep_kernel       job / unit schedule of the second pair-kernel launch from the count
+//   rowmin_kernel           per flagged row the smallest squared distance to a training row (FP32 arithmetic: the shift
+//                           only has to bring the largest term near 1, not to be exact)
+//   pair_kernel<SHIFT>      the same tiled stream-K kernel with the per-row shift on the exponent (pair_kernel.cuh)
+//   finalize_shift_kernel   logl = lognorm + log(sum) - shift; rows that still have no usable sum (farther than 2^31
+//                           kernel units, non-finite coordinates) go to row_kernel, one CTA per row
+// Replaces the reference's max-shifted logsumexp_cols_offset (opencl/opencl_config.hpp:517-536), which it runs for every row.
+// ------------------------------------------------------------------------------------
+__global__ void compact_flagged_kernel(const unsigned char* __restrict__ mask, long long m, const int* __restrict__ n_flagged,
+                                       int* __restrict__ flagged, float* __restrict__ shift_j, float* __restrict__ shift_m) {
+    __shared__ int warp_tot[32];
+    __shared__ int base_s;
+    const int cnt = *n_flagged;
+    if (cnt == 0) return;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
+    if (tid == 0) base_s = 0;
+    __syncthreads();
+    for (long long r0 = 0; r0 < m; r0 += blockDim.x) {
+        const long long row = r0 + tid;
+        const int f = (row < m && mask[row]) ? 1 : 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) warp_tot[w] = __popc(bal);
+        __syncthreads();
+        int off = base_s;
+        for (int q = 0; q < w; ++q) off += warp_tot[q];
+        if (f) flagged[off + __popc(bal & ((1u << lane) - 1u))] = (int)row;
+        __syncthreads();
+        if (tid == 0) {
+            int t = 0;
+            for (int q = 0; q < nw; ++q) t += warp_tot[q];
+            base_s += t;
+        }
+        __syncthreads();
+        if (base_s == cnt) break;  // every flagged row has been listed
+    }
+    for (int i = tid; i < cnt; i += blockDim.x) {
+        shift_j[i] = INFINITY;
+        shift_m[i] = INFINITY;
+    }
+}
+
+struct ShiftPrepParams {
+    PairJob job;          // train / norms / part / shifts of the second launch; m and the schedule are filled here
+    const int* n_flagged;
+    PairJob* d_job;
+    long long* dyn;       // {total_units, upb}
+    int tb, grid;
+    int* n_flagged2;
+};
+
+__global__ void shift_prep_kernel(ShiftPrepParams P) {
+    const long long cnt = *P.n_flagged;
+    PairJob j = P.job;
+    j.m = cnt;
+    j.m_pad = (cnt + 31) / 32 * 32;
+    j.n_test_tiles = (int)((cnt + P.tb - 1) / P.tb);
+    const long long U = (long long)j.n_test_tiles * j.n_train_tiles;
+    const long long upb = U > 0 ? (U + P.grid - 1) / P.grid : 1;
+    long long slots = (j.n_train_tiles + upb - 1) / upb + 1;
+    j.slots = (int)(slots < P.grid ? slots : P.grid);
+    j.unit_begin = 0;
+    *P.d_job = j;
+    P.dyn[0] = U;
+    P.dyn[1] = upb;
+    *P.n_flagged2 = 0;
+}
+
+// grid = (row tiles, training splits); the minima of the splits are combined with an integer atomicMin (non-negative
+// floats order like their bit patterns)
+template <typename T, int D, bool CKDE>
+__global__ void rowmin_kernel(const T* __restrict__ train, long long n, const T* __restrict__ test, const int* __restrict__ rows,
+                              const int* __restrict__ n_rows, float* __restrict__ smin_j, float* __restrict__ smin_m) {
+    constexpr int TP = 256;
+    __shared__ float tile[TP * D];
+    const int cnt = *n_rows;
+    if (cnt == 0) return;
+    const long long chunk = ((n + gridDim.y - 1) / gridDim.y + TP - 1) / TP * TP;
+    const long long i0 = blockIdx.y * chunk;
+    const long long i1 = i0 + chunk < n ? i0 + chunk : n;
+    for (long long rt = blockIdx.x; rt * blockDim.x < cnt; rt += gridDim.x) {
+        const long long f = rt * blockDim.x + threadIdx.x;
+        const bool ok = f < cnt;
+        const long long row = ok ? rows[f] : rows[0];
+        float yt[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) yt[c] = static_cast<float>(test[row * D + c]);
+        float mj = INFINITY, mm = INFINITY;
+        for (long long base = i0; base < i1; base += TP) {
+            const int np = (int)(i1 - base < TP ? i1 - base : TP);
+            __syncthreads();
+            for (int q = threadIdx.x; q < np * D; q += blockDim.x) tile[q] = static_cast<float>(train[base * D + q]);
+            __syncthreads();
+#pragma unroll 4
+            for (int i = 0; i < np; ++i) {
+                float sq = 0.f, sm = 0.f;
+#pragma unroll
+                for (int c = 0; c < D; ++c) {
+                    const float dl = yt[c] - tile[i * D + c];
+                    sq = fmaf(dl, dl, sq);
+                    if (CKDE && c == D - 2) sm = sq;
+                }
+                mj = fminf(mj, sq);
+                if (CKDE) mm = fminf(mm, sm);
+            }
+        }
+        if (ok && i0 < i1) {
+            if (mj == mj) atomicMin(reinterpret_cast<int*>(smin_j + f), __float_as_int(mj));
+            if (CKDE && mm == mm) atomicMin(reinterpret_cast<int*>(smin_m + f), __float_as_int(mm));
+        }
+    }
+}
+
+template <typename T>
+static cudaError_t launch_rowmin(int d, bool ckde, dim3 grid, cudaStream_t st, const void* train, long long n, const void* test,
+                                 const int* rows, const int* n_rows, float* smin_j, float* smin_m) {
+#define PBN_RM_CASE(DD)                                                                                                        \
+    case DD:                                                                                                                   \
+        if (ckde) rowmin_kernel<T, (DD < 2 ? 2 : DD), true><<<grid, 256, 0, st>>>(static_cast<const T*>(train), n,              \
+                                                                                 static_cast<const T*>(test), rows, n_rows,   \
+                                                                                 smin_j, smin_m);                              \
+        else rowmin_kernel<T, DD, false><<<grid, 256, 0, st>>>(static_cast<const T*>(train), n, static_cast<const T*>(test),    \
+                                                               rows, n_rows, smin_j, smin_m);                                  \
+        break;
+    switch (d) {
+        PBN_RM_CASE(1) PBN_RM_CASE(2) PBN_RM_CASE(3) PBN_RM_CASE(4) PBN_RM_CASE(5)
+        PBN_RM_CASE(6) PBN_RM_CASE(7) PBN_RM_CASE(8) PBN_RM_CASE(9) PBN_RM_CASE(10)
+        default: return cudaErrorInvalidValue;
+    }
+#undef PBN_RM_CASE
+    return cudaGetLastError();
+}
+
+struct FinalizeShiftParams {
+    const PairJob* job;      // the second launch's job (device)
+    const long long* dyn;    // {total_units, upb}
+    int tb, ckde, f64;
+    double lognorm_joint, lognorm_marg, u2ln, thresh;
+    double* out;             // [m] of the ORIGINAL row numbering
+    const int* flagged;      // flagged position -> original row
+    int* flagged2;           // rows still without a usable sum
+    int* n_flagged2;
+};
+
+__global__ void finalize_shift_kernel(FinalizeShiftParams P) {
+    const PairJob jb = *P.job;
+    const long long upb = P.dyn[1];
+    for (long long f = blockIdx.x * (long long)blockDim.x + threadIdx.x; f < jb.m; f += (long long)gridDim.x * blockDim.x) {
+        const long long tt = f / P.tb;
+        const long long ustart = tt * jb.n_train_tiles;
+        const int first = (int)(ustart / upb);
+        const int last = (int)((ustart + jb.n_train_tiles - 1) / upb);
+        double sj = 0, sm = 0;
+        for (int s = 0; s <= last - first; ++s) {
+            sj += jb.part[(long long)s * jb.m_pad + f];
+            if (P.ckde) sm += jb.part[((long long)jb.slots + s) * jb.m_pad + f];
+        }
+        // the shift the kernel applied (pair_kernel: integer part for f64, the float itself for f32)
+        float fj = jb.shift_j[f], fm = P.ckde ? jb.shift_m[f] : 0.f;
+        double aj = P.f64 ? (fj < 2.0e9f ? (double)rintf(fj) : 0.0) : (double)fj;
+        double am = P.f64 ? (fm < 2.0e9f ? (double)rintf(fm) : 0.0) : (double)fm;
+        const bool bad = !(sj >= P.thresh) || !(sj < INFINITY) || (P.ckde && (!(sm >= P.thresh) || !(sm < INFINITY)));
+        const int row = P.flagged[f];
+        if (bad) {
+            P.flagged2[atomicAdd(P.n_flagged2, 1)] = row;
+            continue;
+        }
+        double v = P.lognorm_joint + log(sj) - aj * P.u2ln;
+        if (P.ckde) v -= P.lognorm_marg + log(sm) - am * P.u2ln;
+        P.out[row] = v;
+    }
+}
+
 // Robust per-row evaluation (max-shifted two-pass log-sum-exp, one CTA per test row).
-// Used for rows flagged by finalize_kernel and as the generic path for d > 8.
+// Used for rows flagged by finalize_kernel and as the generic path for d > kMaxFastD (10).
 struct RowParams {
     const void* train;   // whitened AoS [n][d]
     const void* test;    // whitened AoS [m][d]
@@ -561,7 +738,7 @@ static int fit_impl(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, 
     int64_t n_pad = ((n + tile - 1) / tile) * tile + 16;
     size_t ybytes = ((size_t)n_pad * d * elem_size(k->dtype) + 255) / 256 * 256;
     // row norms for the dot-product form of the pair kernel (f64 fast path only)
-    size_t nbytes = (k->dtype == PBN_F64 && d <= 8) ? ((size_t)n_pad * sizeof(double) + 255) / 256 * 256 : 0;
+    size_t nbytes = (k->dtype == PBN_F64 && d <= pbn::kMaxFastD) ? ((size_t)n_pad * sizeof(double) + 255) / 256 * 256 : 0;
     cudaError_t e = cudaMallocAsync(&k->y, ybytes + 256 + nbytes, ctx->stream);
     if (e != cudaSuccess) { delete k; PBN_CUDA_TRY(e); }
     e = cudaMemsetAsync(k->y, 0, ybytes + 256 + nbytes, ctx->stream);
@@ -573,6 +750,27 @@ static int fit_impl(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, 
     *out = k;
     return PBN_OK;
 }
+
+// Stream-ordered scratch of one call: everything allocated through it is returned to the pool when the call leaves,
+// on the error paths too (PBN_CUDA_TRY / PBN_TRY return early).
+struct Scratch {
+    cudaStream_t st;
+    std::vector<void*> ptrs;
+    std::vector<cudaEvent_t> events;  // destroyed on exit unless released
+    explicit Scratch(cudaStream_t s) : st(s) {}
+    ~Scratch() {
+        for (void* p : ptrs) cudaFreeAsync(p, st);
+        for (cudaEvent_t e : events) cudaEventDestroy(e);
+    }
+    template <typename T>
+    cudaError_t alloc(T** out, size_t bytes) {
+        void* p = nullptr;
+        cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 8, st);
+        if (e == cudaSuccess) ptrs.push_back(p);
+        *out = static_cast<T*>(p);
+        return e;
+    }
+};
 
 int pbn_logl_impl(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const int* cols, pbn_rows rows,
                      double* d_out_logl, double* d_out_slogl, double* h_out_logl, double* h_out_slogl) {
@@ -595,43 +793,68 @@ int pbn_logl_impl(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const i
     const size_t es = elem_size(k->dtype);
     const int TILE = f64 ? pbn::pair_tile_f64(d) : pbn::pair_tile_f32(d);
     const int TB = f64 ? pbn::pair_tb_for_f64(d, k->ckde) : pbn::pair_tb_for_f32(d, k->ckde);
-    const bool fast = d <= 8;
+    const bool fast = d <= pbn::kMaxFastD;
+    Scratch sc(st);
 
-    void* ytest = nullptr;
+    char* ytest = nullptr;
     size_t ytbytes = ((size_t)m * d * es + 255) / 256 * 256;
     const size_t tnbytes = k->nrm ? ((size_t)m * sizeof(double) + 255) / 256 * 256 : 0;
-    PBN_CUDA_TRY(cudaMallocAsync(&ytest, ytbytes + 256 + tnbytes, st));
-    float* bound_test = reinterpret_cast<float*>(static_cast<char*>(ytest) + ytbytes);
-    double* nrm_test = tnbytes ? reinterpret_cast<double*>(static_cast<char*>(ytest) + ytbytes + 256) : nullptr;
+    PBN_CUDA_TRY(sc.alloc(&ytest, ytbytes + 256 + tnbytes));
+    float* bound_test = reinterpret_cast<float*>(ytest + ytbytes);
+    double* nrm_test = tnbytes ? reinterpret_cast<double*>(ytest + ytbytes + 256) : nullptr;
     PBN_CUDA_TRY(cudaMemsetAsync(bound_test, 0, 256, st));
     PBN_TRY(pbn_whiten_kde(ctx, k, test, cols, rows, ytest, bound_test, nrm_test));
 
     double* out = d_out_logl;
-    bool own_out = false;
-    if (!out) {
-        PBN_CUDA_TRY(cudaMallocAsync(&out, (size_t)m * sizeof(double), st));
-        own_out = true;
-    }
+    if (!out) PBN_CUDA_TRY(sc.alloc(&out, (size_t)m * sizeof(double)));
     const double u2ln = 1.0 / unit_scale(k->dtype);  // (kernel units of s'/ -t) -> natural log
+
+    RowParams R;
+    R.train = k->y;
+    R.test = ytest;
+    R.n = k->n;
+    R.d = d;
+    R.ckde = k->ckde ? 1 : 0;
+    R.lognorm_joint = k->lognorm_joint;
+    R.lognorm_marg = k->lognorm_marg;
+    R.u2ln = u2ln;
+    R.out = out;
+    const int rgrid = (int)std::min<int64_t>(m, (int64_t)ctx->sm_count * 8);
 
     if (fast) {
         int n_test_tiles = (int)((m + TB - 1) / TB);
         int n_train_tiles = (int)((k->n + TILE - 1) / TILE);
         long long U = (long long)n_test_tiles * n_train_tiles;
-        int max_grid = ctx->sm_count * 2;
+        const int max_grid = ctx->sm_count * 2;
         int grid = (int)std::min<long long>(U, max_grid);
         long long upb = (U + grid - 1) / grid;
         grid = (int)((U + upb - 1) / upb);
         int slots = (int)std::min<long long>((n_train_tiles + upb - 1) / upb + 1, grid);
         int n_acc = k->ckde ? 2 : 1;
         long long m_pad = (m + 31) / 32 * 32;
+        // one carve for the bookkeeping of both passes:
+        //   [PairJob x 2][dyn: 2 x i64][counters: 2 x int][flagged: m int][flagged2: m int][shift_j, shift_m: m float][mask: m bytes]
+        const size_t o_dyn = 2 * ((sizeof(PairJob) + 15) / 16 * 16), o_cnt = o_dyn + 16, o_fl = o_cnt + 16;
+        const size_t o_fl2 = o_fl + (size_t)m * 4, o_sj = o_fl2 + (size_t)m * 4, o_sm = o_sj + (size_t)m * 4;
+        const size_t o_mask = o_sm + (size_t)m * 4;
+        char* book = nullptr;
         double* part = nullptr;
-        PairJob* d_job = nullptr;
-        int* flagged = nullptr;
-        PBN_CUDA_TRY(cudaMallocAsync(&part, (size_t)n_acc * slots * m_pad * sizeof(double), st));
-        PBN_CUDA_TRY(cudaMallocAsync(&d_job, sizeof(PairJob) + 16, st));
-        PBN_CUDA_TRY(cudaMallocAsync(&flagged, ((size_t)m + 1) * sizeof(int), st));
-        int* n_flagged = flagged + m;
+        double* part2 = nullptr;
+        PBN_CUDA_TRY(sc.alloc(&book, o_mask + (size_t)m));
+        PBN_CUDA_TRY(sc.alloc(&part, (size_t)n_acc * slots * m_pad * sizeof(double)));
+        // second pass: slots' x m_pad' <= grid x TB + 2 (m + TB) whatever the flagged count is (see shift_prep_kernel)
+        PBN_CUDA_TRY(sc.alloc(&part2, (size_t)n_acc * ((size_t)max_grid * TB + 2 * ((size_t)m + TB) + 64) * sizeof(double)));
+        PairJob* d_job = reinterpret_cast<PairJob*>(book);
+        PairJob* d_job2 = reinterpret_cast<PairJob*>(book + o_dyn / 2);
+        long long* dyn = reinterpret_cast<long long*>(book + o_dyn);
+        int* n_flagged = reinterpret_cast<int*>(book + o_cnt);
+        int* n_flagged2 = n_flagged + 1;
+        int* flagged = reinterpret_cast<int*>(book + o_fl);
+        int* flagged2 = reinterpret_cast<int*>(book + o_fl2);
+        float* shift_j = reinterpret_cast<float*>(book + o_sj);
+        float* shift_m = reinterpret_cast<float*>(book + o_sm);
+        unsigned char* mask = reinterpret_cast<unsigned char*>(book + o_mask);
+        PBN_CUDA_TRY(cudaMemsetAsync(mask, 0, (size_t)m, st));
         PairJob job;
         memset(&job, 0, sizeof(job));
         job.train = k->y;
@@ -654,7 +877,9 @@ int pbn_logl_impl(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const i
         cudaEvent_t ev0 = nullptr, ev1 = nullptr;
         if (ctx->timing) {
             PBN_CUDA_TRY(cudaEventCreate(&ev0));
+            sc.events.push_back(ev0);
             PBN_CUDA_TRY(cudaEventCreate(&ev1));
+            sc.events.push_back(ev1);
             PBN_CUDA_TRY(cudaEventRecord(ev0, st));
         }
         cudaError_t e = f64 ? pbn::launch_pair_f64(d, k->ckde, d_job, 1, U, upb, grid, ctx->d_exp_tab, st)
@@ -664,6 +889,7 @@ int pbn_logl_impl(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const i
         if (ctx->timing) {
             PBN_CUDA_TRY(cudaEventRecord(ev1, st));
             ctx->timed.emplace_back(ev0, ev1);
+            sc.events.clear();  // owned by ctx->timed from here on
             ctx->pair_units += (int64_t)k->n * m * (k->ckde ? 2 : 1);
         }
         FinalizeParams F;
@@ -676,55 +902,76 @@ int pbn_logl_impl(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const i
         F.u2ln = u2ln;
         F.thresh = f64 ? ldexp(1.0, -900) : ldexp(1.0, -64);
         F.out = out;
-        F.flagged = flagged;
+        F.mask = mask;
         F.n_flagged = n_flagged;
         finalize_kernel<<<(int)((m + 255) / 256), 256, 0, st>>>(F);
         ctx->launches++;
         PBN_CUDA_TRY(cudaGetLastError());
-        // rows whose unshifted sums underflowed: exact max-shifted evaluation (count read on device)
-        RowParams R;
-        R.train = k->y;
-        R.test = ytest;
-        R.n = k->n;
-        R.d = d;
-        R.ckde = k->ckde ? 1 : 0;
-        R.lognorm_joint = k->lognorm_joint;
-        R.lognorm_marg = k->lognorm_marg;
-        R.u2ln = u2ln;
-        R.rows = flagged;
-        R.count_ptr = n_flagged;
+
+        // ---- second pass over the flagged rows, scheduled on the device from their count ----
+        compact_flagged_kernel<<<1, 1024, 0, st>>>(mask, m, n_flagged, flagged, shift_j, shift_m);
+        ShiftPrepParams SP;
+        SP.job = job;
+        SP.job.part = part2;
+        SP.job.bound_train = nullptr;  // the shifted tile takes the SAFE exponent path
+        SP.job.bound_test = nullptr;
+        SP.job.train_nrm = nullptr;
+        SP.job.test_nrm = nullptr;
+        SP.job.shift_j = shift_j;
+        SP.job.shift_m = shift_m;
+        SP.job.test_rows = flagged;
+        SP.n_flagged = n_flagged;
+        SP.d_job = d_job2;
+        SP.dyn = dyn;
+        SP.tb = TB;
+        SP.grid = max_grid;
+        SP.n_flagged2 = n_flagged2;
+        shift_prep_kernel<<<1, 1, 0, st>>>(SP);
+        // few flagged rows: split the training rows so that the scan still spreads over the GPU
+        dim3 rmgrid((unsigned)std::min<int64_t>((m + 255) / 256, 4096), 8);
+        cudaError_t e2 = f64 ? launch_rowmin<double>(d, k->ckde, rmgrid, st, k->y, k->n, ytest, flagged, n_flagged, shift_j, shift_m)
+                             : launch_rowmin<float>(d, k->ckde, rmgrid, st, k->y, k->n, ytest, flagged, n_flagged, shift_j, shift_m);
+        PBN_CUDA_TRY(e2);
+        e2 = f64 ? pbn::launch_pair_shift_f64(d, k->ckde, d_job2, dyn, max_grid, ctx->d_exp_tab, st)
+                 : pbn::launch_pair_shift_f32(d, k->ckde, d_job2, dyn, max_grid, ctx->d_exp_tab, st);
+        PBN_CUDA_TRY(e2);
+        FinalizeShiftParams FS;
+        FS.job = d_job2;
+        FS.dyn = dyn;
+        FS.tb = TB;
+        FS.ckde = k->ckde ? 1 : 0;
+        FS.f64 = f64 ? 1 : 0;
+        FS.lognorm_joint = k->lognorm_joint;
+        FS.lognorm_marg = k->lognorm_marg;
+        FS.u2ln = u2ln;
+        FS.thresh = ldexp(1.0, -40);  // the largest term of a shifted row is ~1
+        FS.out = out;
+        FS.flagged = flagged;
+        FS.flagged2 = flagged2;
+        FS.n_flagged2 = n_flagged2;
+        finalize_shift_kernel<<<(int)std::min<int64_t>((m + 255) / 256, (int64_t)ctx->sm_count * 4), 256, 0, st>>>(FS);
+        ctx->launches += 5;
+        PBN_CUDA_TRY(cudaGetLastError());
+        // rows the shifted pass could not evaluate either: exact per-row evaluation (count read on device)
+        R.rows = flagged2;
+        R.count_ptr = n_flagged2;
         R.count = 0;
-        R.out = out;
-        int rgrid = (int)std::min<int64_t>(m, (int64_t)ctx->sm_count * 8);
         if (f64) row_kernel<double><<<rgrid, 256, 0, st>>>(R);
         else row_kernel<float><<<rgrid, 256, 0, st>>>(R);
         ctx->launches++;
         PBN_CUDA_TRY(cudaGetLastError());
         if (h_out_logl || h_out_slogl) {
-            int nf = 0;
-            PBN_CUDA_TRY(cudaMemcpyAsync(&nf, n_flagged, sizeof(int), cudaMemcpyDeviceToHost, st));
+            int nf[2] = {0, 0};
+            PBN_CUDA_TRY(cudaMemcpyAsync(nf, n_flagged, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
             PBN_CUDA_TRY(cudaStreamSynchronize(st));
-            ctx->last_fallback_rows = nf;
-            ctx->d2h += 4;
+            ctx->last_fallback_rows = nf[0];
+            ctx->last_row_kernel_rows = nf[1];
+            ctx->d2h += 8;
         }
-        PBN_CUDA_TRY(cudaFreeAsync(part, st));
-        PBN_CUDA_TRY(cudaFreeAsync(d_job, st));
-        PBN_CUDA_TRY(cudaFreeAsync(flagged, st));
     } else {
-        RowParams R;
-        R.train = k->y;
-        R.test = ytest;
-        R.n = k->n;
-        R.d = d;
-        R.ckde = k->ckde ? 1 : 0;
-        R.lognorm_joint = k->lognorm_joint;
-        R.lognorm_marg = k->lognorm_marg;
-        R.u2ln = u2ln;
         R.rows = nullptr;
         R.count_ptr = nullptr;
         R.count = m;
-        R.out = out;
-        int rgrid = (int)std::min<int64_t>(m, (int64_t)ctx->sm_count * 8);
         if (f64) row_kernel<double><<<rgrid, 256, 0, st>>>(R);
         else row_kernel<float><<<rgrid, 256, 0, st>>>(R);
         ctx->launches++;
@@ -735,7 +982,7 @@ int pbn_logl_impl(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const i
     if (h_out_slogl || d_out_slogl) {
         int sb = (int)std::min<int64_t>((m + 255) / 256, (int64_t)ctx->sm_count * 4);
         double* partial = nullptr;
-        PBN_CUDA_TRY(cudaMallocAsync(&partial, (size_t)(sb + 1) * sizeof(double), st));
+        PBN_CUDA_TRY(sc.alloc(&partial, (size_t)(sb + 1) * sizeof(double)));
         if (!d_sum) d_sum = partial + sb;
         sum_partial_kernel<<<sb, 256, 0, st>>>(out, m, partial);
         sum_final_kernel<<<1, 256, 0, st>>>(partial, sb, d_sum);
@@ -744,17 +991,14 @@ int pbn_logl_impl(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const i
         if (h_out_slogl) {
             PBN_CUDA_TRY(cudaMemcpyAsync(h_out_slogl, d_sum, sizeof(double), cudaMemcpyDeviceToHost, st));
             ctx->d2h += 8;
+            PBN_CUDA_TRY(cudaStreamSynchronize(st));
         }
-        if (h_out_slogl) PBN_CUDA_TRY(cudaStreamSynchronize(st));
-        PBN_CUDA_TRY(cudaFreeAsync(partial, st));
     }
     if (h_out_logl) {
         PBN_CUDA_TRY(cudaMemcpyAsync(h_out_logl, out, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, st));
         PBN_CUDA_TRY(cudaStreamSynchronize(st));
         ctx->d2h += m * 8;
     }
-    PBN_CUDA_TRY(cudaFreeAsync(ytest, st));
-    if (own_out) PBN_CUDA_TRY(cudaFreeAsync(out, st));
     return PBN_OK;
 }
 
@@ -874,6 +1118,11 @@ int pbn_ctx_pair_kernel_time(pbn_ctx* ctx, double* total_ms, int64_t* n_launches
 int pbn_ctx_last_fallback_rows(pbn_ctx* ctx, int64_t* out) {
     if (!ctx || !out) return set_error(PBN_ERR_ARG, "null argument");
     *out = ctx->last_fallback_rows;
+    return PBN_OK;
+}
+int pbn_ctx_last_row_kernel_rows(pbn_ctx* ctx, int64_t* out) {
+    if (!ctx || !out) return set_error(PBN_ERR_ARG, "null argument");
+    *out = ctx->last_row_kernel_rows;
     return PBN_OK;
 }
 

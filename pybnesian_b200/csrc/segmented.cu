@@ -90,6 +90,8 @@ cudaError_t launch_whiten_seg(int d, const SegWhitenJob* jobs, int n_jobs, long 
         case 6: whiten_seg_kernel<T, 6><<<grid, 256, 0, st>>>(jobs); break;
         case 7: whiten_seg_kernel<T, 7><<<grid, 256, 0, st>>>(jobs); break;
         case 8: whiten_seg_kernel<T, 8><<<grid, 256, 0, st>>>(jobs); break;
+        case 9: whiten_seg_kernel<T, 9><<<grid, 256, 0, st>>>(jobs); break;
+        case 10: whiten_seg_kernel<T, 10><<<grid, 256, 0, st>>>(jobs); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

@@ -100,7 +100,10 @@ def test_config5_iid_1m_subsample_and_additivity(pbn, d, dtype, tol):
     assert np.all(np.isfinite(logl))
     X = train.to_numpy()
     H = oracle.bandwidth(X)
-    assert np.allclose(k.bandwidth, H, rtol=1e-11 if dtype == "float64" else 2e-5, atol=0)
+    # the off-diagonal covariances of independent columns are ~1e-3 of the variances and carry the cancellation of
+    # their sums: the bar is relative to the size of the matrix
+    btol = 1e-11 if dtype == "float64" else 2e-5
+    assert np.max(np.abs(np.asarray(k.bandwidth) - H)) <= btol * np.max(np.abs(H))
     rows = np.random.default_rng(d).choice(N5, 512, replace=False)
     # the extreme rows of the test set are where unshifted float sums are smallest: always part of the sample
     r2 = (test.to_numpy().astype(np.float64) ** 2).sum(axis=1)
