@@ -640,7 +640,7 @@ int pbn_ckde_cdf(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const in
         int n_test_tiles = (int)((m + TB - 1) / TB);
         int n_train_tiles = (int)((k->n + TILE - 1) / TILE);
         long long U = (long long)n_test_tiles * n_train_tiles;
-        int grid = (int)std::min<long long>(U, ctx->sm_count * 2);
+        int grid = (int)std::min<long long>(U, (long long)ctx->sm_count * (f64 ? pbn::pair_ctas_per_sm_f64() : pbn::pair_ctas_per_sm_f32()));
         long long upb = (U + grid - 1) / grid;
         grid = (int)((U + upb - 1) / upb);
         int slots = (int)std::min<long long>((n_train_tiles + upb - 1) / upb + 1, grid);

@@ -731,7 +731,7 @@ int score_ckde_group(pbn_ctx* ctx, pbn_cv* cv, const pbn_cv_item* items, const s
             U += (long long)pj[j].n_train_tiles * pj[j].n_test_tiles;
             max_m = std::max<long long>(max_m, hj[j].m);
         }
-        int grid = (int)std::min<long long>(U, (long long)ctx->sm_count * 2);
+        int grid = (int)std::min<long long>(U, (long long)ctx->sm_count * (f64 ? pbn::pair_ctas_per_sm_f64() : pbn::pair_ctas_per_sm_f32()));
         long long upb = (U + grid - 1) / grid;
         grid = (int)((U + upb - 1) / upb);
         const int n_acc = ckde ? 2 : 1;

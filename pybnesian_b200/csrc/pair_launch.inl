@@ -55,6 +55,7 @@ int PBN_TILE_NAME(int D) { return pair_tile<PBN_T>(D); }
 int PBN_TB_NAME() { return kThreads * PairCfg<PBN_T>::R; }
 int PBN_TB_FOR_NAME(int D, bool ckde) { return kThreads * pair_rows<PBN_T>(D, ckde); }
 int PBN_TB_CDF_NAME(int D) { return kThreads * pair_rows_cdf<PBN_T>(D); }
+int PBN_CTAS_NAME() { return PairCfg<PBN_T>::MIN_CTAS; }
 
 #endif  // PBN_LAUNCH_NAME
 

@@ -825,7 +825,7 @@ int pbn_logl_impl(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const i
         int n_test_tiles = (int)((m + TB - 1) / TB);
         int n_train_tiles = (int)((k->n + TILE - 1) / TILE);
         long long U = (long long)n_test_tiles * n_train_tiles;
-        const int max_grid = ctx->sm_count * 2;
+        const int max_grid = ctx->sm_count * (f64 ? pbn::pair_ctas_per_sm_f64() : pbn::pair_ctas_per_sm_f32());
         int grid = (int)std::min<long long>(U, max_grid);
         long long upb = (U + grid - 1) / grid;
         grid = (int)((U + upb - 1) / upb);

@@ -250,7 +250,7 @@ int pbn_kde_logl_multi(pbn_ctx* ctx, const pbn_kde* const* kdes, int n_jobs, con
             fj[q].lognorm_marg = k->lognorm_marg;
             fj[q].out_off = off[j];
         }
-        int grid = (int)std::min<long long>(U, (long long)ctx->sm_count * 2);
+        int grid = (int)std::min<long long>(U, (long long)ctx->sm_count * (f64 ? pbn::pair_ctas_per_sm_f64() : pbn::pair_ctas_per_sm_f32()));
         long long upb = (U + grid - 1) / grid;
         grid = (int)((U + upb - 1) / upb);
         const int n_acc = ckde ? 2 : 1;

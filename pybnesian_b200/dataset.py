@@ -31,7 +31,17 @@ def _to_record_batch(obj):
             return pa.RecordBatch.from_pandas(obj, None, False)
     except ImportError:  # pragma: no cover
         pass
-    raise TypeError("expected a pandas.DataFrame, pyarrow.RecordBatch or pyarrow.Table")
+    # Arrow C Data Interface, the boundary the reference's type caster uses (dataset/dataset.hpp:2088-2143:
+    # extract_pycapsule_array + arrow::ImportRecordBatch): a (schema, array) pair of PyCapsules, or any object that
+    # exports them through the PyCapsule protocol (__arrow_c_array__ for one struct array, __arrow_c_stream__ for a
+    # stream of batches - polars / nanoarrow / duckdb frames)
+    if isinstance(obj, tuple) and len(obj) == 2 and all(type(c).__name__ == "PyCapsule" for c in obj):
+        return pa.RecordBatch._import_from_c_capsule(*obj)
+    if hasattr(obj, "__arrow_c_array__"):
+        return pa.record_batch(obj)
+    if hasattr(obj, "__arrow_c_stream__"):
+        return _to_record_batch(pa.table(obj))
+    raise TypeError("expected a pandas.DataFrame, pyarrow.RecordBatch / Table, or an Arrow C-Data capsule exporter")
 
 
 _DTYPE_CODE = {pa.float64(): _lib.PBN_F64, pa.float32(): _lib.PBN_F32}

@@ -102,7 +102,8 @@ def test_config5_iid_1m_subsample_and_additivity(pbn, d, dtype, tol):
     H = oracle.bandwidth(X)
     # the off-diagonal covariances of independent columns are ~1e-3 of the variances and carry the cancellation of
     # their sums: the bar is relative to the size of the matrix
-    btol = 1e-11 if dtype == "float64" else 2e-5
+    # (float32: the reference - and the oracle - accumulate the 1M products in float, this library in double)
+    btol = 1e-11 if dtype == "float64" else 1e-4
     assert np.max(np.abs(np.asarray(k.bandwidth) - H)) <= btol * np.max(np.abs(H))
     rows = np.random.default_rng(d).choice(N5, 512, replace=False)
     # the extreme rows of the test set are where unshifted float sums are smallest: always part of the sample
