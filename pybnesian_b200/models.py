@@ -78,8 +78,14 @@ class Dag:
                         nodes.append(n)
         if len(set(nodes)) != len(nodes):
             raise ValueError("Graph cannot be created with repeated names.")
+        # raw slots (None once removed) / name -> raw index / names in collapsed order / name -> collapsed index / free
+        # raw slots: GraphBase::m_nodes, m_indices, m_string_nodes (a BidirectionalMapIndex), m_free_indices
+        # (graph/generic_graph.hpp:395-507)
         self._names = nodes
         self._index = {n: i for i, n in enumerate(nodes)}
+        self._collapsed = list(nodes)
+        self._cindex = {n: i for i, n in enumerate(nodes)}
+        self._free = []
         self._parents = [_IntSet() for _ in nodes]
         self._children = [_IntSet() for _ in nodes]
         self._arcs = set()
@@ -93,9 +99,12 @@ class Dag:
 
     # -- nodes ---------------------------------------------------------------------------
     def nodes(self):
-        return list(self._names)
+        return list(self._collapsed)
 
     def num_nodes(self):
+        return len(self._collapsed)
+
+    def num_raw_nodes(self):
         return len(self._names)
 
     def contains_node(self, name):
@@ -107,12 +116,59 @@ class Dag:
         except KeyError:
             raise IndexError("Node " + str(name) + " not present in the graph.")
 
-    collapsed_index = index
+    def collapsed_index(self, name):
+        try:
+            return self._cindex[name]
+        except KeyError:
+            raise IndexError("Node " + str(name) + " not present in the graph.")
 
     def name(self, idx):
+        if idx < 0 or idx >= len(self._names) or self._names[idx] is None:
+            raise IndexError("Node index " + str(idx) + " not present in the graph.")
         return self._names[idx]
 
-    collapsed_name = name
+    def collapsed_name(self, idx):
+        return self._collapsed[idx]
+
+    def add_node(self, name):
+        """GraphBase::add_node / create_node (generic_graph.hpp:509-544): a freed raw slot is reused, last freed first."""
+        if name in self._index:
+            raise ValueError("Cannot add node " + str(name) + " because a node with the same name already exists.")
+        if self._free:
+            idx = self._free.pop()
+            self._names[idx] = name
+            self._parents[idx], self._children[idx] = _IntSet(), _IntSet()
+        else:
+            idx = len(self._names)
+            self._names.append(name)
+            self._parents.append(_IntSet())
+            self._children.append(_IntSet())
+        self._index[name] = idx
+        self._cindex[name] = len(self._collapsed)
+        self._collapsed.append(name)
+        self._roots.insert(idx)
+        return idx
+
+    def remove_node(self, name):
+        """GraphBase::remove_node_unsafe (generic_graph.hpp:546-580): arcs of the node go first, the raw slot is freed, and
+        the collapsed order closes the gap with the LAST node (BidirectionalMapIndex::remove = swap_remove)."""
+        idx = self.index(name)
+        if idx in self._roots:
+            self._roots.erase(idx)
+        for p in self._parents[idx].list():
+            self._remove_arc_unsafe(p, idx)
+        for ch in self._children[idx].list():
+            self._remove_arc_unsafe(idx, ch)
+        if idx in self._roots:  # _remove_arc_unsafe re-inserts a node that lost its last parent
+            self._roots.erase(idx)
+        ci = self._cindex.pop(name)
+        last = self._collapsed.pop()
+        if ci < len(self._collapsed):
+            self._collapsed[ci] = last
+            self._cindex[last] = ci
+        del self._index[name]
+        self._names[idx] = None
+        self._free.append(idx)
 
     # -- arcs ----------------------------------------------------------------------------
     def num_arcs(self):
@@ -232,7 +288,7 @@ class Dag:
         return {self._names[i] for i in self._roots.list()}
 
     def leaves(self):
-        return {n for i, n in enumerate(self._names) if len(self._children[i]) == 0}
+        return {n for i, n in enumerate(self._names) if n is not None and len(self._children[i]) == 0}
 
     def save(self, filename):
         if not filename.endswith(".pickle"):
@@ -251,7 +307,7 @@ class Dag:
                 indeg[ch] -= 1
                 if indeg[ch] == 0:
                     stack.append(ch)
-        if len(order) != len(self._names):
+        if len(order) != len(self._collapsed):
             raise ValueError("Graph must be a DAG to obtain a topological sort.")
         return order
 
@@ -259,6 +315,9 @@ class Dag:
         g = Dag.__new__(Dag)
         g._names = list(self._names)
         g._index = dict(self._index)
+        g._collapsed = list(self._collapsed)
+        g._cindex = dict(self._cindex)
+        g._free = list(self._free)
         g._parents = [p.clone() for p in self._parents]  # unordered_set copy keeps the iteration order
         g._children = [c.clone() for c in self._children]
         g._arcs = set(self._arcs)
@@ -266,7 +325,8 @@ class Dag:
         return g
 
     def __getstate__(self):
-        return (self._names, self.arcs())
+        # graph::__getstate__ (generic_graph.hpp:282-330) saves the collapsed node list: removed slots do not survive
+        return (self.nodes(), self.arcs())
 
     def __setstate__(self, t):
         self.__init__(t[0], t[1])
@@ -534,10 +594,29 @@ class BayesianNetwork:
         return self._g.index(node)
 
     def collapsed_index(self, node):
-        return self._g.index(node)
+        return self._g.collapsed_index(node)
 
     def collapsed_name(self, idx):
-        return self._g.name(idx)
+        return self._g.collapsed_name(idx)
+
+    def add_node(self, node):
+        """BNGeneric::add_node (models/BayesianNetwork.hpp:503-515)."""
+        idx = self._g.add_node(node)
+        if idx == self._g.num_raw_nodes() - 1:
+            if self._cpds:
+                self._cpds.append(None)
+            if not self._type.is_homogeneous():
+                self._node_types.append(UnknownFactorType())
+        return idx
+
+    def remove_node(self, node):
+        """BNGeneric::remove_node (models/BayesianNetwork.hpp:517-527)."""
+        idx = self._g.index(node)
+        if self._cpds:
+            self._cpds[idx] = None
+        if not self._type.is_homogeneous():
+            self._node_types[idx] = UnknownFactorType()
+        self._g.remove_node(node)
 
     def name(self, idx):
         return self._g.name(idx)
@@ -644,7 +723,7 @@ class BayesianNetwork:
     def has_unknown_node_types(self):
         if self._type.is_homogeneous():
             return False
-        return any(t == UnknownFactorType() for t in self._node_types)
+        return any(self._node_types[self.index(n)] == UnknownFactorType() for n in self.nodes())
 
     def set_unknown_node_types(self, df, type_blacklist=()):
         if self._type.is_homogeneous():
@@ -686,7 +765,10 @@ class BayesianNetwork:
 
     # -- CPDs --------------------------------------------------------------------------------
     def fitted(self):
-        return bool(self._cpds) and all(c is not None and c.fitted() for c in self._cpds)
+        if not self._cpds:
+            return False
+        cpds = [self._cpds[self.index(n)] for n in self.nodes()]
+        return all(c is not None and c.fitted() for c in cpds)
 
     def cpd(self, node):
         i = self.index(node)
@@ -697,7 +779,7 @@ class BayesianNetwork:
     def fit(self, df, construction_args=None):
         frame = DataFrame.wrap(df)
         if not self._cpds:
-            self._cpds = [None] * self.num_nodes()
+            self._cpds = [None] * self._g.num_raw_nodes()
         # BayesianNetwork.hpp:965-976: nodes without a type take their data's default type first, so that
         # new_factor sees the (possibly discrete) types of the parents
         if not self._type.is_homogeneous():
@@ -755,6 +837,13 @@ class BayesianNetwork:
         m._node_types = list(self._node_types)
         m._cpds = list(self._cpds)
         m._include_cpd = self.include_cpd()
+        # a Python-derived network keeps its own state across clone(), as the reference's trampoline does through
+        # __getstate_extra__ / __setstate_extra__ (models/BayesianNetwork.hpp:1139-1167, pybindings_models.cpp)
+        for key, val in self.__dict__.items():
+            if key not in m.__dict__:
+                m.__dict__[key] = val
+        if hasattr(self, "__getstate_extra__") and hasattr(m, "__setstate_extra__"):
+            m.__setstate_extra__(self.__getstate_extra__())
         return m
 
     def check_compatible_cpd(self, cpd):
@@ -783,7 +872,7 @@ class BayesianNetwork:
             self.force_type_whitelist([(c.variable(), c.type()) for c in cpds
                                        if self.node_type(c.variable()) == UnknownFactorType()])
         if not self._cpds:
-            self._cpds = [None] * self.num_nodes()
+            self._cpds = [None] * self._g.num_raw_nodes()
         for cpd in cpds:
             self._cpds[self.index(cpd.variable())] = cpd
 

@@ -269,3 +269,68 @@ def test_arguments_lookup_order():
     assert A.args("c", pbn.LinearGaussianCPDType()) == ((), {})
     with pytest.raises(ValueError):
         pbn.Arguments({3: ()})
+
+
+def test_remove_and_add_node_keep_the_reference_index_semantics():
+    """graph/generic_graph.hpp:509-580 and util/bidirectionalmap_index.hpp:59-65: raw indices are stable, a freed slot is
+    reused by the next add_node, the collapsed order closes a gap with the LAST node.  The reference's
+    hillclimbing_test.py:13-20,108-112 builds its start models this way."""
+    import pybnesian_b200 as pbn
+    g = pbn.GaussianNetwork(["a", "e", "b", "f", "c", "d"], [("a", "e"), ("e", "b"), ("b", "c"), ("f", "d")])
+    g.remove_node("e")
+    assert g.nodes() == ["a", "d", "b", "f", "c"] and g.num_nodes() == 5 and g.num_arcs() == 2
+    assert g.index("d") == 5 and g.collapsed_index("d") == 1 and g.collapsed_name(1) == "d" and g.name(5) == "d"
+    assert not g.contains_node("e") and g.arcs() == [("b", "c"), ("f", "d")]
+    with pytest.raises(IndexError):
+        g.index("e")
+    g.remove_node("f")
+    assert g.nodes() == ["a", "d", "b", "c"] and g.num_arcs() == 1
+    assert sorted(g.graph().roots()) == ["a", "b", "d"]
+    assert sorted(g.graph().topological_sort()) == ["a", "b", "c", "d"]
+    assert g.add_node("z") == 3 and g.add_node("y") == 1 and g.add_node("x") == 6   # last freed slot first
+    assert g.nodes() == ["a", "d", "b", "c", "z", "y", "x"]
+    with pytest.raises(ValueError, match="same name"):
+        g.add_node("a")
+    g.add_arc("z", "a")
+    assert g.can_add_arc("a", "b") and not g.can_add_arc("a", "z")
+    c = g.clone()
+    c.remove_node("z")
+    assert g.has_arc("z", "a") and c.nodes() == ["a", "d", "b", "c", "x", "y"]
+    import pickle
+    r = pickle.loads(pickle.dumps(g))
+    assert r.nodes() == g.nodes() and r.arcs() == g.arcs()
+    sp = pbn.SemiparametricBN(["a", "b", "c"], node_types=[("b", pbn.CKDEType())])
+    sp.remove_node("a")
+    assert not sp.has_unknown_node_types() or sp.node_type("c") == pbn.UnknownFactorType()
+    assert sp.node_type("b") == pbn.CKDEType() and sp.nodes() == ["c", "b"]
+
+
+def test_clone_keeps_python_side_state_of_derived_networks():
+    """reference hillclimbing_test.py:178-207 (NewBN.extra_data through __getstate_extra__ / __setstate_extra__)."""
+    import pybnesian_b200 as pbn
+
+    class NewType(pbn.BayesianNetworkType):
+        def is_homogeneous(self):
+            return True
+
+        def default_node_type(self):
+            return pbn.LinearGaussianCPDType()
+
+        def new_bn(self, nodes):
+            return NewBN(nodes)
+
+    class NewBN(pbn.BayesianNetwork):
+        def __init__(self, variables):
+            pbn.BayesianNetwork.__init__(self, NewType(), variables)
+            self.extra_data = "extra"
+
+        def __getstate_extra__(self):
+            return self.extra_data
+
+        def __setstate_extra__(self, extra):
+            self.extra_data = extra
+
+    m = NewBN(["a", "b"])
+    m.extra_data = "changed"
+    c = m.clone()
+    assert type(c) is NewBN and c.extra_data == "changed" and c.nodes() == ["a", "b"]

@@ -32,6 +32,8 @@ FILES = [
 
 # test id (file::name) -> why it cannot pass on a build scoped to SURVEY.md section 8
 EXPECTED_FAILURES = {
+    "hillclimbing_test.py::test_hc_conditional_estimate":
+        "needs ConditionalGaussianNetwork (conditional Bayesian networks: out of scope, SURVEY.md section 2)",
 }
 
 
