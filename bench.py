@@ -316,6 +316,9 @@ def main():
         extras["strong_scaling"] = strong_scaling_leg(args, ctx, cpd, world, rank, barrier, reduce_max, pbn, parallel)
         extras["hc_cv"] = hc_leg(world)
         barrier()
+        if world > 1:
+            extras["inproc_multi_gpu"] = inproc_leg(args, world, rank, extras["strong_scaling"]["slogl_single_gpu"])
+            barrier()
 
     if rank != 0:
         if world > 1:
@@ -393,6 +396,8 @@ def main():
                   "fallback_rows_last_call": ctx.last_fallback_rows(), "wall_s_timed_loop": wall},
     }
     if extras:
+        if "inproc_multi_gpu" in extras:
+            line["inproc_multi_gpu"] = extras["inproc_multi_gpu"]
         line["strong_scaling"] = extras["strong_scaling"]
         line["hc_cv"] = extras["hc_cv"]
         line["hc_cv_s_per_iter"] = extras["hc_cv"].get("hc_cv_s_per_iter_mean")
@@ -425,6 +430,53 @@ def strong_scaling_leg(args, ctx, cpd, world, rank, barrier, reduce_max, pbn, pa
             "n_gpus": world, "workload": "one %d x %d CKDE slogl sharded by pybnesian_b200.parallel" % (args.n_train, args.n_test),
             "slogl_sharded": s_sharded, "slogl_single_gpu": s_single, "rel_diff": rel,
             "timer": "host wall clock around the blocking API calls, max over ranks"}
+
+
+def inproc_leg(args, world, rank, s_single):
+    """The same two workloads from ONE process over all N GPUs (pbn_ctx_create_multi: replicated tables and models,
+    test rows / (candidate, fold) jobs split over the devices by one host thread each, scalars added on the host) - how
+    a user of the reference, which is single-process by construction, gets the whole box.  Rank 0 runs it; the other
+    ranks wait on the rendezvous store (host side: no NCCL kernel spins on their GPUs meanwhile)."""
+    import datetime
+    import torch.distributed as dist
+    store = dist.distributed_c10d._get_default_store()
+    if rank != 0:
+        store.wait(["pbn_inproc_done"], datetime.timedelta(seconds=1200))
+        return None
+    import pybnesian_b200 as pbn
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import hc_bench
+    out = {"n_gpus": world}
+    prev = pbn.default_context()
+    try:
+        ctx = pbn.set_default_context(pbn.Context(list(range(world))))
+        train, frame = pbn.DataFrame(gen(args.n_train, 0)), pbn.DataFrame(gen(args.n_test, 1))
+        cpd = pbn.CKDE("d", ["a", "b", "c"])
+        cpd.fit(train)
+        s = cpd.slogl(frame)
+        ctx.synchronize()
+        n = 3
+        t0 = time.perf_counter()
+        for _ in range(n):
+            s = cpd.slogl(frame)
+        ctx.synchronize()
+        dt = time.perf_counter() - t0
+        rel = abs(s - s_single) / abs(s_single)
+        assert rel < 1e-12, ("in-process multi-GPU slogl differs from the single-GPU one", s, s_single)
+        out["strong_scaling"] = {"value": 2.0 * args.n_train * args.n_test * n / dt, "unit": UNIT, "ms_per_step": 1e3 * dt / n,
+                                 "steps": n, "slogl": s, "rel_diff_vs_single_gpu": rel,
+                                 "workload": "one %d x %d CKDE slogl, one process, %d devices" % (args.n_train, args.n_test, world)}
+        r = hc_bench.run(100_000, 20, 0, 4)
+        import hashlib
+        out["hc_cv"] = {"hc_cv_s_per_iter_mean": r["hc_cv_s_per_iter_mean"], "iterations": r["iterations"],
+                        "cache_scores_s": r["cache_scores_s"], "total_s": r["total_s"],
+                        "operators_sha1": hashlib.sha1("\n".join(r["operators"]).encode()).hexdigest()}
+    except Exception as ex:  # reported, never fatal for the headline measurement
+        out["error"] = "%s: %s" % (type(ex).__name__, ex)
+    finally:
+        pbn.set_default_context(prev)
+        store.set("pbn_inproc_done", "1")
+    return out
 
 
 def hc_leg(world):

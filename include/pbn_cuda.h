@@ -60,6 +60,19 @@ int pbn_device_count(int* out);
 /* Replaces opencl::OpenCLConfig::get() (opencl/opencl_config.cpp:149-220): one context
  * per GPU instead of a process-wide platform-0/device-0 singleton. */
 int pbn_ctx_create(int device, pbn_ctx** out);
+/* One context over n GPUs of THIS process (the form SURVEY.md 8b sketches).  The reference is driven from a single
+ * process and a single device (opencl/opencl_config.hpp:120-121, opencl_config.cpp:217-220); with this context the same
+ * single-process caller uses every listed B200: tables, fitted KDEs / CKDEs, pbn_cv and pbn_ucv objects created through
+ * it hold one replica per device (uploaded over each device's own PCIe link in parallel), and
+ *   pbn_kde_logl / pbn_ckde_cdf   shard the test rows (contiguous ranges, training set replicated),
+ *   pbn_cv_scores / _score_jobs   deal the (candidate, fold) jobs, most expensive first,
+ *   pbn_ucv_score / _pair_sums    cut the pair-tile schedule once more per device,
+ * one host thread per device; per-device scalars are added on the host in device order, so a result depends on the
+ * number of devices (last-bit rounding of the partial sums) but not on timing.  There is no device-to-device traffic.
+ * Every other entry point runs on devices[0].  Small calls stay on devices[0] as well. */
+int pbn_ctx_create_multi(const int* devices, int n, pbn_ctx** out);
+int pbn_ctx_num_devices(pbn_ctx* ctx);
+int pbn_ctx_device(pbn_ctx* ctx, int i); /* CUDA ordinal of the i-th device of the context, -1 if out of range */
 int pbn_ctx_destroy(pbn_ctx* ctx);
 /* Use an externally owned cudaStream_t (e.g. torch's current stream); NULL restores the own stream. */
 int pbn_ctx_set_stream(pbn_ctx* ctx, void* cuda_stream);
@@ -217,6 +230,13 @@ typedef struct pbn_cv_item {
  * pbn_last_error() holds the message of the first failed item. */
 int pbn_cv_scores(pbn_ctx* ctx, pbn_cv* cv, const pbn_cv_item* items, int n_items, int fold_begin, int fold_end,
                   double* scores, int* status);
+/* The same scores one fold at a time: job j = fold job_fold[j] of items[job_item[j]], job_scores[j] = slogl of that
+ * fold alone (the summand of cv_likelihood.cpp:19-23).  This is the unit the multi-GPU paths deal: a caller that owns a
+ * subset of the (candidate, fold) jobs of a hill-climbing step (one rank of a torchrun job, pybnesian_b200/scores.py)
+ * scores exactly that subset in ONE batched launch per family size, and a multi-device context splits any job list
+ * over its devices.  The caller adds the folds of an item in fold order. */
+int pbn_cv_score_jobs(pbn_ctx* ctx, pbn_cv* cv, const pbn_cv_item* items, int n_items, const int32_t* job_item,
+                      const int32_t* job_fold, int n_jobs, double* job_scores, int* status);
 
 /* ---- hybrid factors: one base factor per configuration of the discrete parents -----------------------
  * factors::discrete::discrete_slice_indices (factors/discrete/discrete_indices.cpp:166-201) with

@@ -4,7 +4,7 @@ log-likelihood hot path behind the reference's Python API.
 Same class names as `pybnesian` for the path: KDE, CKDE, CKDEType, BandwidthSelector,
 NormalReferenceRule, ScottsBandwidth, SingularCovarianceData, ...
 """
-from ._lib import SingularCovarianceData, Context, default_context, LIB_PATH
+from ._lib import SingularCovarianceData, Context, default_context, set_default_context, LIB_PATH
 from .dataset import DataFrame, CrossValidation, HoldOut
 from .kde import BandwidthSelector, NormalReferenceRule, ScottsBandwidth, UCV, UCVScorer, KDE, ProductKDE
 from .factors import (Factor, FactorType, CKDE, CKDEType, LinearGaussianCPD, LinearGaussianCPDType,

@@ -16,7 +16,8 @@ PBN_F64, PBN_F32 = 0, 1
 BW_NORMAL_REFERENCE, BW_SCOTT = 0, 1
 
 EXPORTS = [
-    "pbn_last_error", "pbn_version", "pbn_device_count", "pbn_ctx_create", "pbn_ctx_destroy", "pbn_ctx_set_stream",
+    "pbn_last_error", "pbn_version", "pbn_device_count", "pbn_ctx_create", "pbn_ctx_create_multi", "pbn_ctx_num_devices",
+    "pbn_ctx_device", "pbn_cv_score_jobs", "pbn_ctx_destroy", "pbn_ctx_set_stream",
     "pbn_ctx_stream", "pbn_ctx_synchronize", "pbn_ctx_sm_count", "pbn_ctx_counters", "pbn_table_upload",
     "pbn_table_free", "pbn_table_rows", "pbn_table_cols", "pbn_table_download", "pbn_table_moments", "pbn_bandwidth",
     "pbn_diag_bandwidth", "pbn_kde_fit", "pbn_ckde_fit", "pbn_product_kde_fit", "pbn_kde_free", "pbn_kde_num_instances", "pbn_kde_lognorm",
@@ -73,6 +74,9 @@ def lib():
         L.pbn_version.restype = ctypes.c_char_p
         L.pbn_device_count.argtypes = [ip]
         L.pbn_ctx_create.argtypes = [ci, ctypes.POINTER(vp)]
+        L.pbn_ctx_create_multi.argtypes = [ip, ci, ctypes.POINTER(vp)]
+        L.pbn_ctx_num_devices.argtypes = [vp]
+        L.pbn_ctx_device.argtypes = [vp, ci]
         L.pbn_ctx_destroy.argtypes = [vp]
         L.pbn_ctx_set_stream.argtypes = [vp, vp]
         L.pbn_ctx_stream.argtypes = [vp]
@@ -124,6 +128,7 @@ def lib():
         L.pbn_cv_folds.argtypes = [vp]
         L.pbn_cv_train_moments.argtypes = [vp, ci, ip, ci, dp, dp]
         L.pbn_cv_scores.argtypes = [vp, vp, ctypes.POINTER(CVItem), ci, ci, ci, dp, ip]
+        L.pbn_cv_score_jobs.argtypes = [vp, vp, ctypes.POINTER(CVItem), ci, i32p, i32p, ci, dp, ip]
         L.pbn_sort_desc.argtypes = [i32p, i64, dp]
         L.pbn_intset_new.argtypes = [ctypes.POINTER(vp)]
         L.pbn_intset_clone.argtypes = [vp, ctypes.POINTER(vp)]
@@ -169,12 +174,31 @@ def check(rc):
 
 
 class Context:
-    """One GPU (pbn_ctx).  The default context uses device PBN_CUDA_DEVICE, else LOCAL_RANK, else 0."""
+    """One GPU (pbn_ctx) or, with a list of devices, one context over several GPUs of this process
+    (pbn_ctx_create_multi): tables and fitted models are then replicated and logl / cdf / CV scores / UCV shard over
+    all of them without torchrun.
+
+    The default context is chosen from the environment:
+      PBN_CUDA_DEVICES=0,1,2 | all   the listed (all visible) devices in ONE context
+      PBN_CUDA_DEVICE=k              device k only (what bench.py and every torchrun rank set)
+      LOCAL_RANK=k (torchrun)        device k only: one process per GPU, pybnesian_b200.parallel sums the scalars
+      nothing set                    every visible device in one context
+    """
 
     def __init__(self, device=0):
         self.handle = ctypes.c_void_p()
-        check(lib().pbn_ctx_create(int(device), ctypes.byref(self.handle)))
-        self.device = int(device)
+        if isinstance(device, (list, tuple)):
+            devs = [int(d) for d in device]
+            check(lib().pbn_ctx_create_multi(int_array(devs), len(devs), ctypes.byref(self.handle)))
+            self.devices = devs
+        else:
+            check(lib().pbn_ctx_create(int(device), ctypes.byref(self.handle)))
+            self.devices = [int(device)]
+        self.device = self.devices[0]
+
+    @property
+    def num_devices(self):
+        return len(self.devices)
 
     def synchronize(self):
         check(lib().pbn_ctx_synchronize(self.handle))
@@ -219,12 +243,37 @@ class Context:
 _default_ctx = None
 
 
+def _default_devices():
+    env = os.environ
+    spec = env.get("PBN_CUDA_DEVICES")
+    if spec:
+        if spec.strip().lower() == "all":
+            n = ctypes.c_int()
+            check(lib().pbn_device_count(ctypes.byref(n)))
+            return list(range(n.value))
+        return [int(x) for x in spec.split(",") if x.strip() != ""]
+    if "PBN_CUDA_DEVICE" in env:
+        return [int(env["PBN_CUDA_DEVICE"])]
+    if "LOCAL_RANK" in env:
+        return [int(env["LOCAL_RANK"])]
+    n = ctypes.c_int()
+    check(lib().pbn_device_count(ctypes.byref(n)))
+    return list(range(max(n.value, 1)))
+
+
 def default_context():
     global _default_ctx
     if _default_ctx is None:
-        dev = int(os.environ.get("PBN_CUDA_DEVICE", os.environ.get("LOCAL_RANK", "0")))
-        _default_ctx = Context(dev)
+        devs = _default_devices()
+        _default_ctx = Context(devs if len(devs) > 1 else devs[0])
     return _default_ctx
+
+
+def set_default_context(ctx):
+    """Replace the process-wide default context (e.g. `Context([0, 1, 2, 3])`); objects created earlier keep theirs."""
+    global _default_ctx
+    _default_ctx = ctx
+    return ctx
 
 
 def int_array(values):

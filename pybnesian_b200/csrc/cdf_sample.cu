@@ -600,7 +600,25 @@ void sample_host_multivariate(const T* gathered /* [d][n]: variable, evidence.. 
 
 extern "C" {
 
+static int ckde_cdf_one(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const int* cols, pbn_rows rows, double* out);
+
 int pbn_ckde_cdf(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const int* cols, pbn_rows rows, double* out) {
+    if (!ctx || !out) return set_error(PBN_ERR_ARG, "null argument");
+    const int nd = pbn_num_devices(ctx);
+    const int64_t m = (test && rows.e0 >= rows.b0 && rows.e1 >= rows.b1) ? seg_count(rows) : 0;
+    if (!k || !pbn_replicated(ctx, k) || !pbn_replicated(ctx, test) || m < (int64_t)2048 * nd || (double)k->n * (double)m < 1.0e9 * nd)
+        return ckde_cdf_one(ctx, k, test, cols, rows, out);
+    PBN_TRY(check_cols(test, cols, k->d));
+    PBN_TRY(check_rows(test, rows));
+    // multi-device context: contiguous shards of the test rows against the replicated model (as pbn_kde_logl)
+    return pbn_run_on_devices(nd, [&](int i) {
+        const int64_t b = m * i / nd, e = m * (i + 1) / nd;
+        return ckde_cdf_one(pbn_device_ctx(ctx, i), pbn_replica(const_cast<pbn_kde*>(k), i), pbn_replica(const_cast<pbn_table*>(test), i),
+                            cols, pbn_sub_rows(rows, b, e), out + b);
+    });
+}
+
+static int ckde_cdf_one(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const int* cols, pbn_rows rows, double* out) {
     if (!ctx || !out) return set_error(PBN_ERR_ARG, "null argument");
     PBN_TRY(check_ckde(k));
     PBN_TRY(check_cols(test, cols, k->d));

@@ -26,6 +26,7 @@
 using pbn::PairJob;
 
 struct pbn_cv {
+    std::vector<pbn_cv*> rep;  // replicas on ctx->peers (multi-device context): the (item, fold) jobs are dealt over them
     pbn_ctx* ctx = nullptr;
     pbn_table* tbl = nullptr;  // shuffled-order copy (owned)
     int k = 0;
@@ -380,8 +381,31 @@ struct CkdeJobHost {
 
 extern "C" {
 
+static int cv_create_one(pbn_ctx* ctx, const pbn_table* tbl, const int32_t* indices, int64_t n, const int32_t* limits, int k,
+                         pbn_cv** out);
+
 int pbn_cv_create(pbn_ctx* ctx, const pbn_table* tbl, const int32_t* indices, int64_t n, const int32_t* limits, int k,
                   pbn_cv** out) {
+    if (!ctx || !tbl || !indices || !limits || !out) return set_error(PBN_ERR_ARG, "null argument");
+    if (!pbn_replicated(ctx, tbl)) return cv_create_one(ctx, tbl, indices, n, limits, k, out);
+    // multi-device context: the shuffled-order table (16 MB at config 4) and the fold statistics on every device
+    const int nd = pbn_num_devices(ctx);
+    std::vector<pbn_cv*> c(nd, nullptr);
+    int rc = pbn_run_on_devices(nd, [&](int i) {
+        return cv_create_one(pbn_device_ctx(ctx, i), pbn_replica(const_cast<pbn_table*>(tbl), i), indices, n, limits, k, &c[i]);
+    });
+    if (rc != PBN_OK) {
+        for (pbn_cv* q : c)
+            if (q) pbn_cv_free(q);
+        return rc;
+    }
+    c[0]->rep.assign(c.begin() + 1, c.end());
+    *out = c[0];
+    return PBN_OK;
+}
+
+static int cv_create_one(pbn_ctx* ctx, const pbn_table* tbl, const int32_t* indices, int64_t n, const int32_t* limits, int k,
+                         pbn_cv** out) {
     if (!ctx || !tbl || !indices || !limits || !out) return set_error(PBN_ERR_ARG, "null argument");
     if (k < 1 || n < 1) return set_error(PBN_ERR_ARG, "invalid fold structure");
     if (limits[0] != 0 || limits[k] != n) return set_error(PBN_ERR_ARG, "fold limits must span [0, n]");
@@ -552,6 +576,8 @@ int pbn_cv_create(pbn_ctx* ctx, const pbn_table* tbl, const int32_t* indices, in
 
 int pbn_cv_free(pbn_cv* cv) {
     if (!cv) return PBN_OK;
+    for (pbn_cv* r : cv->rep) pbn_cv_free(r);
+    cv->rep.clear();
     DevSetter ds(cv->ctx->device);
     if (cv->tbl) {
         if (cv->tbl->data) cudaFreeAsync(cv->tbl->data, cv->ctx->stream);
@@ -612,9 +638,15 @@ int fold_bandwidth(const pbn_cv* cv, int f, const int* vars, int d, int rule, in
     return PBN_OK;
 }
 
-// scores the CKDE items `sel` (all with the same number of variables d <= kMaxFast) over folds [f0, f1)
-int score_ckde_group(pbn_ctx* ctx, pbn_cv* cv, const pbn_cv_item* items, const std::vector<int>& sel, int d, int f0, int f1,
-                     double* scores, int* status, std::string* first_error) {
+struct CvJob {
+    int item, fold;
+};
+
+// scores the CKDE (item, fold) jobs `jobs[sel[.]]` (all items with the same number of variables d <= kMaxFast): ONE
+// whitening launch and ONE multi-job pair-kernel launch per chunk of jobs; job_scores[sel[q]] = slogl of that fold
+int score_ckde_jobs(pbn_ctx* ctx, pbn_cv* cv, const pbn_cv_item* items, const CvJob* jobs, const std::vector<int>& sel, int d,
+                    double* job_scores, int* status, std::string* first_error) {
+    DevSetter ds(ctx->device);
     cudaStream_t st = ctx->stream;
     const pbn_table* tbl = cv->tbl;
     const bool f64 = tbl->dtype == PBN_F64;
@@ -622,7 +654,6 @@ int score_ckde_group(pbn_ctx* ctx, pbn_cv* cv, const pbn_cv_item* items, const s
     const bool ckde = d >= 2;
     const int TILE = f64 ? pbn::pair_tile_f64(d) : pbn::pair_tile_f32(d);
     const int TB = f64 ? pbn::pair_tb_for_f64(d, ckde) : pbn::pair_tb_for_f32(d, ckde);
-    const int nfold = f1 - f0;
     const double unit = unit_scale(tbl->dtype);
     const double cscale = sqrt(0.5 * unit);
     const double log2pi = 1.8378770664093454836;
@@ -635,12 +666,18 @@ int score_ckde_group(pbn_ctx* ctx, pbn_cv* cv, const pbn_cv_item* items, const s
         return a + b;
     };
     const size_t budget = (size_t)3 << 30;  // whitened-row scratch per chunk
-    size_t per_item = 0;
-    for (int f = f0; f < f1; ++f) per_item += job_bytes(cv->n - (cv->limits[f + 1] - cv->limits[f]), cv->limits[f + 1] - cv->limits[f]);
-    int items_per_chunk = (int)std::max<size_t>(1, budget / std::max<size_t>(per_item, 1));
 
-    for (size_t c0 = 0; c0 < sel.size(); c0 += items_per_chunk) {
-        size_t c1 = std::min(sel.size(), c0 + items_per_chunk);
+    for (size_t c0 = 0; c0 < sel.size();) {
+        // a chunk: as many consecutive jobs as fit the scratch budget (at least one)
+        size_t c1 = c0, bytes = 0;
+        while (c1 < sel.size()) {
+            const int f = jobs[sel[c1]].fold;
+            const int64_t m = cv->limits[f + 1] - cv->limits[f];
+            const size_t jb = job_bytes(cv->n - m, m);
+            if (c1 > c0 && bytes + jb > budget) break;
+            bytes += jb;
+            ++c1;
+        }
         std::vector<WhitenJob> wj;
         std::vector<PairJob> pj;
         std::vector<FinJob> fj;
@@ -649,14 +686,15 @@ int score_ckde_group(pbn_ctx* ctx, pbn_cv* cv, const pbn_cv_item* items, const s
         size_t ybytes = 0;
         long long out_total = 0;
         for (size_t q = c0; q < c1; ++q) {
-            const int it = sel[q];
+            const int jid = sel[q];
+            const int it = jobs[jid].item, f = jobs[jid].fold;
             const pbn_cv_item& item = items[it];
+            if (status[it] != PBN_OK) continue;  // an earlier fold of this item already failed
             // internal order: variable last, so that the marginal's whitened coordinates are a prefix of the joint's
             int vars[kMaxFast], pvars[kMaxFast];
             for (int i = 0; i < d; ++i) vars[i] = item.vars[i];
             for (int i = 0; i < d; ++i) pvars[i] = ckde ? vars[(i + 1) % d] : vars[i];
-            size_t first_job = hj.size();
-            for (int f = f0; f < f1; ++f) {
+            {
                 const int64_t m = cv->limits[f + 1] - cv->limits[f];
                 int64_t ntr;
                 double mean[kMaxFast], H[kMaxFast * kMaxFast], L[kMaxFast * kMaxFast], Winv[kMaxFast * kMaxFast];
@@ -665,10 +703,7 @@ int score_ckde_group(pbn_ctx* ctx, pbn_cv* cv, const pbn_cv_item* items, const s
                 if (rc != PBN_OK) {
                     status[it] = rc;
                     if (first_error->empty()) *first_error = pbn_last_error();
-                    // drop the jobs of this item that were already queued
-                    wj.resize(first_job); pj.resize(first_job); fj.resize(first_job); hj.resize(first_job);
-                    y_off_train.resize(first_job); y_off_test.resize(first_job);
-                    break;
+                    continue;
                 }
                 if (m == 0) continue;  // an empty test fold adds 0
                 tri_inverse_rowmajor(L, d, Winv);
@@ -687,7 +722,7 @@ int score_ckde_group(pbn_ctx* ctx, pbn_cv* cv, const pbn_cv_item* items, const s
                     if (i < d - 1) slog_m += log(L[i + i * d]);
                 }
                 CkdeJobHost h;
-                h.item = it;
+                h.item = jid;  // position in `jobs`: where the fold's slogl goes
                 h.fold = f;
                 h.n_train = ntr;
                 h.m = m;
@@ -712,6 +747,7 @@ int score_ckde_group(pbn_ctx* ctx, pbn_cv* cv, const pbn_cv_item* items, const s
                 pj.push_back(p);
             }
         }
+        c0 = c1;
         // out offsets are recomputed here because failed items may have removed jobs
         const int J = (int)hj.size();
         if (J == 0) continue;
@@ -830,80 +866,149 @@ int score_ckde_group(pbn_ctx* ctx, pbn_cv* cv, const pbn_cv_item* items, const s
         ctx->d2h += (int64_t)J * 8 + 4;
         ctx->last_fallback_rows = nflag;
         PBN_CUDA_TRY(cudaFreeAsync(base, st));
-        // CVLikelihood::local_score: loglik += slogl(fold) in fold order (cv_likelihood.cpp:19-23)
-        for (int j = 0; j < J; ++j) scores[hj[j].item] += sums[j];
+        for (int j = 0; j < J; ++j) job_scores[hj[j].item] = sums[j];
     }
-    (void)nfold;
     return PBN_OK;
 }
 
 }  // namespace
 
-extern "C" int pbn_cv_scores(pbn_ctx* ctx, pbn_cv* cv, const pbn_cv_item* items, int n_items, int fold_begin, int fold_end,
-                             double* scores, int* status) {
-    if (!ctx || !cv || (n_items > 0 && (!items || !scores))) return set_error(PBN_ERR_ARG, "null argument");
-    if (fold_begin < 0 || fold_end > cv->k || fold_begin >= fold_end) return set_error(PBN_ERR_ARG, "fold range out of bounds");
+// One fold of one item, the unit everything below is scheduled in.  LinearGaussianCPD jobs are closed forms of the fold
+// statistics (host); CKDE jobs of families up to kMaxFast variables are grouped by family size and batched
+// (score_ckde_jobs); wider CKDEs take one fit + slogl per fold through the single-model entry points.
+// Multi-device context: the batched CKDE jobs are dealt over the devices most expensive first (cost = training rows x
+// test rows x variables), every device runs its share as its own batch on its replica of the shuffled table, from one
+// host thread per device.  Each job's value is produced by exactly one device.
+extern "C" int pbn_cv_score_jobs(pbn_ctx* ctx, pbn_cv* cv, const pbn_cv_item* items, int n_items, const int32_t* job_item,
+                                 const int32_t* job_fold, int n_jobs, double* job_scores, int* status) {
+    if (!ctx || !cv || (n_items > 0 && !items) || (n_jobs > 0 && (!job_item || !job_fold || !job_scores)))
+        return set_error(PBN_ERR_ARG, "null argument");
     DevSetter ds(ctx->device);
     std::vector<int> st_local(n_items, PBN_OK);
     int* stat = status ? status : st_local.data();
-    std::string first_error;
-    std::vector<std::vector<int>> groups(kMaxFast + 1);
-    std::vector<int> slow;
     for (int i = 0; i < n_items; ++i) {
         const pbn_cv_item& it = items[i];
-        scores[i] = 0.0;
         stat[i] = PBN_OK;
         if (it.n_vars < 1 || it.n_vars > PBN_MAX_DIM) return set_error(PBN_ERR_UNSUPPORTED, "number of variables must be in [1, 32]");
         PBN_TRY(check_cols(cv->tbl, it.vars, it.n_vars));
+        if (it.factor != PBN_FACTOR_LINEAR_GAUSSIAN && it.factor != PBN_FACTOR_CKDE) return set_error(PBN_ERR_ARG, "unknown factor type");
+    }
+    std::string first_error;
+    std::vector<CvJob> jobs(n_jobs);
+    std::vector<std::vector<int>> groups(kMaxFast + 1);
+    std::vector<int> slow;
+    for (int j = 0; j < n_jobs; ++j) {
+        jobs[j].item = job_item[j];
+        jobs[j].fold = job_fold[j];
+        job_scores[j] = 0.0;
+        if (jobs[j].item < 0 || jobs[j].item >= n_items) return set_error(PBN_ERR_ARG, "job refers to an item out of range");
+        if (jobs[j].fold < 0 || jobs[j].fold >= cv->k) return set_error(PBN_ERR_ARG, "fold range out of bounds");
+        const pbn_cv_item& it = items[jobs[j].item];
         if (it.factor == PBN_FACTOR_LINEAR_GAUSSIAN) {
             // fit on the fold's training rows and slogl on its test rows, both from the fold statistics
             const int d = it.n_vars, p = d - 1;
             std::vector<double> mean(d), Cm((size_t)d * d), beta(d);
-            double tot = 0;
-            for (int f = fold_begin; f < fold_end; ++f) {
-                int64_t ntr;
-                train_moments(cv, f, it.vars, d, &ntr, mean.data(), Cm.data());
-                if (ntr < 1) return set_error(PBN_ERR_ARG, "empty training fold");
-                double var = lg_fit_from_moments(ntr, p, mean.data(), Cm.data(), beta.data());
-                tot += lg_fold_slogl(cv, f, it.vars, p, beta.data(), var);
-            }
-            scores[i] = tot;
-        } else if (it.factor == PBN_FACTOR_CKDE) {
-            if (it.n_vars <= kMaxFast) groups[it.n_vars].push_back(i);
-            else slow.push_back(i);
+            int64_t ntr;
+            train_moments(cv, jobs[j].fold, it.vars, d, &ntr, mean.data(), Cm.data());
+            if (ntr < 1) return set_error(PBN_ERR_ARG, "empty training fold");
+            double var = lg_fit_from_moments(ntr, p, mean.data(), Cm.data(), beta.data());
+            job_scores[j] = lg_fold_slogl(cv, jobs[j].fold, it.vars, p, beta.data(), var);
+        } else if (it.n_vars <= kMaxFast) {
+            groups[it.n_vars].push_back(j);
         } else {
-            return set_error(PBN_ERR_ARG, "unknown factor type");
+            slow.push_back(j);
         }
     }
+    // ---- batched CKDE jobs ----
+    const int nd = pbn_num_devices(ctx);
+    double total_cost = 0;
+    auto job_cost = [&](int j) {
+        const int f = jobs[j].fold;
+        const double m = (double)(cv->limits[f + 1] - cv->limits[f]);
+        return ((double)cv->n - m) * m * items[jobs[j].item].n_vars;
+    };
     for (int d = 1; d <= kMaxFast; ++d)
-        if (!groups[d].empty())
-            PBN_TRY(score_ckde_group(ctx, cv, items, groups[d], d, fold_begin, fold_end, scores, stat, &first_error));
+        for (int j : groups[d]) total_cost += job_cost(j);
+    if (nd > 1 && pbn_replicated(ctx, cv) && total_cost >= 4.0e9 * nd) {
+        // deal: most expensive first (ties by position), round-robin; a device keeps its jobs in their original order
+        std::vector<int> order;
+        for (int d = 1; d <= kMaxFast; ++d) order.insert(order.end(), groups[d].begin(), groups[d].end());
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+            const double ca = job_cost(a), cb = job_cost(b);
+            return ca != cb ? ca > cb : a < b;
+        });
+        std::vector<std::vector<std::vector<int>>> mine(nd, std::vector<std::vector<int>>(kMaxFast + 1));
+        for (size_t pos = 0; pos < order.size(); ++pos) mine[pos % nd][items[jobs[order[pos]].item].n_vars].push_back(order[pos]);
+        std::vector<std::vector<int>> dev_stat(nd, std::vector<int>(n_items, PBN_OK));
+        std::vector<std::string> dev_err(nd);
+        int rc = pbn_run_on_devices(nd, [&](int i) {
+            for (int d = 1; d <= kMaxFast; ++d) {
+                std::sort(mine[i][d].begin(), mine[i][d].end());
+                if (mine[i][d].empty()) continue;
+                PBN_TRY(score_ckde_jobs(pbn_device_ctx(ctx, i), pbn_replica(cv, i), items, jobs.data(), mine[i][d], d, job_scores,
+                                        dev_stat[i].data(), &dev_err[i]));
+            }
+            return PBN_OK;
+        });
+        if (rc != PBN_OK) return rc;
+        int64_t fb = 0;
+        for (int i = 0; i < nd; ++i) {
+            fb += pbn_device_ctx(ctx, i)->last_fallback_rows;
+            for (int q = 0; q < n_items; ++q)
+                if (stat[q] == PBN_OK && dev_stat[i][q] != PBN_OK) stat[q] = dev_stat[i][q];
+            if (first_error.empty() && !dev_err[i].empty()) first_error = dev_err[i];
+        }
+        ctx->last_fallback_rows = fb;
+    } else {
+        for (int d = 1; d <= kMaxFast; ++d)
+            if (!groups[d].empty()) PBN_TRY(score_ckde_jobs(ctx, cv, items, jobs.data(), groups[d], d, job_scores, stat, &first_error));
+    }
     // wide CKDEs (d > kMaxFast = 10): one fit + slogl per fold through the single-model entry points
-    for (int i : slow) {
+    for (int j : slow) {
+        const int i = jobs[j].item, f = jobs[j].fold;
+        if (stat[i] != PBN_OK) continue;
         const pbn_cv_item& it = items[i];
         const int d = it.n_vars;
-        double tot = 0;
-        for (int f = fold_begin; f < fold_end; ++f) {
-            std::vector<double> mean(d), H((size_t)d * d);
-            int64_t ntr;
-            int rc = fold_bandwidth(cv, f, it.vars, d, it.rule, &ntr, mean.data(), H.data());
-            pbn_kde* kde = nullptr;
-            pbn_rows tr = {0, cv->limits[f], cv->limits[f + 1], cv->n};
-            pbn_rows te = {cv->limits[f], cv->limits[f + 1], 0, 0};
-            if (rc == PBN_OK) rc = pbn_ckde_fit(ctx, cv->tbl, it.vars, d, tr, H.data(), &kde);
-            double s = 0;
-            if (rc == PBN_OK) rc = pbn_kde_logl(ctx, kde, cv->tbl, it.vars, te, nullptr, &s);
-            if (kde) pbn_kde_free(kde);
-            if (rc == PBN_ERR_CUDA) return rc;
-            if (rc != PBN_OK) {
-                stat[i] = rc;
-                if (first_error.empty()) first_error = pbn_last_error();
-                break;
-            }
-            tot += s;
+        std::vector<double> mean(d), H((size_t)d * d);
+        int64_t ntr;
+        int rc = fold_bandwidth(cv, f, it.vars, d, it.rule, &ntr, mean.data(), H.data());
+        pbn_kde* kde = nullptr;
+        pbn_rows tr = {0, cv->limits[f], cv->limits[f + 1], cv->n};
+        pbn_rows te = {cv->limits[f], cv->limits[f + 1], 0, 0};
+        if (rc == PBN_OK) rc = pbn_ckde_fit(ctx, cv->tbl, it.vars, d, tr, H.data(), &kde);
+        double sc = 0;
+        if (rc == PBN_OK) rc = pbn_kde_logl(ctx, kde, cv->tbl, it.vars, te, nullptr, &sc);
+        if (kde) pbn_kde_free(kde);
+        if (rc == PBN_ERR_CUDA) return rc;
+        if (rc != PBN_OK) {
+            stat[i] = rc;
+            if (first_error.empty()) first_error = pbn_last_error();
+            continue;
         }
-        scores[i] = tot;
+        job_scores[j] = sc;
     }
     if (!first_error.empty()) set_error(PBN_ERR_SINGULAR, first_error);  // message of the first failed item
+    return PBN_OK;
+}
+
+extern "C" int pbn_cv_scores(pbn_ctx* ctx, pbn_cv* cv, const pbn_cv_item* items, int n_items, int fold_begin, int fold_end,
+                             double* scores, int* status) {
+    if (!ctx || !cv || (n_items > 0 && (!items || !scores))) return set_error(PBN_ERR_ARG, "null argument");
+    if (fold_begin < 0 || fold_end > cv->k || fold_begin >= fold_end) return set_error(PBN_ERR_ARG, "fold range out of bounds");
+    const int nf = fold_end - fold_begin;
+    std::vector<int32_t> ji((size_t)n_items * nf), jf((size_t)n_items * nf);
+    for (int i = 0; i < n_items; ++i)
+        for (int q = 0; q < nf; ++q) {
+            ji[(size_t)i * nf + q] = i;
+            jf[(size_t)i * nf + q] = fold_begin + q;
+        }
+    std::vector<double> js((size_t)n_items * nf);
+    PBN_TRY(pbn_cv_score_jobs(ctx, cv, items, n_items, ji.data(), jf.data(), n_items * nf, js.data(), status));
+    // CVLikelihood::local_score: loglik += slogl(fold) in fold order (cv_likelihood.cpp:19-23)
+    for (int i = 0; i < n_items; ++i) {
+        double tot = 0;
+        for (int q = 0; q < nf; ++q) tot += js[(size_t)i * nf + q];
+        scores[i] = tot;
+    }
     return PBN_OK;
 }

@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <functional>
 #include <string>
 #include <utility>
 #include <vector>
@@ -37,7 +38,13 @@ int pbn_set_error(int code, const std::string& msg);
 // ------------------------------------------------------------------------------------
 // objects
 // ------------------------------------------------------------------------------------
+// A context drives one GPU.  A MULTI-DEVICE context (pbn_ctx_create_multi) is the context of its first device plus
+// `peers`, the contexts of the others: tables, fitted KDEs, cross-validation objects and UCV scorers created through it
+// carry one replica per peer (`rep[i]` lives on `peers[i]`), and the sharding entry points (pbn_kde_logl, pbn_ckde_cdf,
+// pbn_cv_scores, pbn_ucv_score) split their work over all devices from one host thread per device, adding the
+// per-device scalars in device order.  Everything else runs on the first device as before.
 struct pbn_ctx {
+    std::vector<pbn_ctx*> peers;
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
@@ -55,6 +62,7 @@ struct pbn_ctx {
 };
 
 struct pbn_table {
+    std::vector<pbn_table*> rep;  // replicas on ctx->peers (multi-device context), else empty
     pbn_ctx* ctx;
     int ncols;
     int64_t nrows;
@@ -64,6 +72,7 @@ struct pbn_table {
 };
 
 struct pbn_kde {
+    std::vector<pbn_kde*> rep;  // replicas on ctx->peers
     pbn_ctx* ctx;
     int d;
     int dtype;
@@ -78,6 +87,19 @@ struct pbn_kde {
     double lognorm_joint;
     double lognorm_marg;
 };
+
+// ---- multi-device helpers (runtime.cu) ----
+static inline int pbn_num_devices(const pbn_ctx* c) { return 1 + (int)c->peers.size(); }
+static inline pbn_ctx* pbn_device_ctx(pbn_ctx* c, int i) { return i == 0 ? c : c->peers[i - 1]; }
+template <typename Obj>
+static inline Obj* pbn_replica(Obj* o, int i) { return i == 0 ? o : o->rep[i - 1]; }
+template <typename Obj>
+static inline bool pbn_replicated(const pbn_ctx* c, const Obj* o) { return !c->peers.empty() && o && o->rep.size() == c->peers.size(); }
+// fn(i) for i = 0 .. n-1 on one host thread per device (i = 0 on the caller's); the first failure (lowest i) is returned
+// and becomes the caller's pbn_last_error()
+int pbn_run_on_devices(int n, const std::function<int(int)>& fn);
+// rows [begin, end) of the virtual row order of a two-segment range
+pbn_rows pbn_sub_rows(const pbn_rows& r, int64_t begin, int64_t end);
 
 static inline size_t elem_size(int dtype) { return dtype == PBN_F64 ? 8 : 4; }
 static inline int64_t seg_count(const pbn_rows& r) { return (r.e0 - r.b0) + (r.e1 - r.b1); }

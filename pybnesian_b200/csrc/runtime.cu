@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "internal.h"
@@ -24,6 +25,48 @@ static thread_local std::string g_last_error;
 int pbn_set_error(int code, const std::string& msg) {
     g_last_error = msg;
     return code;
+}
+
+// ------------------------------------------------------------------------------------
+// multi-device plumbing
+// ------------------------------------------------------------------------------------
+int pbn_run_on_devices(int n, const std::function<int(int)>& fn) {
+    if (n <= 1) return fn(0);
+    std::vector<int> rc(n, PBN_OK);
+    std::vector<std::string> msg(n);
+    std::vector<std::thread> th;
+    th.reserve(n - 1);
+    for (int i = 1; i < n; ++i)
+        th.emplace_back([&, i] {
+            rc[i] = fn(i);
+            if (rc[i] != PBN_OK) msg[i] = pbn_last_error();  // thread-local in the worker
+        });
+    rc[0] = fn(0);
+    if (rc[0] != PBN_OK) msg[0] = pbn_last_error();
+    for (auto& t : th) t.join();
+    for (int i = 0; i < n; ++i)
+        if (rc[i] != PBN_OK) return set_error(rc[i], msg[i]);
+    return PBN_OK;
+}
+
+pbn_rows pbn_sub_rows(const pbn_rows& r, int64_t begin, int64_t end) {
+    const int64_t n0 = r.e0 - r.b0;
+    pbn_rows o = {0, 0, 0, 0};
+    if (begin < n0) {
+        o.b0 = r.b0 + begin;
+        o.e0 = r.b0 + std::min(end, n0);
+    }
+    if (end > n0) {
+        const int64_t b = std::max<int64_t>(begin, n0) - n0, e = end - n0;
+        if (o.e0 > o.b0) {
+            o.b1 = r.b1 + b;
+            o.e1 = r.b1 + e;
+        } else {
+            o.b0 = r.b1 + b;
+            o.e0 = r.b1 + e;
+        }
+    }
+    return o;
 }
 
 // ------------------------------------------------------------------------------------
@@ -693,7 +736,30 @@ double unit_scale(int dtype) {  // kernel exponent units per natural-log unit of
     return dtype == PBN_F64 ? (double)pbn::kExpTab * log2e : log2e;
 }
 
+static int fit_one(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, pbn_rows rows, const double* H, bool ckde,
+                   pbn_kde** out);
+
+// multi-device context: the fitted model is replicated (every device whitens its own copy of the training rows)
 static int fit_impl(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, pbn_rows rows, const double* H,
+                    bool ckde, pbn_kde** out) {
+    if (!ctx || !out) return set_error(PBN_ERR_ARG, "null argument");
+    if (!pbn_replicated(ctx, tbl)) return fit_one(ctx, tbl, cols, d, rows, H, ckde, out);
+    const int nd = pbn_num_devices(ctx);
+    std::vector<pbn_kde*> k(nd, nullptr);
+    int rc = pbn_run_on_devices(nd, [&](int i) {
+        return fit_one(pbn_device_ctx(ctx, i), pbn_replica(const_cast<pbn_table*>(tbl), i), cols, d, rows, H, ckde, &k[i]);
+    });
+    if (rc != PBN_OK) {
+        for (pbn_kde* q : k)
+            if (q) pbn_kde_free(q);
+        return rc;
+    }
+    k[0]->rep.assign(k.begin() + 1, k.end());
+    *out = k[0];
+    return PBN_OK;
+}
+
+static int fit_one(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, pbn_rows rows, const double* H,
                     bool ckde, pbn_kde** out) {
     if (!ctx || !out || !H) return set_error(PBN_ERR_ARG, "null argument");
     PBN_TRY(check_cols(tbl, cols, d));
@@ -772,8 +838,51 @@ struct Scratch {
     }
 };
 
+static int logl_one(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const int* cols, pbn_rows rows,
+                    double* d_out_logl, double* d_out_slogl, double* h_out_logl, double* h_out_slogl);
+
+// rows each device must at least get before a call is sharded (below that one device finishes sooner than the threads start)
+static bool worth_sharding(const pbn_ctx* ctx, int64_t n_train, int64_t m) {
+    const int nd = pbn_num_devices(ctx);
+    return m >= (int64_t)2048 * nd && (double)n_train * (double)m >= 2.0e9 * nd;
+}
+
+// multi-device context, host outputs: contiguous shards of the test rows against the replicated model, one host thread
+// per device; slogl = the per-device sums added in device order (train replicated, test rows sharded)
 int pbn_logl_impl(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const int* cols, pbn_rows rows,
                      double* d_out_logl, double* d_out_slogl, double* h_out_logl, double* h_out_slogl) {
+    if (!ctx || !k) return set_error(PBN_ERR_ARG, "null argument");
+    const int64_t m_all = (test && rows.e0 >= rows.b0 && rows.e1 >= rows.b1) ? seg_count(rows) : 0;
+    if (d_out_logl || d_out_slogl || !pbn_replicated(ctx, k) || !pbn_replicated(ctx, test) || !worth_sharding(ctx, k->n, m_all))
+        return logl_one(ctx, k, test, cols, rows, d_out_logl, d_out_slogl, h_out_logl, h_out_slogl);
+    PBN_TRY(check_cols(test, cols, k->d));
+    PBN_TRY(check_rows(test, rows));
+    const int nd = pbn_num_devices(ctx);
+    std::vector<double> part(nd, 0.0);
+    int rc = pbn_run_on_devices(nd, [&](int i) {
+        const int64_t b = m_all * i / nd, e = m_all * (i + 1) / nd;
+        return logl_one(pbn_device_ctx(ctx, i), pbn_replica(const_cast<pbn_kde*>(k), i), pbn_replica(const_cast<pbn_table*>(test), i),
+                        cols, pbn_sub_rows(rows, b, e), nullptr, nullptr, h_out_logl ? h_out_logl + b : nullptr,
+                        h_out_slogl ? &part[i] : nullptr);
+    });
+    if (rc != PBN_OK) return rc;
+    int64_t fb = 0, rk = 0;
+    for (int i = 0; i < nd; ++i) {
+        fb += pbn_device_ctx(ctx, i)->last_fallback_rows;
+        rk += pbn_device_ctx(ctx, i)->last_row_kernel_rows;
+    }
+    ctx->last_fallback_rows = fb;
+    ctx->last_row_kernel_rows = rk;
+    if (h_out_slogl) {
+        double s = 0;
+        for (int i = 0; i < nd; ++i) s += part[i];
+        *h_out_slogl = s;
+    }
+    return PBN_OK;
+}
+
+static int logl_one(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const int* cols, pbn_rows rows,
+                    double* d_out_logl, double* d_out_slogl, double* h_out_logl, double* h_out_slogl) {
     if (!ctx || !k) return set_error(PBN_ERR_ARG, "null argument");
     PBN_TRY(check_cols(test, cols, k->d));
     PBN_TRY(check_rows(test, rows));
@@ -1061,8 +1170,39 @@ int pbn_ctx_create(int device, pbn_ctx** out) {
     return PBN_OK;
 }
 
+// One context over several GPUs of this process (pbn_ctx_create(const int* devices, int n, ...)): the
+// reference drives ONE device from ONE process (opencl/opencl_config.hpp:120-121, opencl_config.cpp:217-220), and a
+// caller of KDE.logl / GreedyHillClimbing.estimate keeps doing exactly that while every visible B200 takes its share.
+int pbn_ctx_create_multi(const int* devices, int n, pbn_ctx** out) {
+    if (!devices || !out || n < 1) return set_error(PBN_ERR_ARG, "invalid device list");
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < i; ++j)
+            if (devices[i] == devices[j]) return set_error(PBN_ERR_ARG, "a device is listed twice");
+    pbn_ctx* c = nullptr;
+    PBN_TRY(pbn_ctx_create(devices[0], &c));
+    for (int i = 1; i < n; ++i) {
+        pbn_ctx* p = nullptr;
+        int rc = pbn_ctx_create(devices[i], &p);
+        if (rc != PBN_OK) {
+            std::string msg = pbn_last_error();
+            pbn_ctx_destroy(c);
+            return set_error(rc, msg);
+        }
+        c->peers.push_back(p);
+    }
+    *out = c;
+    return PBN_OK;
+}
+int pbn_ctx_num_devices(pbn_ctx* ctx) { return ctx ? pbn_num_devices(ctx) : 0; }
+int pbn_ctx_device(pbn_ctx* ctx, int i) {
+    if (!ctx || i < 0 || i >= pbn_num_devices(ctx)) return -1;
+    return pbn_device_ctx(ctx, i)->device;
+}
+
 int pbn_ctx_destroy(pbn_ctx* ctx) {
     if (!ctx) return PBN_OK;
+    for (pbn_ctx* p : ctx->peers) pbn_ctx_destroy(p);
+    ctx->peers.clear();
     DevSetter ds(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->d_exp_tab) cudaFree(ctx->d_exp_tab);
@@ -1079,6 +1219,7 @@ int pbn_ctx_set_stream(pbn_ctx* ctx, void* s) {
 void* pbn_ctx_stream(pbn_ctx* ctx) { return ctx ? ctx->stream : nullptr; }
 int pbn_ctx_synchronize(pbn_ctx* ctx) {
     if (!ctx) return set_error(PBN_ERR_ARG, "null context");
+    for (pbn_ctx* p : ctx->peers) PBN_TRY(pbn_ctx_synchronize(p));
     DevSetter ds(ctx->device);
     PBN_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return PBN_OK;
@@ -1086,9 +1227,15 @@ int pbn_ctx_synchronize(pbn_ctx* ctx) {
 int pbn_ctx_sm_count(pbn_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 int pbn_ctx_counters(pbn_ctx* ctx, int64_t* launches, int64_t* h2d, int64_t* d2h) {
     if (!ctx) return set_error(PBN_ERR_ARG, "null context");
-    if (launches) *launches = ctx->launches;
-    if (h2d) *h2d = ctx->h2d;
-    if (d2h) *d2h = ctx->d2h;
+    int64_t l = ctx->launches, a = ctx->h2d, b = ctx->d2h;
+    for (const pbn_ctx* p : ctx->peers) {  // a multi-device context reports the sums over its devices
+        l += p->launches;
+        a += p->h2d;
+        b += p->d2h;
+    }
+    if (launches) *launches = l;
+    if (h2d) *h2d = a;
+    if (d2h) *d2h = b;
     return PBN_OK;
 }
 int pbn_ctx_set_timing(pbn_ctx* ctx, int on) {
@@ -1126,7 +1273,26 @@ int pbn_ctx_last_row_kernel_rows(pbn_ctx* ctx, int64_t* out) {
     return PBN_OK;
 }
 
+static int table_upload_one(pbn_ctx* ctx, const void* const* col_ptrs, int ncols, int64_t nrows, int dtype, pbn_table** out);
+
 int pbn_table_upload(pbn_ctx* ctx, const void* const* col_ptrs, int ncols, int64_t nrows, int dtype, pbn_table** out) {
+    if (!ctx || !col_ptrs || !out) return set_error(PBN_ERR_ARG, "null argument");
+    if (ctx->peers.empty()) return table_upload_one(ctx, col_ptrs, ncols, nrows, dtype, out);
+    // multi-device context: one replica per device, copied over each device's own PCIe link in parallel
+    const int nd = pbn_num_devices(ctx);
+    std::vector<pbn_table*> t(nd, nullptr);
+    int rc = pbn_run_on_devices(nd, [&](int i) { return table_upload_one(pbn_device_ctx(ctx, i), col_ptrs, ncols, nrows, dtype, &t[i]); });
+    if (rc != PBN_OK) {
+        for (pbn_table* q : t)
+            if (q) pbn_table_free(q);
+        return rc;
+    }
+    t[0]->rep.assign(t.begin() + 1, t.end());
+    *out = t[0];
+    return PBN_OK;
+}
+
+static int table_upload_one(pbn_ctx* ctx, const void* const* col_ptrs, int ncols, int64_t nrows, int dtype, pbn_table** out) {
     if (!ctx || !col_ptrs || !out) return set_error(PBN_ERR_ARG, "null argument");
     if (ncols < 1 || nrows < 0) return set_error(PBN_ERR_ARG, "invalid table shape");
     if (dtype != PBN_F64 && dtype != PBN_F32)
@@ -1156,6 +1322,8 @@ int pbn_table_upload(pbn_ctx* ctx, const void* const* col_ptrs, int ncols, int64
 
 int pbn_table_free(pbn_table* t) {
     if (!t) return PBN_OK;
+    for (pbn_table* r : t->rep) pbn_table_free(r);
+    t->rep.clear();
     DevSetter ds(t->ctx->device);
     cudaFreeAsync(t->data, t->ctx->stream);
     delete t;
@@ -1302,6 +1470,8 @@ int pbn_product_kde_fit(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int
 }
 int pbn_kde_free(pbn_kde* k) {
     if (!k) return PBN_OK;
+    for (pbn_kde* r : k->rep) pbn_kde_free(r);
+    k->rep.clear();
     DevSetter ds(k->ctx->device);
     if (k->y) cudaFreeAsync(k->y, k->ctx->stream);
     delete k;

@@ -107,7 +107,27 @@ __global__ void fill_nan_kernel(double* __restrict__ out, long long n) {
 extern "C" {
 
 // DataFrame::take (dataset/dataset.hpp: arrow::compute::Take of every column) on a resident table.
+static int table_take_one(pbn_ctx* ctx, const pbn_table* tbl, const int32_t* indices, int64_t n, pbn_table** out);
+
 int pbn_table_take(pbn_ctx* ctx, const pbn_table* tbl, const int32_t* indices, int64_t n, pbn_table** out) {
+    if (!ctx || !tbl || !out || (n > 0 && !indices)) return set_error(PBN_ERR_ARG, "null argument");
+    if (!pbn_replicated(ctx, tbl)) return table_take_one(ctx, tbl, indices, n, out);
+    const int nd = pbn_num_devices(ctx);  // multi-device context: every replica is gathered on its own device
+    std::vector<pbn_table*> t(nd, nullptr);
+    int rc = pbn_run_on_devices(nd, [&](int i) {
+        return table_take_one(pbn_device_ctx(ctx, i), pbn_replica(const_cast<pbn_table*>(tbl), i), indices, n, &t[i]);
+    });
+    if (rc != PBN_OK) {
+        for (pbn_table* q : t)
+            if (q) pbn_table_free(q);
+        return rc;
+    }
+    t[0]->rep.assign(t.begin() + 1, t.end());
+    *out = t[0];
+    return PBN_OK;
+}
+
+static int table_take_one(pbn_ctx* ctx, const pbn_table* tbl, const int32_t* indices, int64_t n, pbn_table** out) {
     if (!ctx || !tbl || !out || (n > 0 && !indices)) return set_error(PBN_ERR_ARG, "null argument");
     if (n < 0) return set_error(PBN_ERR_ARG, "negative row count");
     for (int64_t i = 0; i < n; ++i)

@@ -12,6 +12,7 @@
 #include "internal.h"
 
 struct pbn_ucv {
+    std::vector<pbn_ucv*> rep;  // replicas on ctx->peers (multi-device context): each sums its slice of the pair tiles
     pbn_ctx* ctx;
     const pbn_table* tbl;
     int cols[PBN_MAX_DIM];
@@ -117,11 +118,32 @@ static int ucv_factor(const pbn_ucv* s, const double* H, int is_diag, std::vecto
     return PBN_OK;
 }
 
+// slice `part` of `nparts` of the pair-tile schedule; a multi-device scorer cuts that slice once more, one piece per
+// device (upper-triangular tile list split by tile count), and adds the pieces in device order
+static int ucv_sums_devices(pbn_ucv* s, const double* Lchol, long long part, long long nparts, double* S2, double* S1) {
+    // (below ~2e8 pairs one device finishes before the threads have started)
+    if (!pbn_replicated(s->ctx, s) || s->n < 20000) return ucv_sums(s, Lchol, part, nparts, S2, S1);
+    const int nd = pbn_num_devices(s->ctx);
+    std::vector<double> a(nd, 0.0), b(nd, 0.0);
+    PBN_TRY(pbn_run_on_devices(nd, [&](int i) {
+        pbn_ucv* r = pbn_replica(s, i);
+        DevSetter ds(r->ctx->device);
+        return ucv_sums(r, Lchol, part * nd + i, nparts * nd, &a[i], &b[i]);
+    }));
+    *S2 = 0;
+    *S1 = 0;
+    for (int i = 0; i < nd; ++i) {
+        *S2 += a[i];
+        *S1 += b[i];
+    }
+    return PBN_OK;
+}
+
 static int ucv_score_full(pbn_ucv* s, const double* H, int is_diag, double* out) {
     std::vector<double> L;
     PBN_TRY(ucv_factor(s, H, is_diag, L));
     double S2, S1;
-    PBN_TRY(ucv_sums(s, L.data(), 0, 1, &S2, &S1));
+    PBN_TRY(ucv_sums_devices(s, L.data(), 0, 1, &S2, &S1));
     *out = ucv_combine(s, L.data(), S2, S1);
     return PBN_OK;
 }
@@ -238,7 +260,27 @@ NMResult nelder_mead(const std::function<double(const double*)>& f, std::vector<
 
 extern "C" {
 
+static int ucv_create_one(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, pbn_rows rows, pbn_ucv** out);
+
 int pbn_ucv_create(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, pbn_rows rows, pbn_ucv** out) {
+    if (!ctx || !out) return set_error(PBN_ERR_ARG, "null argument");
+    if (!pbn_replicated(ctx, tbl)) return ucv_create_one(ctx, tbl, cols, d, rows, out);
+    const int nd = pbn_num_devices(ctx);
+    std::vector<pbn_ucv*> u(nd, nullptr);
+    int rc = pbn_run_on_devices(nd, [&](int i) {
+        return ucv_create_one(pbn_device_ctx(ctx, i), pbn_replica(const_cast<pbn_table*>(tbl), i), cols, d, rows, &u[i]);
+    });
+    if (rc != PBN_OK) {
+        for (pbn_ucv* q : u)
+            if (q) pbn_ucv_free(q);
+        return rc;
+    }
+    u[0]->rep.assign(u.begin() + 1, u.end());
+    *out = u[0];
+    return PBN_OK;
+}
+
+static int ucv_create_one(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, pbn_rows rows, pbn_ucv** out) {
     if (!ctx || !out) return set_error(PBN_ERR_ARG, "null argument");
     PBN_TRY(check_cols(tbl, cols, d));
     PBN_TRY(check_rows(tbl, rows));
@@ -246,8 +288,7 @@ int pbn_ucv_create(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, p
     int64_t n = seg_count(rows);
     if (n < 2) return set_error(PBN_ERR_ARG, "UCV needs at least 2 instances");
     DevSetter ds(ctx->device);
-    pbn_ucv* s = new pbn_ucv();
-    memset(s, 0, sizeof(*s));
+    pbn_ucv* s = new pbn_ucv();  // value-initialised: every scalar member starts at zero
     s->ctx = ctx;
     s->tbl = tbl;
     s->d = d;
@@ -294,6 +335,8 @@ int pbn_ucv_create(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, p
 
 int pbn_ucv_free(pbn_ucv* s) {
     if (!s) return PBN_OK;
+    for (pbn_ucv* r : s->rep) pbn_ucv_free(r);
+    s->rep.clear();
     DevSetter ds(s->ctx->device);
     cudaStream_t st = s->ctx->stream;
     cudaFreeAsync(s->y, st);
@@ -315,7 +358,7 @@ int pbn_ucv_pair_sums(pbn_ucv* s, const double* H_or_hdiag, int is_diag, int par
     DevSetter ds(s->ctx->device);
     std::vector<double> L;
     PBN_TRY(ucv_factor(s, H_or_hdiag, is_diag, L));
-    return ucv_sums(s, L.data(), part, nparts, S2, S1);
+    return ucv_sums_devices(s, L.data(), part, nparts, S2, S1);
 }
 
 int pbn_ucv_score_from_sums(pbn_ucv* s, const double* H_or_hdiag, int is_diag, double S2, double S1, double* out) {

@@ -272,24 +272,23 @@ class _FoldScorer:
         return {items[i][0]: float(scores[i]) for i in range(len(items))}
 
     def _score_native_by_fold(self, code, items, rank, world):
-        """(item, fold) jobs dealt over the ranks; every rank scores its jobs fold by fold (one pbn_cv_scores call per
-        fold), the [items x folds] matrix is summed over ranks (each entry written by exactly one rank) and the folds of
-        an item are added in fold order - the same additions as the single-GPU call."""
+        """(item, fold) jobs dealt over the ranks, most expensive first; every rank scores ITS jobs in one
+        pbn_cv_score_jobs call (one batched launch per family size, however the jobs spread over folds), the
+        [items x folds] matrix is summed over ranks (each entry written by exactly one rank) and the folds of an item
+        are added in fold order - the same additions as the single-GPU call."""
         nfolds = self.fold_end - self.fold_begin
         cost = []
         for _, f, _, v in items:
             cost.extend([len(v) if f == _lib.FACTOR_CKDE else 0] * nfolds)
         mine = parallel.deal(cost, rank, world)
-        per_fold = {}
-        for job in mine:
-            per_fold.setdefault(job % nfolds, []).append(job // nfolds)
         mat = np.zeros((len(items), nfolds))
         with parallel.guard() as g:
-            for q in sorted(per_fold):
-                idx = per_fold[q]
-                f0 = self.fold_begin + q
-                mat[idx, q] = self._run_items(code, [items[i] for i in idx], f0, f0 + 1)
-                self.stats["device_items"] += len(idx)
+            if mine:
+                mine = sorted(mine)
+                ji = [job // nfolds for job in mine]
+                jq = [job % nfolds for job in mine]
+                mat[ji, jq] = self._run_jobs(code, items, ji, [self.fold_begin + q for q in jq])
+                self.stats["device_items"] += len(mine)
                 self.stats["batches"] += 1
         mat = parallel.all_reduce_sum(mat.ravel(), self._ctx(code), error=g.error).reshape(len(items), nfolds)
         out = {}
@@ -300,6 +299,31 @@ class _FoldScorer:
             out[items[i][0]] = total
         return out
 
+    def _run_jobs(self, code, items, job_item, job_fold):
+        """One pbn_cv_score_jobs call: job j = fold job_fold[j] of items[job_item[j]]; returns the per-job slogl."""
+        handle, index = self._device(code)
+        arr = self._item_array(items, index)
+        ji = np.ascontiguousarray(job_item, dtype=np.int32)
+        jf = np.ascontiguousarray(job_fold, dtype=np.int32)
+        local = np.zeros(len(ji))
+        status = (ctypes.c_int * len(items))()
+        check(lib().pbn_cv_score_jobs(handle.tbl.ctx.handle, handle.h, arr, len(items), _i32p(ji), _i32p(jf), len(ji),
+                                      local.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), status))
+        used = set(int(i) for i in ji)
+        bad = [status[i] for i in sorted(used) if status[i] != _lib.PBN_OK]
+        if bad:
+            _lib.raise_for(bad[0], lib().pbn_last_error().decode("utf-8", "replace"))
+        return local
+
+    @staticmethod
+    def _item_array(items, index):
+        arr = (CVItem * len(items))()
+        for slot, (_, factor, rule, variables) in enumerate(items):
+            arr[slot].factor, arr[slot].rule, arr[slot].n_vars = factor, rule, len(variables)
+            for q, v in enumerate(variables):
+                arr[slot].vars[q] = index[v]
+        return arr
+
     def _ctx(self, code):
         return self._device(code)[0].tbl.ctx
 
@@ -309,11 +333,7 @@ class _FoldScorer:
         fold_begin = self.fold_begin if fold_begin is None else fold_begin
         fold_end = self.fold_end if fold_end is None else fold_end
         handle, index = self._device(code)
-        arr = (CVItem * len(items))()
-        for slot, (_, factor, rule, variables) in enumerate(items):
-            arr[slot].factor, arr[slot].rule, arr[slot].n_vars = factor, rule, len(variables)
-            for q, v in enumerate(variables):
-                arr[slot].vars[q] = index[v]
+        arr = self._item_array(items, index)
         local = np.zeros(len(items))
         status = (ctypes.c_int * len(items))()
         check(lib().pbn_cv_scores(handle.tbl.ctx.handle, handle.h, arr, len(items), fold_begin, fold_end,

@@ -304,6 +304,23 @@ def test_multi_gpu_shards_match_single_gpu():
     assert out.returncode == 0 and "MULTI_GPU_CHECK_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
 
 
+def test_in_process_multi_device_context_matches_single_device():
+    """Needs >= 2 GPUs: ONE process, a context over all devices (pbn_ctx_create_multi, no torchrun) - sharded logl / slogl /
+    cdf, dealt CV jobs, per-device UCV slices and hill climbing against the single-device results
+    (tools/inproc_multi_gpu_check.py)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = {k: v for k, v in os.environ.items() if k not in ("PBN_CUDA_DEVICE", "PBN_CUDA_DEVICES", "LOCAL_RANK")}
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "inproc_multi_gpu_check.py"), "--no-timing"],
+                         capture_output=True, text=True, timeout=1200, env=env)
+    assert out.returncode == 0 and "INPROC_MULTI_GPU_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
 def test_mle_linear_gaussian_like_the_reference_test(pbn):
     """tests/learning/parameters/mle_test.py: MLE(LinearGaussianCPDType()).estimate against numpy lstsq;
     MLE(CKDEType()) is not available."""

@@ -68,11 +68,10 @@ class FoldScorer(_FoldScorer):
     calls = []
     def _ctx(self, code):
         return None
-    def _run_items(self, code, items, fold_begin=None, fold_end=None):
-        fb = self.fold_begin if fold_begin is None else fold_begin
-        fe = self.fold_end if fold_end is None else fold_end
-        FoldScorer.calls.append((fb, fe, len(items)))
-        return np.array([sum(fold_value(v, f) for f in range(fb, fe)) for _, _, _, v in items])
+    def _run_jobs(self, code, items, job_item, job_fold):
+        FoldScorer.calls.append(len(job_item))
+        assert list(zip(job_item, job_fold)) == sorted(zip(job_item, job_fold))
+        return np.array([fold_value(items[i][3], f) for i, f in zip(job_item, job_fold)])
 
 fs = FoldScorer(pbn.DataFrame(data), idx, lim, 0, 5, pbn.Arguments())
 got = fs.score_batch(model, reqs)
@@ -81,17 +80,17 @@ for (t, v, e), g in zip(reqs, got):
     for f in range(5):
         want_f += fold_value([v] + e, f)
     assert g == want_f, (v, e, g, want_f)
-assert all(fe - fb == 1 for fb, fe, _ in FoldScorer.calls) and len(FoldScorer.calls) <= 5
-jobs = sum(n for _, _, n in FoldScorer.calls)
+assert len(FoldScorer.calls) == 1   # ONE batched call per rank however its jobs spread over the folds
+jobs = sum(FoldScorer.calls)
 tot = parallel.all_reduce_sum(np.array([jobs if rank == 0 else 0.0, jobs if rank == 1 else 0.0]))
 assert tot.sum() == 5 * len(reqs) and abs(tot[0] - tot[1]) <= 1, tot
 # 3c. a failure on ONE rank (an item only it was dealt) raises on EVERY rank after the collective - no rank is left
 # waiting in the all-reduce (ADVICE round 1: the reference raises cleanly from its single process)
 class FailingScorer(FoldScorer):
-    def _run_items(self, code, items, fold_begin=None, fold_end=None):
+    def _run_jobs(self, code, items, job_item, job_fold):
         if rank == 1:
             raise _lib.SingularCovarianceData("Covariance matrix for variables [a, b] is not positive-definite.")
-        return super()._run_items(code, items, fold_begin, fold_end)
+        return super()._run_jobs(code, items, job_item, job_fold)
 
 bad = FailingScorer(pbn.DataFrame(data), idx, lim, 0, 5, pbn.Arguments())
 try:
