@@ -57,7 +57,33 @@ struct PairJob {
     const float* shift_j;
     const float* shift_m;
     const int* test_rows;  // row r of the job is row test_rows[r] of `test`
+    // tile skipping (single-job launches, runtime.cu): the units of the job are an explicit list instead of the full
+    // (test tile) x (train tile) grid.  unit_list[q] = train tile of the job's q-th unit, test-tile major, ascending train
+    // tile inside a test tile; tile_first[tt] .. tile_first[tt + 1] delimits the units of test tile tt.  Null = full grid.
+    const int* unit_list;
+    const long long* tile_first;
 };
+
+// (test tile, train tile) of the job's `local`-th unit
+__device__ __forceinline__ void pair_unit(const PairJob& jb, long long local, long long& tt, int& nt) {
+    if (jb.unit_list) {
+        // largest tt with tile_first[tt] <= local (test tiles without units repeat the same offset)
+        long long lo = 0, hi = jb.n_test_tiles - 1;
+        while (lo < hi) {
+            const long long mid = (lo + hi + 1) >> 1;
+            if (jb.tile_first[mid] <= local) lo = mid; else hi = mid - 1;
+        }
+        tt = lo;
+        nt = jb.unit_list[local];
+    } else {
+        tt = local / jb.n_train_tiles;
+        nt = static_cast<int>(local - tt * jb.n_train_tiles);
+    }
+}
+// first unit (relative to unit_begin) of test tile tt
+__device__ __forceinline__ long long pair_tile_first(const PairJob& jb, long long tt) {
+    return jb.unit_list ? jb.tile_first[tt] : tt * jb.n_train_tiles;
+}
 
 constexpr int kThreads = 256;
 // the pair kernel (log-likelihood and CDF modes) is instantiated for 1..kMaxFastD variables: north_star's family
@@ -818,7 +844,7 @@ pair_kernel(const PairJob* __restrict__ jobs, int n_jobs, long long total_units,
         while (pj + 1 < n_jobs && jobs[pj + 1].unit_begin <= pu) ++pj;
         const PairJob& jb = jobs[pj];
         long long local = pu - jb.unit_begin;
-        int nt = static_cast<int>(local % jb.n_train_tiles);
+        int nt = jb.unit_list ? jb.unit_list[local] : static_cast<int>(local % jb.n_train_tiles);
         long long start = static_cast<long long>(nt) * TILE;
         long long cnt = jb.n_train - start;
         if (cnt > TILE) cnt = TILE;
@@ -849,7 +875,7 @@ pair_kernel(const PairJob* __restrict__ jobs, int n_jobs, long long total_units,
     auto flush = [&]() {
         if (cur_job < 0) return;
         const PairJob& jb = jobs[cur_job];
-        long long ustart = jb.unit_begin + cur_tt * jb.n_train_tiles;
+        long long ustart = jb.unit_begin + pair_tile_first(jb, cur_tt);
         int slot = static_cast<int>(blockIdx.x - ustart / upb);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -873,8 +899,14 @@ pair_kernel(const PairJob* __restrict__ jobs, int n_jobs, long long total_units,
         while (cj + 1 < n_jobs && jobs[cj + 1].unit_begin <= u) ++cj;
         const PairJob& jb = jobs[cj];
         const long long local = u - jb.unit_begin;
-        const long long tt = local / jb.n_train_tiles;
-        const int nt = static_cast<int>(local - tt * jb.n_train_tiles);
+        long long tt;
+        int nt;
+        if (cj == cur_job && jb.unit_list && local < jb.tile_first[cur_tt + 1]) {  // still inside the current test tile
+            tt = cur_tt;
+            nt = jb.unit_list[local];
+        } else {
+            pair_unit(jb, local, tt, nt);
+        }
         if (cj != cur_job || tt != cur_tt) {
             flush();
             cur_job = cj;

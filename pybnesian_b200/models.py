@@ -130,6 +130,12 @@ class Dag:
     def collapsed_name(self, idx):
         return self._collapsed[idx]
 
+    def collapsed_from_index(self, idx):
+        return self._cindex[self.name(idx)]
+
+    def index_from_collapsed(self, cidx):
+        return self._index[self._collapsed[cidx]]
+
     def add_node(self, name):
         """GraphBase::add_node / create_node (generic_graph.hpp:509-544): a freed raw slot is reused, last freed first."""
         if name in self._index:
@@ -598,6 +604,12 @@ class BayesianNetwork:
 
     def collapsed_name(self, idx):
         return self._g.collapsed_name(idx)
+
+    def collapsed_from_index(self, idx):
+        return self._g.collapsed_from_index(idx)
+
+    def index_from_collapsed(self, cidx):
+        return self._g.index_from_collapsed(cidx)
 
     def add_node(self, node):
         """BNGeneric::add_node (models/BayesianNetwork.hpp:503-515)."""

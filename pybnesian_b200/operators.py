@@ -340,12 +340,17 @@ class ArcOperatorSet(OperatorSet):
             self._n = n
         self._valid[:] = True
         black, white = _validate_restrictions(model, self._blacklist, self._whitelist)
+        # the restrictions hold raw node indices; delta / valid_op are indexed by COLLAPSED indices
+        # (operators.cpp:36-52: model.collapsed_from_index), which differ once nodes have been removed
+        cfi = model.collapsed_from_index
         for s, t in white:
+            s, t = cfi(s), cfi(t)
             self._valid[self._d(s, t)] = False
             self._valid[self._d(t, s)] = False
             self._delta[self._d(s, t)] = LOWEST
             self._delta[self._d(t, s)] = LOWEST
         for s, t in black:
+            s, t = cfi(s), cfi(t)
             self._valid[self._d(s, t)] = False
             self._delta[self._d(s, t)] = LOWEST
         for i in range(n):

@@ -334,3 +334,19 @@ def test_clone_keeps_python_side_state_of_derived_networks():
     m.extra_data = "changed"
     c = m.clone()
     assert type(c) is NewBN and c.extra_data == "changed" and c.nodes() == ["a", "b"]
+
+
+def test_arc_operator_set_uses_collapsed_indices_after_node_removal():
+    """operators.cpp:36-52 (collapsed_from_index): the reference's hillclimbing_test.py:13-45 runs an ArcOperatorSet with an
+    arc blacklist on a network whose nodes 'e' and 'f' were removed (raw indices 4, 5 of the survivors >= num_nodes)."""
+    import pybnesian_b200 as pbn
+    g = pbn.GaussianNetwork(["a", "e", "b", "f", "c", "d"])
+    g.remove_node("e")
+    g.remove_node("f")
+    ops = pbn.ArcOperatorSet(blacklist=[("c", "d")], whitelist=[])
+    ops.update_valid_ops(g)
+    n = g.num_nodes()
+    valid = ops._valid.reshape(n, n, order="F")
+    ci = g.collapsed_index
+    assert not valid[ci("c"), ci("d")] and valid[ci("d"), ci("c")] and not valid[ci("a"), ci("a")]
+    assert int(valid.sum()) == n * n - n - 1 == len(ops._sorted_idx)
