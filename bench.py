@@ -257,6 +257,8 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    # `value` and the roofline: EVERY (train, test) pair evaluated (tile skipping off)
+    ctx.set_skipping(False)
     for _ in range(warmup):
         step()
     barrier()
@@ -284,34 +286,77 @@ def main():
     pairs_per_step_job = 2.0 * n_train * n_test * (1 if strong else world)
     value = pairs_per_step_job * steps / (total_ms * 1e-3)
 
-    # ---- e2e: public API with host buffers (pinned), H2D + D2H inside the timed region ----
+    # ---- the same steps with the product's default, tile skipping on (spatial.cu): units the bounding boxes prove
+    # negligible (< 2^-48 of every row's sum) are dropped; the metric still counts n_train x n_test pairs per step ----
+    ctx.set_skipping(True)
+    step()
+    barrier()
+    ctx.set_timing(True)
+    ctx.pair_kernel_time(reset=True)
+    ctx.skip_stats(reset=True)
+    sk_steps = max(3, min(steps, 10))
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(sk_steps)]
+    for a, b in evs:
+        flush.zero_()
+        a.record(stream)
+        step()
+        b.record(stream)
+    barrier()
+    ctx.set_timing(False)
+    sk_ms = reduce_max(float(sum(a.elapsed_time(b) for a, b in evs)))
+    sk_stats = ctx.skip_stats(reset=True)
+    ctx.pair_kernel_time(reset=True)
+    slogl_skipping = float(out.item())
+    with_skipping = {"value": pairs_per_step_job * sk_steps / (sk_ms * 1e-3), "unit": UNIT, "ms_per_step": sk_ms / sk_steps,
+                     "steps": sk_steps, "units_total": sk_stats["timed_total"], "units_evaluated": sk_stats["timed_evaluated"],
+                     "fraction_evaluated": sk_stats["timed_evaluated"] / max(sk_stats["timed_total"], 1),
+                     "slogl_sum_over_ranks": slogl_skipping,
+                     "rel_diff_vs_all_pairs": abs(slogl_skipping - slogl_total) / abs(slogl_total),
+                     "note": "same steps with tile skipping on (the library default): (test tile x train tile) units whose "
+                             "bounding boxes prove all their terms < 2^-48 of every row's sum are not evaluated; the metric "
+                             "counts n_train x n_test pairs regardless, so this is NOT comparable with `value`"}
+    assert with_skipping["rel_diff_vs_all_pairs"] < 1e-12, with_skipping
+
+    # ---- e2e: public API with host buffers (pinned), H2D + D2H inside the timed region.  Measured twice: every pair
+    # evaluated (`e2e`, comparable with `value` and with the reference arm's arithmetic) and with the library default,
+    # tile skipping on (`e2e_with_skipping`) ----
     e2e_steps = args.e2e_steps or min(steps, 10)
     parallel.enable(strong)   # strong: CKDE.slogl shards the frame itself (and all-reduces the scalar)
     pinned = {c: torch.from_numpy(test_df[c].to_numpy()).pin_memory() for c in VARIABLES}
     host_rb = pa.RecordBatch.from_arrays([pa.array(pinned[c].numpy()) for c in VARIABLES], names=VARIABLES)
-    cpd.slogl(host_rb)  # warm
-    barrier()
-    e0 = ctx.counters()
-    t0 = time.perf_counter()
-    e2e_sum = torch.zeros(1, dtype=torch.float64, device="cuda")
-    for _ in range(e2e_steps):
-        s_e2e = cpd.slogl(host_rb)
-        if world > 1 and not strong:   # weak: the job's result is the sum over the ranks' own frames
-            e2e_sum[0] = s_e2e
-            dist.all_reduce(e2e_sum)
-    ctx.synchronize()
-    torch.cuda.synchronize()
-    e2e_s = reduce_max(time.perf_counter() - t0)
-    e1 = ctx.counters()
+    def e2e_run(skipping):
+        ctx.set_skipping(skipping)
+        cpd.slogl(host_rb)  # warm
+        barrier()
+        c_a = ctx.counters()
+        t0 = time.perf_counter()
+        acc = torch.zeros(1, dtype=torch.float64, device="cuda")
+        s_last = None
+        for _ in range(e2e_steps):
+            s_last = cpd.slogl(host_rb)
+            if world > 1 and not strong:   # weak: the job's result is the sum over the ranks' own frames
+                acc[0] = s_last
+                dist.all_reduce(acc)
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        dt = reduce_max(time.perf_counter() - t0)
+        c_b = ctx.counters()
+        return {"value": pairs_per_step_job * e2e_steps / dt, "unit": UNIT,
+                "h2d_bytes_per_step": (c_b["h2d_bytes"] - c_a["h2d_bytes"]) // e2e_steps,
+                "d2h_bytes_per_step": (c_b["d2h_bytes"] - c_a["d2h_bytes"]) // e2e_steps,
+                "api": "CKDE.slogl(pyarrow.RecordBatch over pinned host buffers)", "steps": e2e_steps,
+                "timer": "host wall clock around the blocking API call, max over ranks"}, s_last
+
+    e2e, s_e2e = e2e_run(False)
+    e2e["tile_skipping"] = "off: every pair evaluated"
+    e2e_skip, s_e2e_skip = e2e_run(True)
+    e2e_skip["tile_skipping"] = "on (library default)"
+    e2e_skip["slogl_rank0"] = s_e2e_skip
     parallel.enable(False)
-    e2e = {"value": pairs_per_step_job * e2e_steps / e2e_s, "unit": UNIT,
-           "h2d_bytes_per_step": (e1["h2d_bytes"] - e0["h2d_bytes"]) // e2e_steps,
-           "d2h_bytes_per_step": (e1["d2h_bytes"] - e0["d2h_bytes"]) // e2e_steps,
-           "api": "CKDE.slogl(pyarrow.RecordBatch over pinned host buffers)", "steps": e2e_steps,
-           "timer": "host wall clock around the blocking API call, max over ranks"}
 
     # ---- side measurements (every rank takes part; rank 0 reports) ----
     extras = {}
+    ctx.set_skipping(False)   # the side measurements evaluate every pair, like `value`
     if not args.no_extras:
         extras["strong_scaling"] = strong_scaling_leg(args, ctx, cpd, world, rank, barrier, reduce_max, pbn, parallel)
         extras["hc_cv"] = hc_leg(world)
@@ -390,7 +435,8 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": workload_config(args),
-        "clocks": clocks, "e2e": e2e, "gpu_launches": c1["launches"] - c0["launches"],
+        "clocks": clocks, "e2e": e2e, "value_with_skipping": with_skipping, "e2e_with_skipping": e2e_skip,
+        "gpu_launches": c1["launches"] - c0["launches"],
         "roofline": roofline, "cpu_baseline": cpu_baseline,
         "check": {"slogl_sum_over_ranks": slogl_total, "slogl_e2e_rank0": s_e2e,
                   "fallback_rows_last_call": ctx.last_fallback_rows(), "wall_s_timed_loop": wall},
@@ -450,6 +496,7 @@ def inproc_leg(args, world, rank, s_single):
     prev = pbn.default_context()
     try:
         ctx = pbn.set_default_context(pbn.Context(list(range(world))))
+        ctx.set_skipping(False)   # every pair evaluated, like `value`
         train, frame = pbn.DataFrame(gen(args.n_train, 0)), pbn.DataFrame(gen(args.n_test, 1))
         cpd = pbn.CKDE("d", ["a", "b", "c"])
         cpd.fit(train)

@@ -157,6 +157,16 @@ int pbn_ctx_last_fallback_rows(pbn_ctx* ctx, int64_t* out);
 /* ... and how many of those the shifted pass could not evaluate either (farther than 2^31
  * kernel units from every training row, non-finite coordinates): one CTA per row. */
 int pbn_ctx_last_row_kernel_rows(pbn_ctx* ctx, int64_t* out);
+/* Tile skipping (on by default).  The reference evaluates every (train, test) pair (kde/KDE.hpp:592-640).  For large
+ * single-model calls (>= 2^17 training rows, >= 2^14 test rows, d <= 10) this library keeps the whitened rows in Morton
+ * order, one bounding box per tile, and drops every (test tile, train tile) unit whose boxes prove that ALL dropped
+ * terms of a row together stay below 2^-48 of that row's sum (lower-bounded by a first pass against the nearest
+ * training tile): logl changes by < 4e-15 absolute.  pbn_ctx_set_skipping(ctx, 0) evaluates every pair, which is what
+ * bench.py's `value` and the roofline are measured on.  pbn_ctx_skip_stats reports (test tile x train tile) units in
+ * total / actually evaluated, for the last call and accumulated over the timed launches. */
+int pbn_ctx_set_skipping(pbn_ctx* ctx, int on);
+int pbn_ctx_skip_stats(pbn_ctx* ctx, int64_t* last_total, int64_t* last_done, int64_t* timed_total, int64_t* timed_done,
+                       int reset);
 
 /* kde::UCVScorer (kde/UCV.hpp:12-45): constructed once per (data, variables); every score call
  * evaluates all N(N-1)/2 pairs in ONE launch (64-bit pair indexing; the reference's 32-bit chunk

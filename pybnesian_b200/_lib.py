@@ -17,7 +17,7 @@ BW_NORMAL_REFERENCE, BW_SCOTT = 0, 1
 
 EXPORTS = [
     "pbn_last_error", "pbn_version", "pbn_device_count", "pbn_ctx_create", "pbn_ctx_create_multi", "pbn_ctx_num_devices",
-    "pbn_ctx_device", "pbn_cv_score_jobs", "pbn_ctx_destroy", "pbn_ctx_set_stream",
+    "pbn_ctx_device", "pbn_cv_score_jobs", "pbn_ctx_set_skipping", "pbn_ctx_skip_stats", "pbn_ctx_destroy", "pbn_ctx_set_stream",
     "pbn_ctx_stream", "pbn_ctx_synchronize", "pbn_ctx_sm_count", "pbn_ctx_counters", "pbn_table_upload",
     "pbn_table_free", "pbn_table_rows", "pbn_table_cols", "pbn_table_download", "pbn_table_moments", "pbn_bandwidth",
     "pbn_diag_bandwidth", "pbn_kde_fit", "pbn_ckde_fit", "pbn_product_kde_fit", "pbn_kde_free", "pbn_kde_num_instances", "pbn_kde_lognorm",
@@ -105,6 +105,8 @@ def lib():
         L.pbn_kde_logl_device.argtypes = [vp, vp, vp, ip, Rows, vp, vp]
         L.pbn_ctx_last_fallback_rows.argtypes = [vp, ctypes.POINTER(i64)]
         L.pbn_ctx_last_row_kernel_rows.argtypes = [vp, ctypes.POINTER(i64)]
+        L.pbn_ctx_set_skipping.argtypes = [vp, ci]
+        L.pbn_ctx_skip_stats.argtypes = [vp] + [ctypes.POINTER(i64)] * 4 + [ci]
         L.pbn_device_alloc.argtypes = [vp, i64, ctypes.POINTER(vp)]
         L.pbn_device_free.argtypes = [vp, vp]
         L.pbn_device_read.argtypes = [vp, vp, i64, vp]
@@ -233,6 +235,17 @@ class Context:
         v = ctypes.c_int64()
         check(lib().pbn_ctx_last_fallback_rows(self.handle, ctypes.byref(v)))
         return v.value
+
+    def set_skipping(self, on):
+        """Tile skipping on (default) / off = every (train, test) pair evaluated (include/pbn_cuda.h)."""
+        check(lib().pbn_ctx_set_skipping(self.handle, 1 if on else 0))
+
+    def skip_stats(self, reset=False):
+        """(test tile x train tile) units: of the last call (total, evaluated) and of the timed launches."""
+        a, b, c, d = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        check(lib().pbn_ctx_skip_stats(self.handle, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c), ctypes.byref(d),
+                                       1 if reset else 0))
+        return {"last_total": a.value, "last_evaluated": b.value, "timed_total": c.value, "timed_evaluated": d.value}
 
     def last_row_kernel_rows(self):
         v = ctypes.c_int64()

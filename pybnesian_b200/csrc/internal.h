@@ -53,6 +53,10 @@ struct pbn_ctx {
     int64_t launches = 0, h2d = 0, d2h = 0;
     int64_t last_fallback_rows = 0;     // rows of the last logl call that took the shifted second pass
     int64_t last_row_kernel_rows = 0;   // ... of which the per-row kernel had to finish (farther than 2^31 kernel units)
+    // tile skipping (spatial.cu): on by default for large single-model calls; the unit counts of the last such call
+    bool skipping = true;
+    int64_t last_units_total = 0, last_units_done = 0;
+    int64_t units_total = 0, units_done = 0;  // accumulated while `timing` is on
     // optional device timing of the pair kernel (CUDA events on the launching stream)
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;
@@ -81,6 +85,13 @@ struct pbn_kde {
     void* y;  // whitened training rows AoS [n_pad][d]
     float* d_bound;  // device scalar: max |whitened training coordinate|
     double* nrm;     // f64, d <= kMaxFastD only (else null): -sum_{c<dn} y_c^2 per training row, dn = d-1 if ckde else d
+    // tile skipping (spatial.cu), large training sets with d <= kMaxFastD only (else null): the same rows in Morton order
+    // (y itself keeps the caller's order: CKDE::sample addresses training rows by index), their norms, and the bounding
+    // box of every training tile, [n_box_tiles][2 d] floats (min, max)
+    void* ys = nullptr;
+    double* nrm_s = nullptr;
+    float* box = nullptr;
+    int n_box_tiles = 0;
     double W[PBN_MAX_DIM * PBN_MAX_DIM];  // row-major lower-triangular whitening matrix (incl. unit scale)
     double mu[PBN_MAX_DIM];
     int perm[PBN_MAX_DIM];  // internal column k = caller column perm[k]
@@ -158,6 +169,19 @@ int pbn_logl_impl(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const i
 // MLE<LinearGaussianCPD> from centred moments (cv.cu): Cm = sum (x_a - mean_a)(x_b - mean_b), column-major d x d,
 // variable first; writes beta[p + 1], returns the variance.
 double lg_fit_from_moments(int64_t rows, int p, const double* mean, const double* Cm, double* beta);
+
+// ---- spatial order and tile skipping (spatial.cu) ----
+int pbn_spatial_sort(pbn_ctx* ctx, int dtype, int d, const void* y, const double* nrm, int64_t n, const float* bound, void* ys,
+                     double* nrm_s, int* perm);
+int pbn_spatial_boxes(pbn_ctx* ctx, int dtype, int d, const void* ys, int64_t n, int tile_rows, float* box);
+int pbn_skip_nearest(pbn_ctx* ctx, const float* box_test, int n_test_tiles, const float* box_train, int n_train_tiles, int d, int* nearest,
+                     long long* iota);
+int pbn_skip_count(pbn_ctx* ctx, const pbn::PairJob* d_jobA, long long upbA, int tb, int ckde, int dtype, int64_t n_train,
+                   const float* box_test, int n_test_tiles, const float* box_train, int n_train_tiles, int d, const int* nearest,
+                   float* thr, long long* count, long long* tile_first, long long* total_out);
+int pbn_skip_fill(pbn_ctx* ctx, int ckde, const float* box_test, int n_test_tiles, const float* box_train, int n_train_tiles, int d,
+                  const int* nearest, const float* thr, const long long* tile_first, int* unit_list);
+int pbn_scatter_out(pbn_ctx* ctx, const double* src, const int* perm, int64_t n, double* dst);
 
 namespace pbn {
 cudaError_t launch_pair_f64(int D, bool ckde, const PairJob* jobs, int n_jobs, long long total_units, long long upb,

@@ -281,6 +281,8 @@ __global__ void whiten_kernel(const __grid_constant__ WhitenParams P, T* __restr
 struct FinalizeParams {
     const PairJob* job;  // single job in device memory
     long long upb;
+    const PairJob* jobA; // tile skipping: the pass-A job (nearest training tile of every test tile) whose sums are added, or null
+    long long upbA;
     int tb;              // test rows per tile
     int ckde;
     double lognorm_joint, lognorm_marg;
@@ -296,14 +298,23 @@ __global__ void finalize_kernel(FinalizeParams P) {
     long long row = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (row >= jb.m) return;
     long long tt = row / P.tb;
-    long long ustart = jb.unit_begin + tt * jb.n_train_tiles;
-    int first = (int)(ustart / P.upb);
-    int last = (int)((ustart + jb.n_train_tiles - 1) / P.upb);
-    int ns = last - first + 1;
     double sj = 0, sm = 0;
-    for (int s = 0; s < ns; ++s) {
-        sj += jb.part[(long long)s * jb.m_pad + row];
-        if (P.ckde) sm += jb.part[((long long)jb.slots + s) * jb.m_pad + row];
+    {
+        const long long ufirst = jb.unit_begin + (jb.unit_list ? jb.tile_first[tt] : tt * jb.n_train_tiles);
+        const long long ucount = jb.unit_list ? jb.tile_first[tt + 1] - jb.tile_first[tt] : jb.n_train_tiles;
+        if (ucount > 0) {
+            int first = (int)(ufirst / P.upb);
+            int last = (int)((ufirst + ucount - 1) / P.upb);
+            for (int s = 0; s <= last - first; ++s) {
+                sj += jb.part[(long long)s * jb.m_pad + row];
+                if (P.ckde) sm += jb.part[((long long)jb.slots + s) * jb.m_pad + row];
+            }
+        }
+    }
+    if (P.jobA) {  // one unit per test tile: one CTA, slot 0
+        const PairJob ja = *P.jobA;
+        sj += ja.part[row];
+        if (P.ckde) sm += ja.part[(long long)ja.slots * ja.m_pad + row];
     }
     bool bad = !(sj >= P.thresh) || (P.ckde && !(sm >= P.thresh));
     // NaN sums (NaN inputs) are not "underflow": propagate them
@@ -738,6 +749,9 @@ double unit_scale(int dtype) {  // kernel exponent units per natural-log unit of
 
 static int fit_one(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, pbn_rows rows, const double* H, bool ckde,
                    pbn_kde** out);
+// tile skipping pays from a few dozen tiles on each side (tools/skip_model.py: a 90k x 10k cross-validation fold has too few)
+constexpr int64_t kSkipMinTrain = 1 << 17;
+constexpr int64_t kSkipMinTest = 1 << 14;
 
 // multi-device context: the fitted model is replicated (every device whitens its own copy of the training rows)
 static int fit_impl(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, pbn_rows rows, const double* H,
@@ -813,6 +827,31 @@ static int fit_one(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, p
     k->nrm = nbytes ? reinterpret_cast<double*>(static_cast<char*>(k->y) + ybytes + 256) : nullptr;
     rc = pbn_whiten_kde(ctx, k, tbl, cols, rows, k->y, k->d_bound, k->nrm);
     if (rc != PBN_OK) { cudaFreeAsync(k->y, ctx->stream); delete k; return rc; }
+    // tile skipping: a second copy of the whitened rows in Morton order with one bounding box per training tile
+    if (d <= pbn::kMaxFastD && n >= kSkipMinTrain) {
+        const int n_tiles = (int)((n + tile - 1) / tile);
+        const size_t bbytes = ((size_t)n_tiles * 2 * d * sizeof(float) + 255) / 256 * 256;
+        int* perm = nullptr;
+        e = cudaMallocAsync(&k->ys, ybytes + nbytes + bbytes, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(k->ys, 0, ybytes + nbytes + bbytes, ctx->stream);
+        if (e == cudaSuccess) e = cudaMallocAsync(&perm, (size_t)n * sizeof(int), ctx->stream);
+        if (e == cudaSuccess) {
+            k->nrm_s = nbytes ? reinterpret_cast<double*>(static_cast<char*>(k->ys) + ybytes) : nullptr;
+            k->box = reinterpret_cast<float*>(static_cast<char*>(k->ys) + ybytes + nbytes);
+            k->n_box_tiles = n_tiles;
+            rc = pbn_spatial_sort(ctx, k->dtype, d, k->y, k->nrm, n, k->d_bound, k->ys, k->nrm_s, perm);
+            if (rc == PBN_OK) rc = pbn_spatial_boxes(ctx, k->dtype, d, k->ys, n, tile, k->box);
+        }
+        if (perm) cudaFreeAsync(perm, ctx->stream);
+        if (e != cudaSuccess || rc != PBN_OK) {  // skipping is an optimisation: the model works without it
+            if (k->ys) cudaFreeAsync(k->ys, ctx->stream);
+            k->ys = nullptr;
+            k->nrm_s = nullptr;
+            k->box = nullptr;
+            k->n_box_tiles = 0;
+            cudaGetLastError();
+        }
+    }
     *out = k;
     return PBN_OK;
 }
@@ -918,8 +957,28 @@ static int logl_one(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const
     if (!out) PBN_CUDA_TRY(sc.alloc(&out, (size_t)m * sizeof(double)));
     const double u2ln = 1.0 / unit_scale(k->dtype);  // (kernel units of s'/ -t) -> natural log
 
+    // tile skipping (spatial.cu): test rows in Morton order against the Morton-ordered copy of the training rows; every
+    // kernel below then works in that order and the results are scattered back at the end
+    const bool use_skip = ctx->skipping && fast && k->ys && m >= kSkipMinTest;
+    const void* train_y = k->y;
+    const double* train_nrm = k->nrm;
+    int* perm = nullptr;
+    double* out_final = out;
+    if (use_skip) {
+        char* ys_test = nullptr;
+        PBN_CUDA_TRY(sc.alloc(&ys_test, ytbytes + tnbytes));
+        PBN_CUDA_TRY(sc.alloc(&perm, (size_t)m * sizeof(int)));
+        PBN_CUDA_TRY(sc.alloc(&out, (size_t)m * sizeof(double)));
+        double* nrm_sorted = tnbytes ? reinterpret_cast<double*>(ys_test + ytbytes) : nullptr;
+        PBN_TRY(pbn_spatial_sort(ctx, k->dtype, d, ytest, nrm_test, m, bound_test, ys_test, nrm_sorted, perm));
+        ytest = ys_test;
+        nrm_test = nrm_sorted;
+        train_y = k->ys;
+        train_nrm = k->nrm_s;
+    }
+
     RowParams R;
-    R.train = k->y;
+    R.train = train_y;
     R.test = ytest;
     R.n = k->n;
     R.d = d;
@@ -943,18 +1002,19 @@ static int logl_one(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const
         long long m_pad = (m + 31) / 32 * 32;
         // one carve for the bookkeeping of both passes:
         //   [PairJob x 2][dyn: 2 x i64][counters: 2 x int][flagged: m int][flagged2: m int][shift_j, shift_m: m float][mask: m bytes]
-        const size_t o_dyn = 2 * ((sizeof(PairJob) + 15) / 16 * 16), o_cnt = o_dyn + 16, o_fl = o_cnt + 16;
+        const size_t jsz = (sizeof(PairJob) + 15) / 16 * 16;
+        const size_t o_dyn = 3 * jsz, o_cnt = o_dyn + 16, o_fl = o_cnt + 16;
         const size_t o_fl2 = o_fl + (size_t)m * 4, o_sj = o_fl2 + (size_t)m * 4, o_sm = o_sj + (size_t)m * 4;
         const size_t o_mask = o_sm + (size_t)m * 4;
         char* book = nullptr;
         double* part = nullptr;
         double* part2 = nullptr;
         PBN_CUDA_TRY(sc.alloc(&book, o_mask + (size_t)m));
-        PBN_CUDA_TRY(sc.alloc(&part, (size_t)n_acc * slots * m_pad * sizeof(double)));
         // second pass: slots' x m_pad' <= grid x TB + 2 (m + TB) whatever the flagged count is (see shift_prep_kernel)
         PBN_CUDA_TRY(sc.alloc(&part2, (size_t)n_acc * ((size_t)max_grid * TB + 2 * ((size_t)m + TB) + 64) * sizeof(double)));
         PairJob* d_job = reinterpret_cast<PairJob*>(book);
-        PairJob* d_job2 = reinterpret_cast<PairJob*>(book + o_dyn / 2);
+        PairJob* d_job2 = reinterpret_cast<PairJob*>(book + jsz);
+        PairJob* d_jobA = reinterpret_cast<PairJob*>(book + 2 * jsz);
         long long* dyn = reinterpret_cast<long long*>(book + o_dyn);
         int* n_flagged = reinterpret_cast<int*>(book + o_cnt);
         int* n_flagged2 = n_flagged + 1;
@@ -966,12 +1026,12 @@ static int logl_one(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const
         PBN_CUDA_TRY(cudaMemsetAsync(mask, 0, (size_t)m, st));
         PairJob job;
         memset(&job, 0, sizeof(job));
-        job.train = k->y;
+        job.train = train_y;
         job.test = ytest;
         job.part = part;
         job.bound_train = k->d_bound;
         job.bound_test = bound_test;
-        job.train_nrm = k->nrm;
+        job.train_nrm = train_nrm;
         job.test_nrm = nrm_test;
         job.n_train = k->n;
         job.m = m;
@@ -980,9 +1040,6 @@ static int logl_one(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const
         job.n_train_tiles = n_train_tiles;
         job.n_test_tiles = n_test_tiles;
         job.slots = slots;
-        write_job_kernel<<<1, 1, 0, st>>>(job, d_job, n_flagged);
-        ctx->launches++;
-        PBN_CUDA_TRY(cudaGetLastError());
         cudaEvent_t ev0 = nullptr, ev1 = nullptr;
         if (ctx->timing) {
             PBN_CUDA_TRY(cudaEventCreate(&ev0));
@@ -991,19 +1048,80 @@ static int logl_one(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const
             sc.events.push_back(ev1);
             PBN_CUDA_TRY(cudaEventRecord(ev0, st));
         }
-        cudaError_t e = f64 ? pbn::launch_pair_f64(d, k->ckde, d_job, 1, U, upb, grid, ctx->d_exp_tab, st)
-                            : pbn::launch_pair_f32(d, k->ckde, d_job, 1, U, upb, grid, ctx->d_exp_tab, st);
+        long long upbA = 1;
+        bool have_A = false;
+        ctx->last_units_total = U;
+        ctx->last_units_done = U;
+        if (use_skip) {
+            // pass A: every test tile against its nearest training tile -> lower bounds of the sums
+            const int ntt = n_test_tiles, ntr = n_train_tiles;
+            const size_t b_box = ((size_t)ntt * 2 * d * sizeof(float) + 255) / 256 * 256, b_ll = ((size_t)(ntt + 1) * 8 + 255) / 256 * 256;
+            char* sk = nullptr;
+            PBN_CUDA_TRY(sc.alloc(&sk, b_box + 3 * b_ll + 2 * (((size_t)ntt * 4 + 255) / 256 * 256) + ((size_t)ntt * 4 + 255) / 256 * 256));
+            float* box_test = reinterpret_cast<float*>(sk);
+            long long* iota = reinterpret_cast<long long*>(sk + b_box);
+            long long* count = reinterpret_cast<long long*>(sk + b_box + b_ll);
+            long long* tile_first = reinterpret_cast<long long*>(sk + b_box + 2 * b_ll);
+            float* thr = reinterpret_cast<float*>(sk + b_box + 3 * b_ll);
+            int* nearest = reinterpret_cast<int*>(sk + b_box + 3 * b_ll + 2 * (((size_t)ntt * 4 + 255) / 256 * 256));
+            double* partA = nullptr;
+            PBN_CUDA_TRY(sc.alloc(&partA, (size_t)n_acc * 2 * m_pad * sizeof(double)));
+            PBN_TRY(pbn_spatial_boxes(ctx, k->dtype, d, ytest, m, TB, box_test));
+            PBN_TRY(pbn_skip_nearest(ctx, box_test, ntt, k->box, ntr, d, nearest, iota));
+            PairJob jobA = job;
+            jobA.part = partA;
+            jobA.slots = 2;
+            jobA.unit_list = nearest;
+            jobA.tile_first = iota;
+            int gridA = (int)std::min<long long>(ntt, max_grid);
+            upbA = (ntt + gridA - 1) / gridA;
+            gridA = (int)((ntt + upbA - 1) / upbA);
+            write_job_kernel<<<1, 1, 0, st>>>(jobA, d_jobA, nullptr);
+            cudaError_t ea = f64 ? pbn::launch_pair_f64(d, k->ckde, d_jobA, 1, ntt, upbA, gridA, ctx->d_exp_tab, st)
+                                 : pbn::launch_pair_f32(d, k->ckde, d_jobA, 1, ntt, upbA, gridA, ctx->d_exp_tab, st);
+            ctx->launches += 2;
+            PBN_CUDA_TRY(ea);
+            // list B: the units the boxes cannot prove negligible (one small D2H of their number)
+            long long total = 0;
+            PBN_TRY(pbn_skip_count(ctx, d_jobA, upbA, TB, k->ckde ? 1 : 0, k->dtype, k->n, box_test, ntt, k->box, ntr, d, nearest, thr,
+                                   count, tile_first, &total));
+            int* unit_list = nullptr;
+            PBN_CUDA_TRY(sc.alloc(&unit_list, (size_t)std::max<long long>(total, 1) * sizeof(int)));
+            PBN_TRY(pbn_skip_fill(ctx, k->ckde ? 1 : 0, box_test, ntt, k->box, ntr, d, nearest, thr, tile_first, unit_list));
+            job.unit_list = unit_list;
+            job.tile_first = tile_first;
+            ctx->last_units_done = total + ntt;
+            have_A = true;
+            U = total;
+            grid = (int)std::max<long long>(1, std::min<long long>(U, max_grid));
+            upb = std::max<long long>(1, (U + grid - 1) / grid);
+            grid = (int)std::max<long long>(1, (U + upb - 1) / upb);
+            job.slots = slots = (int)std::min<long long>((n_train_tiles + upb - 1) / upb + 1, grid);
+        }
+        PBN_CUDA_TRY(sc.alloc(&part, (size_t)n_acc * slots * m_pad * sizeof(double)));
+        job.part = part;
+        write_job_kernel<<<1, 1, 0, st>>>(job, d_job, n_flagged);
         ctx->launches++;
-        PBN_CUDA_TRY(e);
+        PBN_CUDA_TRY(cudaGetLastError());
+        if (U > 0) {
+            cudaError_t e = f64 ? pbn::launch_pair_f64(d, k->ckde, d_job, 1, U, upb, grid, ctx->d_exp_tab, st)
+                                : pbn::launch_pair_f32(d, k->ckde, d_job, 1, U, upb, grid, ctx->d_exp_tab, st);
+            ctx->launches++;
+            PBN_CUDA_TRY(e);
+        }
         if (ctx->timing) {
             PBN_CUDA_TRY(cudaEventRecord(ev1, st));
             ctx->timed.emplace_back(ev0, ev1);
             sc.events.clear();  // owned by ctx->timed from here on
             ctx->pair_units += (int64_t)k->n * m * (k->ckde ? 2 : 1);
+            ctx->units_total += ctx->last_units_total;
+            ctx->units_done += ctx->last_units_done;
         }
         FinalizeParams F;
         F.job = d_job;
         F.upb = upb;
+        F.jobA = have_A ? d_jobA : nullptr;
+        F.upbA = upbA;
         F.tb = TB;
         F.ckde = k->ckde ? 1 : 0;
         F.lognorm_joint = k->lognorm_joint;
@@ -1026,6 +1144,9 @@ static int logl_one(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const
         SP.job.bound_test = nullptr;
         SP.job.train_nrm = nullptr;
         SP.job.test_nrm = nullptr;
+        SP.job.unit_list = nullptr;  // the second pass evaluates the flagged rows against EVERY training tile
+        SP.job.tile_first = nullptr;
+        SP.job.slots = 0;
         SP.job.shift_j = shift_j;
         SP.job.shift_m = shift_m;
         SP.job.test_rows = flagged;
@@ -1087,6 +1208,10 @@ static int logl_one(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const
         PBN_CUDA_TRY(cudaGetLastError());
     }
 
+    if (use_skip) {  // back to the caller's row order
+        PBN_TRY(pbn_scatter_out(ctx, out, perm, m, out_final));
+        out = out_final;
+    }
     double* d_sum = d_out_slogl;
     if (h_out_slogl || d_out_slogl) {
         int sb = (int)std::min<int64_t>((m + 255) / 256, (int64_t)ctx->sm_count * 4);
@@ -1265,6 +1390,21 @@ int pbn_ctx_pair_kernel_time(pbn_ctx* ctx, double* total_ms, int64_t* n_launches
 int pbn_ctx_last_fallback_rows(pbn_ctx* ctx, int64_t* out) {
     if (!ctx || !out) return set_error(PBN_ERR_ARG, "null argument");
     *out = ctx->last_fallback_rows;
+    return PBN_OK;
+}
+int pbn_ctx_set_skipping(pbn_ctx* ctx, int on) {
+    if (!ctx) return set_error(PBN_ERR_ARG, "null context");
+    ctx->skipping = on != 0;
+    for (pbn_ctx* p : ctx->peers) p->skipping = on != 0;
+    return PBN_OK;
+}
+int pbn_ctx_skip_stats(pbn_ctx* ctx, int64_t* last_total, int64_t* last_done, int64_t* timed_total, int64_t* timed_done, int reset) {
+    if (!ctx) return set_error(PBN_ERR_ARG, "null context");
+    if (last_total) *last_total = ctx->last_units_total;
+    if (last_done) *last_done = ctx->last_units_done;
+    if (timed_total) *timed_total = ctx->units_total;
+    if (timed_done) *timed_done = ctx->units_done;
+    if (reset) { ctx->units_total = 0; ctx->units_done = 0; }
     return PBN_OK;
 }
 int pbn_ctx_last_row_kernel_rows(pbn_ctx* ctx, int64_t* out) {
@@ -1474,6 +1614,7 @@ int pbn_kde_free(pbn_kde* k) {
     k->rep.clear();
     DevSetter ds(k->ctx->device);
     if (k->y) cudaFreeAsync(k->y, k->ctx->stream);
+    if (k->ys) cudaFreeAsync(k->ys, k->ctx->stream);
     delete k;
     return PBN_OK;
 }
