@@ -174,13 +174,13 @@ double lg_fit_from_moments(int64_t rows, int p, const double* mean, const double
 int pbn_spatial_sort(pbn_ctx* ctx, int dtype, int d, const void* y, const double* nrm, int64_t n, const float* bound, void* ys,
                      double* nrm_s, int* perm);
 int pbn_spatial_boxes(pbn_ctx* ctx, int dtype, int d, const void* ys, int64_t n, int tile_rows, float* box);
-int pbn_skip_nearest(pbn_ctx* ctx, const float* box_test, int n_test_tiles, const float* box_train, int n_train_tiles, int d, int* nearest,
-                     long long* iota);
+int pbn_skip_nearest(pbn_ctx* ctx, const float* box_test, int n_test_tiles, const float* box_train, int n_train_tiles, int d, int K,
+                     int* nearest, long long* first);
 int pbn_skip_count(pbn_ctx* ctx, const pbn::PairJob* d_jobA, long long upbA, int tb, int ckde, int dtype, int64_t n_train,
                    const float* box_test, int n_test_tiles, const float* box_train, int n_train_tiles, int d, const int* nearest,
-                   float* thr, long long* count, long long* tile_first, long long* total_out);
+                   int K, float* thr, long long* count, long long* tile_first, long long* total_out);
 int pbn_skip_fill(pbn_ctx* ctx, int ckde, const float* box_test, int n_test_tiles, const float* box_train, int n_train_tiles, int d,
-                  const int* nearest, const float* thr, const long long* tile_first, int* unit_list);
+                  const int* nearest, int K, const float* thr, const long long* tile_first, int* unit_list);
 int pbn_scatter_out(pbn_ctx* ctx, const double* src, const int* perm, int64_t n, double* dst);
 
 namespace pbn {

@@ -89,6 +89,8 @@ constexpr int kThreads = 256;
 // the pair kernel (log-likelihood and CDF modes) is instantiated for 1..kMaxFastD variables: north_star's family
 // sizes (d = 1..10); wider families take the generic row kernels
 constexpr int kMaxFastD = 10;
+// tile skipping (spatial.cu): training tiles per test tile evaluated first, to lower-bound the sums of its rows
+constexpr int kNearTiles = 8;
 #ifndef PBN_F64_UNROLL
 #define PBN_F64_UNROLL 4
 #endif

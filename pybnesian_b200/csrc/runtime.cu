@@ -311,10 +311,16 @@ __global__ void finalize_kernel(FinalizeParams P) {
             }
         }
     }
-    if (P.jobA) {  // one unit per test tile: one CTA, slot 0
+    if (P.jobA) {  // tile skipping, pass A: the nearest training tiles of this test tile
         const PairJob ja = *P.jobA;
-        sj += ja.part[row];
-        if (P.ckde) sm += ja.part[(long long)ja.slots * ja.m_pad + row];
+        const long long ufirst = ja.unit_begin + ja.tile_first[tt], ucount = ja.tile_first[tt + 1] - ja.tile_first[tt];
+        if (ucount > 0) {
+            const int first = (int)(ufirst / P.upbA), last = (int)((ufirst + ucount - 1) / P.upbA);
+            for (int s = 0; s <= last - first; ++s) {
+                sj += ja.part[(long long)s * ja.m_pad + row];
+                if (P.ckde) sm += ja.part[((long long)ja.slots + s) * ja.m_pad + row];
+            }
+        }
     }
     bool bad = !(sj >= P.thresh) || (P.ckde && !(sm >= P.thresh));
     // NaN sums (NaN inputs) are not "underflow": propagate them
@@ -1053,11 +1059,12 @@ static int logl_one(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const
         ctx->last_units_total = U;
         ctx->last_units_done = U;
         if (use_skip) {
-            // pass A: every test tile against its nearest training tile -> lower bounds of the sums
+            // pass A: every test tile against its nearest training tiles -> lower bounds of the sums
             const int ntt = n_test_tiles, ntr = n_train_tiles;
+            const int KA = std::min(pbn::kNearTiles, ntr);
             const size_t b_box = ((size_t)ntt * 2 * d * sizeof(float) + 255) / 256 * 256, b_ll = ((size_t)(ntt + 1) * 8 + 255) / 256 * 256;
             char* sk = nullptr;
-            PBN_CUDA_TRY(sc.alloc(&sk, b_box + 3 * b_ll + 2 * (((size_t)ntt * 4 + 255) / 256 * 256) + ((size_t)ntt * 4 + 255) / 256 * 256));
+            PBN_CUDA_TRY(sc.alloc(&sk, b_box + 3 * b_ll + 2 * (((size_t)ntt * 4 + 255) / 256 * 256) + ((size_t)ntt * KA * 4 + 255) / 256 * 256));
             float* box_test = reinterpret_cast<float*>(sk);
             long long* iota = reinterpret_cast<long long*>(sk + b_box);
             long long* count = reinterpret_cast<long long*>(sk + b_box + b_ll);
@@ -1065,32 +1072,33 @@ static int logl_one(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const
             float* thr = reinterpret_cast<float*>(sk + b_box + 3 * b_ll);
             int* nearest = reinterpret_cast<int*>(sk + b_box + 3 * b_ll + 2 * (((size_t)ntt * 4 + 255) / 256 * 256));
             double* partA = nullptr;
-            PBN_CUDA_TRY(sc.alloc(&partA, (size_t)n_acc * 2 * m_pad * sizeof(double)));
+            PBN_CUDA_TRY(sc.alloc(&partA, (size_t)n_acc * (KA + 1) * m_pad * sizeof(double)));
             PBN_TRY(pbn_spatial_boxes(ctx, k->dtype, d, ytest, m, TB, box_test));
-            PBN_TRY(pbn_skip_nearest(ctx, box_test, ntt, k->box, ntr, d, nearest, iota));
+            PBN_TRY(pbn_skip_nearest(ctx, box_test, ntt, k->box, ntr, d, KA, nearest, iota));
             PairJob jobA = job;
             jobA.part = partA;
-            jobA.slots = 2;
+            jobA.slots = KA + 1;  // KA consecutive units are shared by at most KA + 1 CTAs
             jobA.unit_list = nearest;
-            jobA.tile_first = iota;
-            int gridA = (int)std::min<long long>(ntt, max_grid);
-            upbA = (ntt + gridA - 1) / gridA;
-            gridA = (int)((ntt + upbA - 1) / upbA);
+            jobA.tile_first = iota;   // tile_first[tt] = tt * KA
+            const long long UA = (long long)ntt * KA;
+            int gridA = (int)std::min<long long>(UA, max_grid);
+            upbA = (UA + gridA - 1) / gridA;
+            gridA = (int)((UA + upbA - 1) / upbA);
             write_job_kernel<<<1, 1, 0, st>>>(jobA, d_jobA, nullptr);
-            cudaError_t ea = f64 ? pbn::launch_pair_f64(d, k->ckde, d_jobA, 1, ntt, upbA, gridA, ctx->d_exp_tab, st)
-                                 : pbn::launch_pair_f32(d, k->ckde, d_jobA, 1, ntt, upbA, gridA, ctx->d_exp_tab, st);
+            cudaError_t ea = f64 ? pbn::launch_pair_f64(d, k->ckde, d_jobA, 1, UA, upbA, gridA, ctx->d_exp_tab, st)
+                                 : pbn::launch_pair_f32(d, k->ckde, d_jobA, 1, UA, upbA, gridA, ctx->d_exp_tab, st);
             ctx->launches += 2;
             PBN_CUDA_TRY(ea);
             // list B: the units the boxes cannot prove negligible (one small D2H of their number)
             long long total = 0;
-            PBN_TRY(pbn_skip_count(ctx, d_jobA, upbA, TB, k->ckde ? 1 : 0, k->dtype, k->n, box_test, ntt, k->box, ntr, d, nearest, thr,
+            PBN_TRY(pbn_skip_count(ctx, d_jobA, upbA, TB, k->ckde ? 1 : 0, k->dtype, k->n, box_test, ntt, k->box, ntr, d, nearest, KA, thr,
                                    count, tile_first, &total));
             int* unit_list = nullptr;
             PBN_CUDA_TRY(sc.alloc(&unit_list, (size_t)std::max<long long>(total, 1) * sizeof(int)));
-            PBN_TRY(pbn_skip_fill(ctx, k->ckde ? 1 : 0, box_test, ntt, k->box, ntr, d, nearest, thr, tile_first, unit_list));
+            PBN_TRY(pbn_skip_fill(ctx, k->ckde ? 1 : 0, box_test, ntt, k->box, ntr, d, nearest, KA, thr, tile_first, unit_list));
             job.unit_list = unit_list;
             job.tile_first = tile_first;
-            ctx->last_units_done = total + ntt;
+            ctx->last_units_done = total + UA;
             have_A = true;
             U = total;
             grid = (int)std::max<long long>(1, std::min<long long>(U, max_grid));

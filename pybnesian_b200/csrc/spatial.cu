@@ -6,8 +6,8 @@
 // put in Morton order, every tile of rows gets a bounding box, and a (test tile, train tile) unit is dropped when the
 // boxes alone prove that ALL its terms together are below 2^-kSkipBits of every row's sum:
 //
-//   pass A   each test tile against its nearest train tile  ->  a lower bound S_lb(row) <= S(row) of every sum
-//   list B   units (tt, nt), nt != nearest(tt), with  n_train * 2^(-Dmin^2(tt, nt))  >  2^-kSkipBits * min_rows S_lb
+//   pass A   each test tile against its kNearTiles nearest train tiles  ->  a lower bound S_lb(row) <= S(row) of every sum
+//   list B   units (tt, nt), nt not among those, with  n_train * 2^(-Dmin^2(tt, nt))  >  2^-kSkipBits * min_rows S_lb
 //            (Dmin = distance between the two boxes, in kernel units; joint AND marginal coordinates for a CKDE)
 //   pass B   pair_kernel over list B (PairJob::unit_list); finalize adds the partial sums of A and B
 //
@@ -115,49 +115,66 @@ __device__ __forceinline__ float box_gap2(const float* __restrict__ a, const flo
     return s;
 }
 
-// nearest[tt] = the train tile closest to test tile tt (box distance, ties: closest box centres)
+// nearest[tt * K + j], j = 0 .. K-1: the K train tiles closest to test tile tt (box distance, ties: closest box centres, then
+// lowest index), in ascending tile order; K = min(kNearTiles, n_train_tiles).  One CTA per test tile, K selection rounds.
 __global__ void nearest_tile_kernel(const float* __restrict__ box_test, const float* __restrict__ box_train, int n_train_tiles, int D,
-                                    int* __restrict__ nearest) {
+                                    int K, int* __restrict__ nearest) {
     __shared__ float bt[2 * PBN_MAX_DIM];
     __shared__ float sbest[32][2];
     __shared__ int sidx[32];
+    __shared__ int chosen[pbn::kNearTiles];
     const int tt = blockIdx.x;
     if (threadIdx.x < 2 * D) bt[threadIdx.x] = box_test[(long long)tt * 2 * D + threadIdx.x];
     __syncthreads();
-    float best = INFINITY, bestc = INFINITY;
-    int bi = 0x7fffffff;
-    for (int nt = threadIdx.x; nt < n_train_tiles; nt += blockDim.x) {
-        const float* b = box_train + (long long)nt * 2 * D;
-        float g = box_gap2(bt, b, D, D);
-        float cd = 0.f;
-        for (int c = 0; c < D; ++c) {
-            const float dc = 0.5f * ((bt[c] + bt[D + c]) - (b[c] + b[D + c]));
-            cd = fmaf(dc, dc, cd);
+    for (int round = 0; round < K; ++round) {
+        float best = INFINITY, bestc = INFINITY;
+        int bi = 0x7fffffff;
+        for (int nt = threadIdx.x; nt < n_train_tiles; nt += blockDim.x) {
+            bool taken = false;
+            for (int q = 0; q < round; ++q) taken |= chosen[q] == nt;
+            if (taken) continue;
+            const float* b = box_train + (long long)nt * 2 * D;
+            float g = box_gap2(bt, b, D, D);
+            float cd = 0.f;
+            for (int c = 0; c < D; ++c) {
+                const float dc = 0.5f * ((bt[c] + bt[D + c]) - (b[c] + b[D + c]));
+                cd = fmaf(dc, dc, cd);
+            }
+            if (!(g == g)) g = 0.f;        // unbounded boxes count as touching
+            if (!(cd == cd)) cd = 0.f;
+            if (g < best || (g == best && (cd < bestc || (cd == bestc && nt < bi)))) { best = g; bestc = cd; bi = nt; }
         }
-        if (!(g == g)) g = 0.f;        // unbounded boxes count as touching
-        if (!(cd == cd)) cd = 0.f;
-        if (g < best || (g == best && (cd < bestc || (cd == bestc && nt < bi)))) { best = g; bestc = cd; bi = nt; }
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-        const float g = __shfl_xor_sync(0xffffffffu, best, o), cd = __shfl_xor_sync(0xffffffffu, bestc, o);
-        const int i = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (g < best || (g == best && (cd < bestc || (cd == bestc && i < bi)))) { best = g; bestc = cd; bi = i; }
-    }
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (lane == 0) { sbest[w][0] = best; sbest[w][1] = bestc; sidx[w] = bi; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int q = 1; q < (int)(blockDim.x >> 5); ++q) {
-            const float g = sbest[q][0], cd = sbest[q][1];
-            const int i = sidx[q];
+        for (int o = 16; o > 0; o >>= 1) {
+            const float g = __shfl_xor_sync(0xffffffffu, best, o), cd = __shfl_xor_sync(0xffffffffu, bestc, o);
+            const int i = __shfl_xor_sync(0xffffffffu, bi, o);
             if (g < best || (g == best && (cd < bestc || (cd == bestc && i < bi)))) { best = g; bestc = cd; bi = i; }
         }
-        nearest[tt] = bi == 0x7fffffff ? 0 : bi;
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        if (lane == 0) { sbest[w][0] = best; sbest[w][1] = bestc; sidx[w] = bi; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int q = 1; q < (int)(blockDim.x >> 5); ++q) {
+                const float g = sbest[q][0], cd = sbest[q][1];
+                const int i = sidx[q];
+                if (g < best || (g == best && (cd < bestc || (cd == bestc && i < bi)))) { best = g; bestc = cd; bi = i; }
+            }
+            chosen[round] = bi;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {  // ascending tile order (insertion sort of <= 8 entries)
+        for (int a = 1; a < K; ++a) {
+            const int v = chosen[a];
+            int b = a - 1;
+            while (b >= 0 && chosen[b] > v) { chosen[b + 1] = chosen[b]; --b; }
+            chosen[b + 1] = v;
+        }
+        for (int a = 0; a < K; ++a) nearest[(long long)tt * K + a] = chosen[a];
     }
 }
 
-__global__ void iota_kernel(long long* __restrict__ x, long long n) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) x[i] = i;
+__global__ void iota_kernel(long long* __restrict__ x, long long n, long long step) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) x[i] = i * step;
 }
 
 // thr[tt] (joint), thr[n_test_tiles + tt] (marginal): a unit whose box distance^2 reaches it is negligible for every row
@@ -176,12 +193,16 @@ __global__ void skip_threshold_kernel(LbParams P) {
     __shared__ double sh[2][32];
     const pbn::PairJob jb = *P.jobA;
     const long long tt = blockIdx.x;
-    const long long ustart = jb.unit_begin + tt;  // pass A: exactly one unit per test tile
-    const int first = (int)(ustart / P.upbA);
+    // pass A: tile_first[tt] .. tile_first[tt + 1] units, spread over the slots of the CTAs that shared them
+    const long long ufirst = jb.unit_begin + jb.tile_first[tt], ucount = jb.tile_first[tt + 1] - jb.tile_first[tt];
+    const int nslots = ucount > 0 ? (int)((ufirst + ucount - 1) / P.upbA - ufirst / P.upbA) + 1 : 0;
     double mj = INFINITY, mm = INFINITY;
     for (long long row = tt * P.tb + threadIdx.x; row < (tt + 1) * P.tb && row < jb.m; row += blockDim.x) {
-        double sj = jb.part[row], sm = P.ckde ? jb.part[(long long)jb.slots * jb.m_pad + row] : 1.0;
-        (void)first;  // one unit -> one CTA -> slot 0
+        double sj = 0.0, sm = P.ckde ? 0.0 : 1.0;
+        for (int q = 0; q < nslots; ++q) {
+            sj += jb.part[(long long)q * jb.m_pad + row];
+            if (P.ckde) sm += jb.part[((long long)jb.slots + q) * jb.m_pad + row];
+        }
         if (!(sj > 0.0) || !(sj < INFINITY)) sj = 0.0;
         if (!(sm > 0.0) || !(sm < INFINITY)) sm = 0.0;
         mj = fmin(mj, sj);
@@ -219,22 +240,25 @@ __device__ __forceinline__ bool unit_alive(const float* __restrict__ bt, const f
 // MODE 0: count[tt] = live units of test tile tt (nearest excluded: pass A did it).  MODE 1: write them, ascending.
 template <int MODE>
 __global__ void skip_list_kernel(const float* __restrict__ box_test, const float* __restrict__ box_train, int n_train_tiles, int D,
-                                 int ckde, const float* __restrict__ thr, const int* __restrict__ nearest, long long* __restrict__ count,
-                                 const long long* __restrict__ tile_first, int* __restrict__ unit_list) {
+                                 int ckde, const float* __restrict__ thr, const int* __restrict__ nearest, int K,
+                                 long long* __restrict__ count, const long long* __restrict__ tile_first, int* __restrict__ unit_list) {
     __shared__ float bt[2 * PBN_MAX_DIM];
     __shared__ int wsum[32];
     __shared__ long long base;
+    __shared__ int near_s[pbn::kNearTiles];
     const int tt = blockIdx.x;
     if (threadIdx.x < 2 * D) bt[threadIdx.x] = box_test[(long long)tt * 2 * D + threadIdx.x];
+    if (threadIdx.x < K) near_s[threadIdx.x] = nearest[(long long)tt * K + threadIdx.x];
     if (threadIdx.x == 0) base = MODE == 1 ? tile_first[tt] : 0;
     __syncthreads();
     const float tj = thr[tt], tm = thr[gridDim.x + tt];
-    const int near_nt = nearest[tt];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
     long long total = 0;
     for (int n0 = 0; n0 < n_train_tiles; n0 += blockDim.x) {
         const int nt = n0 + threadIdx.x;
-        const bool alive = nt < n_train_tiles && nt != near_nt && unit_alive(bt, box_train + (long long)nt * 2 * D, D, ckde, tj, tm);
+        bool in_a = false;
+        for (int q = 0; q < K; ++q) in_a |= near_s[q] == nt;
+        const bool alive = nt < n_train_tiles && !in_a && unit_alive(bt, box_train + (long long)nt * 2 * D, D, ckde, tj, tm);
         const unsigned bal = __ballot_sync(0xffffffffu, alive);
         if (lane == 0) wsum[w] = __popc(bal);
         __syncthreads();
@@ -360,11 +384,11 @@ int pbn_spatial_boxes(pbn_ctx* ctx, int dtype, int d, const void* ys, int64_t n,
     return PBN_OK;
 }
 
-int pbn_skip_nearest(pbn_ctx* ctx, const float* box_test, int n_test_tiles, const float* box_train, int n_train_tiles, int d, int* nearest,
-                     long long* iota) {
+int pbn_skip_nearest(pbn_ctx* ctx, const float* box_test, int n_test_tiles, const float* box_train, int n_train_tiles, int d, int K,
+                     int* nearest, long long* first) {
     cudaStream_t st = ctx->stream;
-    nearest_tile_kernel<<<n_test_tiles, 256, 0, st>>>(box_test, box_train, n_train_tiles, d, nearest);
-    iota_kernel<<<(n_test_tiles + 256) / 256, 256, 0, st>>>(iota, (long long)n_test_tiles + 1);
+    nearest_tile_kernel<<<n_test_tiles, 256, 0, st>>>(box_test, box_train, n_train_tiles, d, K, nearest);
+    iota_kernel<<<(n_test_tiles + 256) / 256, 256, 0, st>>>(first, (long long)n_test_tiles + 1, K);
     ctx->launches += 2;
     PBN_CUDA_TRY(cudaGetLastError());
     return PBN_OK;
@@ -372,7 +396,7 @@ int pbn_skip_nearest(pbn_ctx* ctx, const float* box_test, int n_test_tiles, cons
 
 int pbn_skip_count(pbn_ctx* ctx, const pbn::PairJob* d_jobA, long long upbA, int tb, int ckde, int dtype, int64_t n_train,
                    const float* box_test, int n_test_tiles, const float* box_train, int n_train_tiles, int d, const int* nearest,
-                   float* thr, long long* count, long long* tile_first, long long* total_out) {
+                   int K, float* thr, long long* count, long long* tile_first, long long* total_out) {
     cudaStream_t st = ctx->stream;
     LbParams P;
     P.jobA = d_jobA;
@@ -383,7 +407,7 @@ int pbn_skip_count(pbn_ctx* ctx, const pbn::PairJob* d_jobA, long long upbA, int
     P.log2_ntrain = log2((double)n_train);
     P.thr = thr;
     skip_threshold_kernel<<<n_test_tiles, 256, 0, st>>>(P);
-    skip_list_kernel<0><<<n_test_tiles, 256, 0, st>>>(box_test, box_train, n_train_tiles, d, ckde, thr, nearest, count, nullptr, nullptr);
+    skip_list_kernel<0><<<n_test_tiles, 256, 0, st>>>(box_test, box_train, n_train_tiles, d, ckde, thr, nearest, K, count, nullptr, nullptr);
     scan_counts_kernel<<<1, 1024, 0, st>>>(count, n_test_tiles, tile_first);
     ctx->launches += 3;
     PBN_CUDA_TRY(cudaGetLastError());
@@ -394,8 +418,8 @@ int pbn_skip_count(pbn_ctx* ctx, const pbn::PairJob* d_jobA, long long upbA, int
 }
 
 int pbn_skip_fill(pbn_ctx* ctx, int ckde, const float* box_test, int n_test_tiles, const float* box_train, int n_train_tiles, int d,
-                  const int* nearest, const float* thr, const long long* tile_first, int* unit_list) {
-    skip_list_kernel<1><<<n_test_tiles, 256, 0, ctx->stream>>>(box_test, box_train, n_train_tiles, d, ckde, thr, nearest, nullptr,
+                  const int* nearest, int K, const float* thr, const long long* tile_first, int* unit_list) {
+    skip_list_kernel<1><<<n_test_tiles, 256, 0, ctx->stream>>>(box_test, box_train, n_train_tiles, d, ckde, thr, nearest, K, nullptr,
                                                                tile_first, unit_list);
     ctx->launches++;
     PBN_CUDA_TRY(cudaGetLastError());
