@@ -398,7 +398,7 @@ def main():
     try:
         with open(os.path.join(ROOT, "profiles", "pair_kernel_traffic.json")) as f:
             for rec in json.load(f):
-                if rec.get("n_train") == n_train and rec.get("n_test") == (e_sh - b_sh) and rec.get("kernel") == "pair_kernel<double, 4, 1, 0>":
+                if rec.get("n_train") == n_train and rec.get("n_test") == (e_sh - b_sh) and rec.get("kernel", "").startswith("pair_kernel<double, 4, 1, 0"):
                     traffic = rec["dram_bytes_read"] + rec["dram_bytes_write"]
                     traffic_src = rec.get("source")
     except Exception:

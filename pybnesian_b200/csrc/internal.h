@@ -178,7 +178,7 @@ int pbn_skip_nearest(pbn_ctx* ctx, const float* box_test, int n_test_tiles, cons
                      int* nearest, long long* first);
 int pbn_skip_count(pbn_ctx* ctx, const pbn::PairJob* d_jobA, long long upbA, int tb, int ckde, int dtype, int64_t n_train,
                    const float* box_test, int n_test_tiles, const float* box_train, int n_train_tiles, int d, const int* nearest,
-                   int K, float* thr, long long* count, long long* tile_first, long long* total_out);
+                   int K, float* thr, double* sumsA, long long* count, long long* tile_first, long long* total_out);
 int pbn_skip_fill(pbn_ctx* ctx, int ckde, const float* box_test, int n_test_tiles, const float* box_train, int n_train_tiles, int d,
                   const int* nearest, int K, const float* thr, const long long* tile_first, int* unit_list);
 int pbn_scatter_out(pbn_ctx* ctx, const double* src, const int* perm, int64_t n, double* dst);

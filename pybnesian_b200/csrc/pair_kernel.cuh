@@ -62,6 +62,11 @@ struct PairJob {
     // tile inside a test tile; tile_first[tt] .. tile_first[tt + 1] delimits the units of test tile tt.  Null = full grid.
     const int* unit_list;
     const long long* tile_first;
+    // sums the FIRST CTA of every test tile starts from instead of zero: [n_acc][m_pad], the pass-A sums of tile skipping
+    // (finalize then reads pass B alone).  With rows in Morton order the near training tiles no longer turn up early by
+    // chance, so without them the running sums - and with them the exponent floor that keeps the table gathers free of
+    // bank conflicts (pair_floor) - would stay tiny for most of a tile's sweep.  Null = start from zero.
+    const double* init_sums;
 };
 
 // (test tile, train tile) of the job's `local`-th unit
@@ -923,6 +928,10 @@ pair_kernel(const PairJob* __restrict__ jobs, int n_jobs, long long total_units,
                 for (int c = 0; c < D; ++c) yt[r][c] = ok ? tp[src * D + c] : T(0);
                 sum_j[r] = 0.0;
                 sum_m[r] = 0.0;
+                if (!SHIFT && jb.init_sums && ok && jb.unit_begin + pair_tile_first(jb, tt) >= u0) {
+                    sum_j[r] = jb.init_sums[row];
+                    if (CKDE) sum_m[r] = jb.init_sums[jb.m_pad + row];
+                }
                 if constexpr (SHIFT) {
                     // shifts >= 2^31 kernel units cannot be carried on the integer side: such a row keeps a zero sum
                     // and falls through to the per-row kernel

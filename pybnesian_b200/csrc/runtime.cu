@@ -311,7 +311,9 @@ __global__ void finalize_kernel(FinalizeParams P) {
             }
         }
     }
-    if (P.jobA) {  // tile skipping, pass A: the nearest training tiles of this test tile
+    if (P.jobA && jb.tile_first[tt + 1] == jb.tile_first[tt]) {
+        // tile skipping: pass B starts from the pass-A sums (PairJob::init_sums); a test tile without any pass-B unit
+        // has only its pass-A slots
         const PairJob ja = *P.jobA;
         const long long ufirst = ja.unit_begin + ja.tile_first[tt], ucount = ja.tile_first[tt + 1] - ja.tile_first[tt];
         if (ucount > 0) {
@@ -1072,7 +1074,8 @@ static int logl_one(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const
             float* thr = reinterpret_cast<float*>(sk + b_box + 3 * b_ll);
             int* nearest = reinterpret_cast<int*>(sk + b_box + 3 * b_ll + 2 * (((size_t)ntt * 4 + 255) / 256 * 256));
             double* partA = nullptr;
-            PBN_CUDA_TRY(sc.alloc(&partA, (size_t)n_acc * (KA + 1) * m_pad * sizeof(double)));
+            PBN_CUDA_TRY(sc.alloc(&partA, (size_t)n_acc * (KA + 2) * m_pad * sizeof(double)));
+            double* sumsA = partA + (size_t)n_acc * (KA + 1) * m_pad;  // [n_acc][m_pad]: pass-A sums per row
             PBN_TRY(pbn_spatial_boxes(ctx, k->dtype, d, ytest, m, TB, box_test));
             PBN_TRY(pbn_skip_nearest(ctx, box_test, ntt, k->box, ntr, d, KA, nearest, iota));
             PairJob jobA = job;
@@ -1092,12 +1095,13 @@ static int logl_one(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const
             // list B: the units the boxes cannot prove negligible (one small D2H of their number)
             long long total = 0;
             PBN_TRY(pbn_skip_count(ctx, d_jobA, upbA, TB, k->ckde ? 1 : 0, k->dtype, k->n, box_test, ntt, k->box, ntr, d, nearest, KA, thr,
-                                   count, tile_first, &total));
+                                   sumsA, count, tile_first, &total));
             int* unit_list = nullptr;
             PBN_CUDA_TRY(sc.alloc(&unit_list, (size_t)std::max<long long>(total, 1) * sizeof(int)));
             PBN_TRY(pbn_skip_fill(ctx, k->ckde ? 1 : 0, box_test, ntt, k->box, ntr, d, nearest, KA, thr, tile_first, unit_list));
             job.unit_list = unit_list;
             job.tile_first = tile_first;
+            job.init_sums = sumsA;  // pass B continues the pass-A sums
             ctx->last_units_done = total + UA;
             have_A = true;
             U = total;
@@ -1154,6 +1158,7 @@ static int logl_one(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const
         SP.job.test_nrm = nullptr;
         SP.job.unit_list = nullptr;  // the second pass evaluates the flagged rows against EVERY training tile
         SP.job.tile_first = nullptr;
+        SP.job.init_sums = nullptr;
         SP.job.slots = 0;
         SP.job.shift_j = shift_j;
         SP.job.shift_m = shift_m;

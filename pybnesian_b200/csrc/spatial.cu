@@ -12,8 +12,8 @@
 //   pass B   pair_kernel over list B (PairJob::unit_list); finalize adds the partial sums of A and B
 //
 // The terms of all dropped units of a row sum to less than 2^-kSkipBits S(row): a relative change of the sum, and an
-// absolute change of logl, below 3.6e-15 for kSkipBits = 48 - four orders inside the 1e-10 bar, no different in kind from
-// the rounding of the sums.  Results are written back in the caller's row order.
+// absolute change of logl, below 9.1e-13 for kSkipBits = 40 - two orders inside the 1e-10 bar even for a CKDE value that
+// happens to be ~1e-2.  Results are written back in the caller's row order.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -24,7 +24,7 @@
 
 namespace {
 
-constexpr int kSkipBits = 48;
+constexpr int kSkipBits = 40;
 
 // ---- Morton keys ------------------------------------------------------------------------------------------------
 // coordinate c of a row, quantised to `bits` bits over [-B, B] (B = largest |whitened coordinate| of the set)
@@ -187,6 +187,7 @@ struct LbParams {
     double unit_per_binade;  // kernel exponent units per factor 2 (K for f64, 1 for f32)
     double log2_ntrain;
     float* thr;
+    double* sums;  // [n_acc][m_pad]: the pass-A sums of every row (PairJob::init_sums of pass B)
 };
 
 __global__ void skip_threshold_kernel(LbParams P) {
@@ -203,6 +204,8 @@ __global__ void skip_threshold_kernel(LbParams P) {
             sj += jb.part[(long long)q * jb.m_pad + row];
             if (P.ckde) sm += jb.part[((long long)jb.slots + q) * jb.m_pad + row];
         }
+        P.sums[row] = sj;
+        if (P.ckde) P.sums[jb.m_pad + row] = sm;
         if (!(sj > 0.0) || !(sj < INFINITY)) sj = 0.0;
         if (!(sm > 0.0) || !(sm < INFINITY)) sm = 0.0;
         mj = fmin(mj, sj);
@@ -396,7 +399,7 @@ int pbn_skip_nearest(pbn_ctx* ctx, const float* box_test, int n_test_tiles, cons
 
 int pbn_skip_count(pbn_ctx* ctx, const pbn::PairJob* d_jobA, long long upbA, int tb, int ckde, int dtype, int64_t n_train,
                    const float* box_test, int n_test_tiles, const float* box_train, int n_train_tiles, int d, const int* nearest,
-                   int K, float* thr, long long* count, long long* tile_first, long long* total_out) {
+                   int K, float* thr, double* sumsA, long long* count, long long* tile_first, long long* total_out) {
     cudaStream_t st = ctx->stream;
     LbParams P;
     P.jobA = d_jobA;
@@ -406,6 +409,7 @@ int pbn_skip_count(pbn_ctx* ctx, const pbn::PairJob* d_jobA, long long upbA, int
     P.unit_per_binade = dtype == PBN_F64 ? (double)pbn::kExpTab : 1.0;
     P.log2_ntrain = log2((double)n_train);
     P.thr = thr;
+    P.sums = sumsA;
     skip_threshold_kernel<<<n_test_tiles, 256, 0, st>>>(P);
     skip_list_kernel<0><<<n_test_tiles, 256, 0, st>>>(box_test, box_train, n_train_tiles, d, ckde, thr, nearest, K, count, nullptr, nullptr);
     scan_counts_kernel<<<1, 1024, 0, st>>>(count, n_test_tiles, tile_first);

@@ -44,10 +44,10 @@ def test_skipping_matches_all_pairs(pbn, kind, variables, dtype):
     # float64: only the order of the partial sums changes.  float32: the Morton order regroups the per-tile FLOAT partial
     # sums (near terms now meet in the same tiles instead of being absorbed one by one into a large partial sum), which
     # moves a row by a few float ulps - still two orders inside the 1e-4 bar
-    tol = 1e-12 if dtype == "float64" else 2e-6
+    tol = 1e-12 if dtype == "float64" else 5e-6
     assert np.max(np.abs(on - off) / scale) < tol                  # ... and nothing that matters
     s_off, s_on, _ = both(pbn, lambda: f.slogl(fte))
-    assert abs(s_on - s_off) <= (1e-13 if dtype == "float64" else 2e-6) * abs(s_off)
+    assert abs(s_on - s_off) <= (1e-12 if dtype == "float64" else 2e-6) * abs(s_off)
     assert abs(s_on - on.sum()) <= 1e-12 * abs(s_on)
     # and against the oracle on a sub-sample (row order: the caller's)
     rows = np.random.default_rng(1).choice(m, 200, replace=False)
