@@ -509,7 +509,16 @@ __device__ __forceinline__ void tile_f32_shift(const float* __restrict__ tp, int
 #ifndef PBN_F64_HOIST
 #define PBN_F64_HOIST 1
 #endif
-template <int D, bool CKDE, int R, bool CDF>
+// WSKIP (tile skipping on, rows in Morton order): a warp whose 32 rows ALL have this training point's term at or below
+// their exponent floor skips the exp2 of that term altogether - the term would have been evaluated AS the floor, i.e. as
+// less than 2^-kFloorBits of the sum it joins (pair_floor), so dropping it changes the finished sum by less than the
+// floor mechanism itself already does.  The exponent (dot product, rounding) is still computed for every pair; what is
+// saved is 5 of the 6 FP64 instructions of the exp2 and its table gather, for the large majority of the pairs of a
+// localised kernel sum.  Only worthwhile when neighbouring lanes hold neighbouring rows, hence tied to the Morton order.
+#ifndef PBN_F64_WARPSKIP
+#define PBN_F64_WARPSKIP 1
+#endif
+template <int D, bool CKDE, int R, bool CDF, bool WSKIP = false>
 __device__ __forceinline__ void tile_f64_dot(const double* __restrict__ tp, const double* __restrict__ nb, int cnt,
                                              const double (&yt)[R][D], const double (&at)[R], const int (&ati)[R],
                                              const double* __restrict__ tab, double (&sum_j)[R], double (&sum_m)[R],
@@ -541,25 +550,39 @@ __device__ __forceinline__ void tile_f64_dot(const double* __restrict__ tp, cons
 #pragma unroll
             for (int c = 0; c < DN; ++c) acc = fma(yt[r][c], p[c], acc);
             if (CKDE) {
-                double st;
-                double pm = exp2_tab<false>(acc, tab, st, ns, fl_m[r]);
-                if (CDF) {
-                    w = st * pm;
-                    sum_m[r] += w;
-                } else {
-                    sum_m[r] = fma(st, pm, sum_m[r]);
+                bool live = true;
+                if (WSKIP) {
+                    const int n0 = static_cast<int>(static_cast<unsigned>(__double2loint(acc + 6755399441055744.0)) + static_cast<unsigned>(ns));
+                    live = !__all_sync(0xffffffffu, n0 <= fl_m[r]);
+                }
+                if (live) {
+                    double st;
+                    double pm = exp2_tab<false>(acc, tab, st, ns, fl_m[r]);
+                    if (CDF) {
+                        w = st * pm;
+                        sum_m[r] += w;
+                    } else {
+                        sum_m[r] = fma(st, pm, sum_m[r]);
+                    }
                 }
                 double dl = yt[r][D - 1] - p[D - 1];
                 dl_last = dl;
                 acc = fma(-dl, dl, acc);
             }
-            double st;
-            double pj = exp2_tab<false>(acc, tab, st, ns, fl_j[r]);
-            if (CDF && CKDE) {
-                double q = (st * pj) * normal_tail_tg(fabs(dl_last) * inv_c);
-                sum_j[r] += (dl_last < 0.0) ? q : (w - q);
-            } else {
-                sum_j[r] = fma(st, pj, sum_j[r]);
+            bool livej = true;
+            if (WSKIP) {
+                const int n0 = static_cast<int>(static_cast<unsigned>(__double2loint(acc + 6755399441055744.0)) + static_cast<unsigned>(ns));
+                livej = !__all_sync(0xffffffffu, n0 <= fl_j[r]);
+            }
+            if (livej) {
+                double st;
+                double pj = exp2_tab<false>(acc, tab, st, ns, fl_j[r]);
+                if (CDF && CKDE) {
+                    double q = (st * pj) * normal_tail_tg(fabs(dl_last) * inv_c);
+                    sum_j[r] += (dl_last < 0.0) ? q : (w - q);
+                } else {
+                    sum_j[r] = fma(st, pj, sum_j[r]);
+                }
             }
         }
     }
@@ -988,8 +1011,12 @@ pair_kernel(const PairJob* __restrict__ jobs, int n_jobs, long long total_units,
         } else if constexpr (SHIFT) {
             tile_f32_shift<D, CKDE, R>(tp, cnt, yt, shj, shm, sum_j, sum_m);
         } else if constexpr (sizeof(T) == 8) {
-            if (DOT && dot)
-                tile_f64_dot<D, CKDE, R, CDF>(tp, nrm_buf + static_cast<size_t>(stage) * TILE, cnt, yt, at, ati, tab, sum_j, sum_m, inv_c);
+            if (DOT && dot) {
+                if (PBN_F64_WARPSKIP && !CDF && jb.unit_list)
+                    tile_f64_dot<D, CKDE, R, CDF, true>(tp, nrm_buf + static_cast<size_t>(stage) * TILE, cnt, yt, at, ati, tab, sum_j, sum_m, inv_c);
+                else
+                    tile_f64_dot<D, CKDE, R, CDF>(tp, nrm_buf + static_cast<size_t>(stage) * TILE, cnt, yt, at, ati, tab, sum_j, sum_m, inv_c);
+            }
             else if (safe)
                 tile_f64<D, CKDE, true, R, CDF>(tp, cnt, yt, tab, sum_j, sum_m, inv_c);
             else
