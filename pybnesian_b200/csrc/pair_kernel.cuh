@@ -515,8 +515,12 @@ __device__ __forceinline__ void tile_f32_shift(const float* __restrict__ tp, int
 // floor mechanism itself already does.  The exponent (dot product, rounding) is still computed for every pair; what is
 // saved is 5 of the 6 FP64 instructions of the exp2 and its table gather, for the large majority of the pairs of a
 // localised kernel sum.  Only worthwhile when neighbouring lanes hold neighbouring rows, hence tied to the Morton order.
+// MEASURED (B200, 1M x 1M, round 2, profiles/r2_tuning.md): slower than evaluating the floor terms - KDE d=2 5.03e12 ->
+// 3.58e12, d=4 1.67e12 -> 1.39e12 pair-evals/s with skipping on: the 24 warp-uniform branches per unrolled step cut the
+// 12 independent exp2 chains the scheduler interleaves into short dependent runs, and four warps per scheduler cannot
+// hide them.  Kept as a build option, off.
 #ifndef PBN_F64_WARPSKIP
-#define PBN_F64_WARPSKIP 1
+#define PBN_F64_WARPSKIP 0
 #endif
 template <int D, bool CKDE, int R, bool CDF, bool WSKIP = false>
 __device__ __forceinline__ void tile_f64_dot(const double* __restrict__ tp, const double* __restrict__ nb, int cnt,
@@ -942,6 +946,8 @@ pair_kernel(const PairJob* __restrict__ jobs, int n_jobs, long long total_units,
             cur_job = cj;
             cur_tt = tt;
             const T* tp = reinterpret_cast<const T*>(jb.test);
+            // the first CTA of a test tile continues the sums the job brings along (PairJob::init_sums)
+            const bool inited = !SHIFT && jb.init_sums && jb.unit_begin + pair_tile_first(jb, tt) >= u0;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 long long row = tt * TB + r * kThreads + tid;
@@ -951,7 +957,7 @@ pair_kernel(const PairJob* __restrict__ jobs, int n_jobs, long long total_units,
                 for (int c = 0; c < D; ++c) yt[r][c] = ok ? tp[src * D + c] : T(0);
                 sum_j[r] = 0.0;
                 sum_m[r] = 0.0;
-                if (!SHIFT && jb.init_sums && ok && jb.unit_begin + pair_tile_first(jb, tt) >= u0) {
+                if (!SHIFT && inited && ok) {
                     sum_j[r] = jb.init_sums[row];
                     if (CKDE) sum_m[r] = jb.init_sums[jb.m_pad + row];
                 }
@@ -992,6 +998,10 @@ pair_kernel(const PairJob* __restrict__ jobs, int n_jobs, long long total_units,
                             const double ai = rint(at[r]);  // |at| < 2^31 (the `safe` test above)
                             row_scale[r] = exp((at[r] - ai) * kExpA);
                             ati[r] = static_cast<int>(ai);
+                            if (inited) {  // the running sums of this form lack the factor row_scale until flush
+                                sum_j[r] /= row_scale[r];
+                                if (CKDE) sum_m[r] /= row_scale[r];
+                            }
 #endif
 #pragma unroll
                             for (int c = 0; c < DN; ++c) yt[r][c] *= T(2);

@@ -972,6 +972,9 @@ static int logl_one(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const
     const double* train_nrm = k->nrm;
     int* perm = nullptr;
     double* out_final = out;
+    char* ytest_raw = ytest;          // the caller's row order: what the call falls back to when the boxes prove too little
+    double* nrm_raw = nrm_test;
+    bool use_sorted = use_skip;
     if (use_skip) {
         char* ys_test = nullptr;
         PBN_CUDA_TRY(sc.alloc(&ys_test, ytbytes + tnbytes));
@@ -1096,6 +1099,22 @@ static int logl_one(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const
             long long total = 0;
             PBN_TRY(pbn_skip_count(ctx, d_jobA, upbA, TB, k->ckde ? 1 : 0, k->dtype, k->n, box_test, ntt, k->box, ntr, d, nearest, KA, thr,
                                    sumsA, count, tile_first, &total));
+            if ((double)(total + UA) > 0.92 * (double)ctx->last_units_total) {
+                // (almost) nothing can be dropped - families of 6+ variables at these sizes: every pair is evaluated, in
+                // the caller's row order, where the exponent floor of pair_floor works best
+                use_sorted = false;
+                ytest = ytest_raw;
+                nrm_test = nrm_raw;
+                out = out_final;
+                job.train = k->y;
+                job.train_nrm = k->nrm;
+                job.test = ytest;
+                job.test_nrm = nrm_test;
+                R.train = k->y;
+                R.test = ytest;
+                R.out = out;
+                goto plain_launch;
+            }
             int* unit_list = nullptr;
             PBN_CUDA_TRY(sc.alloc(&unit_list, (size_t)std::max<long long>(total, 1) * sizeof(int)));
             PBN_TRY(pbn_skip_fill(ctx, k->ckde ? 1 : 0, box_test, ntt, k->box, ntr, d, nearest, KA, thr, tile_first, unit_list));
@@ -1110,6 +1129,7 @@ static int logl_one(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const
             grid = (int)std::max<long long>(1, (U + upb - 1) / upb);
             job.slots = slots = (int)std::min<long long>((n_train_tiles + upb - 1) / upb + 1, grid);
         }
+    plain_launch:
         PBN_CUDA_TRY(sc.alloc(&part, (size_t)n_acc * slots * m_pad * sizeof(double)));
         job.part = part;
         write_job_kernel<<<1, 1, 0, st>>>(job, d_job, n_flagged);
@@ -1171,7 +1191,7 @@ static int logl_one(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const
         SP.n_flagged2 = n_flagged2;
         shift_prep_kernel<<<1, 1, 0, st>>>(SP);
         // few flagged rows: split the training rows so that the scan still spreads over the GPU
-        dim3 rmgrid((unsigned)std::min<int64_t>((m + 255) / 256, 4096), 8);
+        dim3 rmgrid((unsigned)std::min<int64_t>((m + 255) / 256, (int64_t)ctx->sm_count * 2), 8);
         cudaError_t e2 = f64 ? launch_rowmin<double>(d, k->ckde, rmgrid, st, k->y, k->n, ytest, flagged, n_flagged, shift_j, shift_m)
                              : launch_rowmin<float>(d, k->ckde, rmgrid, st, k->y, k->n, ytest, flagged, n_flagged, shift_j, shift_m);
         PBN_CUDA_TRY(e2);
@@ -1221,7 +1241,7 @@ static int logl_one(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const
         PBN_CUDA_TRY(cudaGetLastError());
     }
 
-    if (use_skip) {  // back to the caller's row order
+    if (use_sorted) {  // back to the caller's row order
         PBN_TRY(pbn_scatter_out(ctx, out, perm, m, out_final));
         out = out_final;
     }
