@@ -71,6 +71,11 @@ int pbn_ctx_create(int device, pbn_ctx** out);
  * number of devices (last-bit rounding of the partial sums) but not on timing.  There is no device-to-device traffic.
  * Every other entry point runs on devices[0].  Small calls stay on devices[0] as well. */
 int pbn_ctx_create_multi(const int* devices, int n, pbn_ctx** out);
+/* Loads the kernel modules on every device of the context now instead of at the first compute call (~2 s of CUDA
+ * module loading for the instantiations of the pair kernel); may be called from another host thread while the caller
+ * prepares its data. The reference pays the equivalent - OpenCL program build - lazily per kernel
+ * (opencl/opencl_config.cpp:23-147). */
+int pbn_ctx_warmup(pbn_ctx* ctx);
 int pbn_ctx_num_devices(pbn_ctx* ctx);
 int pbn_ctx_device(pbn_ctx* ctx, int i); /* CUDA ordinal of the i-th device of the context, -1 if out of range */
 int pbn_ctx_destroy(pbn_ctx* ctx);

@@ -17,7 +17,7 @@ BW_NORMAL_REFERENCE, BW_SCOTT = 0, 1
 
 EXPORTS = [
     "pbn_last_error", "pbn_version", "pbn_device_count", "pbn_ctx_create", "pbn_ctx_create_multi", "pbn_ctx_num_devices",
-    "pbn_ctx_device", "pbn_cv_score_jobs", "pbn_ctx_set_skipping", "pbn_ctx_skip_stats", "pbn_ctx_destroy", "pbn_ctx_set_stream",
+    "pbn_ctx_device", "pbn_ctx_warmup", "pbn_cv_score_jobs", "pbn_ctx_set_skipping", "pbn_ctx_skip_stats", "pbn_ctx_destroy", "pbn_ctx_set_stream",
     "pbn_ctx_stream", "pbn_ctx_synchronize", "pbn_ctx_sm_count", "pbn_ctx_counters", "pbn_table_upload",
     "pbn_table_free", "pbn_table_rows", "pbn_table_cols", "pbn_table_download", "pbn_table_moments", "pbn_bandwidth",
     "pbn_diag_bandwidth", "pbn_kde_fit", "pbn_ckde_fit", "pbn_product_kde_fit", "pbn_kde_free", "pbn_kde_num_instances", "pbn_kde_lognorm",
@@ -76,6 +76,7 @@ def lib():
         L.pbn_ctx_create.argtypes = [ci, ctypes.POINTER(vp)]
         L.pbn_ctx_create_multi.argtypes = [ip, ci, ctypes.POINTER(vp)]
         L.pbn_ctx_num_devices.argtypes = [vp]
+        L.pbn_ctx_warmup.argtypes = [vp]
         L.pbn_ctx_device.argtypes = [vp, ci]
         L.pbn_ctx_destroy.argtypes = [vp]
         L.pbn_ctx_set_stream.argtypes = [vp, vp]
@@ -197,6 +198,13 @@ class Context:
             check(lib().pbn_ctx_create(int(device), ctypes.byref(self.handle)))
             self.devices = [int(device)]
         self.device = self.devices[0]
+        # load the kernel modules in the background (ctypes releases the GIL): the first fit / logl call then finds them ready
+        if os.environ.get("PBN_CUDA_WARMUP", "1") != "0":
+            threading.Thread(target=lib().pbn_ctx_warmup, args=(self.handle,), daemon=True).start()
+
+    def warmup(self):
+        """Blocks until the kernel modules are loaded on every device of the context."""
+        check(lib().pbn_ctx_warmup(self.handle))
 
     @property
     def num_devices(self):

@@ -206,5 +206,9 @@ int pair_tb_for_f32(int D, bool ckde);
 int pair_tb_cdf_f64(int D);  // CDF mode of pair_kernel
 int pair_ctas_per_sm_f64();  // persistent CTAs per SM the kernels are register-bounded for (the launch grid multiplier)
 int pair_ctas_per_sm_f32();
+cudaError_t warm_pair_f64();
+cudaError_t warm_pair_f32();
+cudaError_t warm_pair_shift_f64();
+cudaError_t warm_pair_shift_f32();
 int pair_tb_cdf_f32(int D);
 }  // namespace pbn

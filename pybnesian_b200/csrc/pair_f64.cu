@@ -6,5 +6,6 @@
 #define PBN_TB_FOR_NAME pair_tb_for_f64
 #define PBN_TB_CDF_NAME pair_tb_cdf_f64
 #define PBN_CTAS_NAME pair_ctas_per_sm_f64
+#define PBN_WARM_NAME warm_pair_f64
 #define PBN_CDF_LAUNCH_NAME launch_cdf_f64
 #include "pair_launch.inl"

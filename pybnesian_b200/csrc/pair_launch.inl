@@ -56,6 +56,11 @@ int PBN_TB_NAME() { return kThreads * PairCfg<PBN_T>::R; }
 int PBN_TB_FOR_NAME(int D, bool ckde) { return kThreads * pair_rows<PBN_T>(D, ckde); }
 int PBN_TB_CDF_NAME(int D) { return kThreads * pair_rows_cdf<PBN_T>(D); }
 int PBN_CTAS_NAME() { return PairCfg<PBN_T>::MIN_CTAS; }
+// touches one kernel of this translation unit so that its module is loaded (pbn_ctx_warmup)
+cudaError_t PBN_WARM_NAME() {
+    cudaFuncAttributes a;
+    return cudaFuncGetAttributes(&a, pair_kernel<PBN_T, 4, true, false, false>);
+}
 
 #endif  // PBN_LAUNCH_NAME
 
@@ -75,6 +80,11 @@ cudaError_t PBN_SHIFT_LAUNCH_NAME(int D, bool ckde, const PairJob* job, const lo
             return cudaErrorInvalidValue;
     }
 #undef PBN_CASE
+}
+
+cudaError_t PBN_SHIFT_WARM_NAME() {
+    cudaFuncAttributes a;
+    return cudaFuncGetAttributes(&a, pair_kernel<PBN_T, 4, true, false, true>);
 }
 
 #endif  // PBN_SHIFT_LAUNCH_NAME

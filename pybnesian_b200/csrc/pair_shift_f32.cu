@@ -2,4 +2,5 @@
 // translation unit so that it builds in parallel with pair_f32.cu.
 #define PBN_T float
 #define PBN_SHIFT_LAUNCH_NAME launch_pair_shift_f32
+#define PBN_SHIFT_WARM_NAME warm_pair_shift_f32
 #include "pair_launch.inl"

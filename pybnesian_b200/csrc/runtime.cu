@@ -1425,6 +1425,23 @@ int pbn_ctx_last_fallback_rows(pbn_ctx* ctx, int64_t* out) {
     *out = ctx->last_fallback_rows;
     return PBN_OK;
 }
+// Loads the kernel modules of every device of the context (CUDA loads a module on the first use of one of its kernels:
+// ~2 s for the pair kernels' instantiations, which the first fit / logl / score call would otherwise pay).  Safe to call
+// from another host thread while data are being prepared; pybnesian_b200 does so when a context is created.
+int pbn_ctx_warmup(pbn_ctx* ctx) {
+    if (!ctx) return set_error(PBN_ERR_ARG, "null context");
+    return pbn_run_on_devices(pbn_num_devices(ctx), [&](int i) {
+        pbn_ctx* c = pbn_device_ctx(ctx, i);
+        DevSetter ds(c->device);
+        PBN_CUDA_TRY(pbn::warm_pair_f64());
+        PBN_CUDA_TRY(pbn::warm_pair_f32());
+        PBN_CUDA_TRY(pbn::warm_pair_shift_f64());
+        PBN_CUDA_TRY(pbn::warm_pair_shift_f32());
+        cudaFuncAttributes a;
+        PBN_CUDA_TRY(cudaFuncGetAttributes(&a, finalize_kernel));
+        return PBN_OK;
+    });
+}
 int pbn_ctx_set_skipping(pbn_ctx* ctx, int on) {
     if (!ctx) return set_error(PBN_ERR_ARG, "null context");
     ctx->skipping = on != 0;
