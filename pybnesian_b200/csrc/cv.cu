@@ -929,7 +929,8 @@ extern "C" int pbn_cv_score_jobs(pbn_ctx* ctx, pbn_cv* cv, const pbn_cv_item* it
     };
     for (int d = 1; d <= kMaxFast; ++d)
         for (int j : groups[d]) total_cost += job_cost(j);
-    if (nd > 1 && pbn_replicated(ctx, cv) && total_cost >= 4.0e9 * nd) {
+    // (cost = training rows x test rows x variables; below ~1 ms of kernel time per device one device is faster)
+    if (nd > 1 && pbn_replicated(ctx, cv) && total_cost >= 1.5e9 * nd) {
         // deal: most expensive first (ties by position), round-robin; a device keeps its jobs in their original order
         std::vector<int> order;
         for (int d = 1; d <= kMaxFast; ++d) order.insert(order.end(), groups[d].begin(), groups[d].end());

@@ -112,6 +112,9 @@ int pbn_run_on_devices(int n, const std::function<int(int)>& fn);
 // rows [begin, end) of the virtual row order of a two-segment range
 pbn_rows pbn_sub_rows(const pbn_rows& r, int64_t begin, int64_t end);
 
+// coordinates of the Morton key of a fitted model (spatial.cu): the evidence coordinates for a CKDE unless PBN_MORTON_JOINT=1
+int pbn_morton_dims(const pbn_kde* k);
+
 static inline size_t elem_size(int dtype) { return dtype == PBN_F64 ? 8 : 4; }
 static inline int64_t seg_count(const pbn_rows& r) { return (r.e0 - r.b0) + (r.e1 - r.b1); }
 
@@ -171,7 +174,7 @@ int pbn_logl_impl(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const i
 double lg_fit_from_moments(int64_t rows, int p, const double* mean, const double* Cm, double* beta);
 
 // ---- spatial order and tile skipping (spatial.cu) ----
-int pbn_spatial_sort(pbn_ctx* ctx, int dtype, int d, const void* y, const double* nrm, int64_t n, const float* bound, void* ys,
+int pbn_spatial_sort(pbn_ctx* ctx, int dtype, int d, int dk, const void* y, const double* nrm, int64_t n, const float* bound, void* ys,
                      double* nrm_s, int* perm);
 int pbn_spatial_boxes(pbn_ctx* ctx, int dtype, int d, const void* ys, int64_t n, int tile_rows, float* box);
 int pbn_skip_nearest(pbn_ctx* ctx, const float* box_test, int n_test_tiles, const float* box_train, int n_train_tiles, int d, int K,

@@ -9,6 +9,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -47,6 +48,11 @@ int pbn_run_on_devices(int n, const std::function<int(int)>& fn) {
     for (int i = 0; i < n; ++i)
         if (rc[i] != PBN_OK) return set_error(rc[i], msg[i]);
     return PBN_OK;
+}
+
+int pbn_morton_dims(const pbn_kde* k) {
+    static const bool joint = [] { const char* e = getenv("PBN_MORTON_JOINT"); return e && e[0] == '1'; }();
+    return (k->ckde && !joint) ? k->d - 1 : k->d;
 }
 
 pbn_rows pbn_sub_rows(const pbn_rows& r, int64_t begin, int64_t end) {
@@ -847,7 +853,7 @@ static int fit_one(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, p
             k->nrm_s = nbytes ? reinterpret_cast<double*>(static_cast<char*>(k->ys) + ybytes) : nullptr;
             k->box = reinterpret_cast<float*>(static_cast<char*>(k->ys) + ybytes + nbytes);
             k->n_box_tiles = n_tiles;
-            rc = pbn_spatial_sort(ctx, k->dtype, d, k->y, k->nrm, n, k->d_bound, k->ys, k->nrm_s, perm);
+            rc = pbn_spatial_sort(ctx, k->dtype, d, pbn_morton_dims(k), k->y, k->nrm, n, k->d_bound, k->ys, k->nrm_s, perm);
             if (rc == PBN_OK) rc = pbn_spatial_boxes(ctx, k->dtype, d, k->ys, n, tile, k->box);
         }
         if (perm) cudaFreeAsync(perm, ctx->stream);
@@ -981,7 +987,7 @@ static int logl_one(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const
         PBN_CUDA_TRY(sc.alloc(&perm, (size_t)m * sizeof(int)));
         PBN_CUDA_TRY(sc.alloc(&out, (size_t)m * sizeof(double)));
         double* nrm_sorted = tnbytes ? reinterpret_cast<double*>(ys_test + ytbytes) : nullptr;
-        PBN_TRY(pbn_spatial_sort(ctx, k->dtype, d, ytest, nrm_test, m, bound_test, ys_test, nrm_sorted, perm));
+        PBN_TRY(pbn_spatial_sort(ctx, k->dtype, d, pbn_morton_dims(k), ytest, nrm_test, m, bound_test, ys_test, nrm_sorted, perm));
         ytest = ys_test;
         nrm_test = nrm_sorted;
         train_y = k->ys;

@@ -28,16 +28,18 @@ constexpr int kSkipBits = 40;
 
 // ---- Morton keys ------------------------------------------------------------------------------------------------
 // coordinate c of a row, quantised to `bits` bits over [-B, B] (B = largest |whitened coordinate| of the set)
-template <typename T, int D>
+// DK <= D: only the first DK coordinates enter the key (a CKDE sorts by its evidence coordinates: the marginal sum is the
+// one that decides whether a unit can be dropped, and its boxes should be the compact ones)
+template <typename T, int D, int DK>
 __global__ void morton_key_kernel(const T* __restrict__ y, long long n, const float* __restrict__ bound, unsigned long long* __restrict__ keys,
                                   int* __restrict__ idx) {
-    constexpr int bits = 60 / D > 16 ? 16 : 60 / D;
+    constexpr int bits = 60 / DK > 16 ? 16 : 60 / DK;
     const float B = fmaxf(*bound, 1e-30f);
     const float scale = (float)((1u << bits) - 1) / (2.f * B);
     for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
-        unsigned q[D];
+        unsigned q[DK];
 #pragma unroll
-        for (int c = 0; c < D; ++c) {
+        for (int c = 0; c < DK; ++c) {
             float v = (static_cast<float>(y[r * D + c]) + B) * scale;
             v = v != v ? 0.f : fminf(fmaxf(v, 0.f), (float)((1u << bits) - 1));
             q[c] = (unsigned)v;
@@ -46,7 +48,7 @@ __global__ void morton_key_kernel(const T* __restrict__ y, long long n, const fl
 #pragma unroll
         for (int b = bits - 1; b >= 0; --b)
 #pragma unroll
-            for (int c = 0; c < D; ++c) k = (k << 1) | ((q[c] >> b) & 1u);
+            for (int c = 0; c < DK; ++c) k = (k << 1) | ((q[c] >> b) & 1u);
         keys[r] = k;
         idx[r] = (int)r;
     }
@@ -330,8 +332,9 @@ __global__ void scatter_out_kernel(const double* __restrict__ src, const int* __
         default: return set_error(PBN_ERR_UNSUPPORTED, "spatial order: unsupported dimension"); \
     }
 
-int pbn_spatial_sort(pbn_ctx* ctx, int dtype, int d, const void* y, const double* nrm, int64_t n, const float* bound, void* ys,
+int pbn_spatial_sort(pbn_ctx* ctx, int dtype, int d, int dk, const void* y, const double* nrm, int64_t n, const float* bound, void* ys,
                      double* nrm_s, int* perm) {
+    if (dk != d && dk != d - 1) return set_error(PBN_ERR_ARG, "spatial order: key dimension must be d or d - 1");
     cudaStream_t st = ctx->stream;
     if (n == 0) return PBN_OK;
     unsigned long long *keys = nullptr, *keys2 = nullptr;
@@ -344,12 +347,18 @@ int pbn_spatial_sort(pbn_ctx* ctx, int dtype, int d, const void* y, const double
     idx = reinterpret_cast<int*>(keys2 + n);
     const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 16);
     const bool f64 = dtype == PBN_F64;
-#define PBN_KEYS(DD)                                                                                                         \
-    if (f64) morton_key_kernel<double, DD><<<blocks, 256, 0, st>>>(static_cast<const double*>(y), n, bound, keys, idx);      \
-    else morton_key_kernel<float, DD><<<blocks, 256, 0, st>>>(static_cast<const float*>(y), n, bound, keys, idx)
+#define PBN_KEYS(DD)                                                                                                            \
+    if (dk == DD) {                                                                                                             \
+        if (f64) morton_key_kernel<double, DD, DD><<<blocks, 256, 0, st>>>(static_cast<const double*>(y), n, bound, keys, idx); \
+        else morton_key_kernel<float, DD, DD><<<blocks, 256, 0, st>>>(static_cast<const float*>(y), n, bound, keys, idx);       \
+    } else {                                                                                                                    \
+        constexpr int DKK = DD > 1 ? DD - 1 : 1;                                                                                \
+        if (f64) morton_key_kernel<double, DD, DKK><<<blocks, 256, 0, st>>>(static_cast<const double*>(y), n, bound, keys, idx);\
+        else morton_key_kernel<float, DD, DKK><<<blocks, 256, 0, st>>>(static_cast<const float*>(y), n, bound, keys, idx);      \
+    }
     PBN_D_SWITCH(PBN_KEYS)
 #undef PBN_KEYS
-    const int bits = (60 / d > 16 ? 16 : 60 / d) * d;
+    const int bits = (60 / dk > 16 ? 16 : 60 / dk) * dk;
     e = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, idx, perm, (int)n, 0, bits, st);
     if (e == cudaSuccess) e = cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 8, st);
     if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, idx, perm, (int)n, 0, bits, st);
