@@ -764,8 +764,13 @@ double unit_scale(int dtype) {  // kernel exponent units per natural-log unit of
 static int fit_one(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, pbn_rows rows, const double* H, bool ckde,
                    pbn_kde** out);
 // tile skipping pays from a few dozen tiles on each side (tools/skip_model.py: a 90k x 10k cross-validation fold has too few)
-constexpr int64_t kSkipMinTrain = 1 << 17;
-constexpr int64_t kSkipMinTest = 1 << 14;
+// (PBN_SKIP_MIN_TRAIN / PBN_SKIP_MIN_TEST override them: the sanitizer runs and the small-size tests force the path)
+static int64_t env_rows(const char* name, int64_t dflt) {
+    const char* e = getenv(name);
+    return (e && *e) ? (int64_t)atoll(e) : dflt;
+}
+static const int64_t kSkipMinTrain = env_rows("PBN_SKIP_MIN_TRAIN", 1 << 17);
+static const int64_t kSkipMinTest = env_rows("PBN_SKIP_MIN_TEST", 1 << 14);
 
 // multi-device context: the fitted model is replicated (every device whitens its own copy of the training rows)
 static int fit_impl(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, pbn_rows rows, const double* H,
