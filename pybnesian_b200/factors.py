@@ -35,7 +35,9 @@ class FactorType:
         return inst
 
     def new_factor(self, model, variable, evidence, *args, **kwargs):
-        raise NotImplementedError
+        # pybind11's message for an un-overridden pure virtual of the trampoline (a RuntimeError in the reference;
+        # NotImplementedError is one too)
+        raise NotImplementedError('Tried to call pure virtual function "FactorType::new_factor"')
 
     def __eq__(self, other):
         return type(self) is type(other)

@@ -354,7 +354,8 @@ class KDE:
         self._check_fitted()
         tbl, cols, rows = self._train
         arrays = [pa.array(tbl.download(c, rows)) for c in cols]
-        return pa.RecordBatch.from_arrays(arrays, names=self._variables).to_pandas()
+        # a pyarrow.RecordBatch, what the reference's DataFrame type caster returns (dataset/dataset.hpp:2120-2143)
+        return pa.RecordBatch.from_arrays(arrays, names=self._variables)
 
     def lognorm_const(self):
         self._check_fitted()
@@ -492,7 +493,8 @@ class ProductKDE:
         self._check_fitted()
         tbl, cols, rows = self._train
         arrays = [pa.array(tbl.download(c, rows)) for c in cols]
-        return pa.RecordBatch.from_arrays(arrays, names=self._variables).to_pandas()
+        # a pyarrow.RecordBatch, what the reference's DataFrame type caster returns (dataset/dataset.hpp:2120-2143)
+        return pa.RecordBatch.from_arrays(arrays, names=self._variables)
 
     def lognorm_const(self):
         self._check_fitted()

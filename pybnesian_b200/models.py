@@ -71,6 +71,10 @@ class Dag:
 
     def __init__(self, nodes=None, arcs=None):
         nodes = list(nodes or [])
+        for a in (arcs or []):
+            if not (isinstance(a, (tuple, list)) and len(a) == 2 and all(isinstance(x, str) for x in a)):
+                # what pybind11 answers when no overload takes the arguments (BayesianNetwork_test.py:28-30)
+                raise TypeError("__init__(): incompatible constructor arguments. An arc is a (source, target) pair of node names.")
         if arcs and not nodes:
             for s, t in arcs:
                 for n in (s, t):
@@ -608,6 +612,13 @@ class BayesianNetwork:
     def collapsed_from_index(self, idx):
         return self._g.collapsed_from_index(idx)
 
+    def indices(self):
+        """name -> raw index of every node (GraphBase::indices, graph/generic_graph.hpp:431)."""
+        return dict(self._g._index)
+
+    def collapsed_indices(self):
+        return dict(self._g._cindex)
+
     def index_from_collapsed(self, cidx):
         return self._g.index_from_collapsed(cidx)
 
@@ -785,7 +796,7 @@ class BayesianNetwork:
     def cpd(self, node):
         i = self.index(node)
         if not self._cpds or self._cpds[i] is None:
-            raise ValueError("CPD of variable " + node + " not added. Call add_cpds() or fit() to add the CPD.")
+            raise ValueError("CPD of variable \"" + node + "\" not added. Call add_cpds() or fit() to add the CPD.")
         return self._cpds[i]
 
     def fit(self, df, construction_args=None):
@@ -818,7 +829,10 @@ class BayesianNetwork:
 
     def slogl(self, df):
         frame = DataFrame.wrap(df)
-        return float(sum(self.cpd(node).slogl(frame) for node in self.nodes()))
+        total = 0.0  # plain additions in node order like the reference (the built-in sum() compensates since Python 3.12)
+        for node in self.nodes():
+            total += self.cpd(node).slogl(frame)
+        return float(total)
 
     def sample(self, n, seed=None, ordered=False):
         """BNGeneric::sample (models/BayesianNetwork.hpp:1024-1065): ancestral sampling in topological order; node i of
@@ -840,7 +854,8 @@ class BayesianNetwork:
         if ordered:
             order = [names.index(v) for v in self.nodes()]
             names, arrays = [names[j] for j in order], [arrays[j] for j in order]
-        return pa.RecordBatch.from_arrays(arrays, names=names).to_pandas()
+        # a pyarrow.RecordBatch, what the reference's DataFrame type caster returns (dataset/dataset.hpp:2120-2143)
+        return pa.RecordBatch.from_arrays(arrays, names=names)
 
     def clone(self):
         m = type(self).__new__(type(self))
@@ -872,8 +887,8 @@ class BayesianNetwork:
                              + ", ".join(pa) + "]")
         t = self.node_type(cpd.variable())
         if t != UnknownFactorType() and cpd.type() != t:
-            raise ValueError("CPD defined with a different node type.\nExpected node type: " + str(t)
-                             + "\nCPD node type: " + str(cpd.type()))
+            raise ValueError("Factor " + str(cpd) + " is of type " + str(cpd.type()) + ". Bayesian network expects type "
+                             + str(t))
 
     def add_cpds(self, cpds):
         """BNGeneric::add_cpds (models/BayesianNetwork.hpp:914-940)."""

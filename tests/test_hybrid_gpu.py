@@ -364,7 +364,7 @@ def test_clg_sample_and_hybrid_network_sample(pbn):
     m = pbn.SemiparametricBN(["A", "B", "C", "D"], [("A", "B"), ("A", "D"), ("B", "D"), ("C", "D")],
                              [("D", pbn.CKDEType())])
     m.fit(tr)
-    s = m.sample(2000, 3, ordered=True)
+    s = m.sample(2000, 3, ordered=True).to_pandas()
     assert list(s.columns) == ["A", "B", "C", "D"] and len(s) == 2000
     assert str(s["A"].dtype) == "category" and set(s["B"].cat.categories) == {"b1", "b2", "b3"}
     assert abs(np.mean(s["A"] == "a1") - 0.75) < 0.05
@@ -373,7 +373,7 @@ def test_clg_sample_and_hybrid_network_sample(pbn):
     sel_s = (s["A"] == "a1") & (s["B"] == "b2")
     sel_t = (tr["A"] == "a1") & (tr["B"] == "b2")
     assert abs(s.loc[sel_s, "D"].mean() - tr.loc[sel_t, "D"].mean()) < 0.5
-    assert s.equals(m.sample(2000, 3, ordered=True))
+    assert s.equals(m.sample(2000, 3, ordered=True).to_pandas())
 
 
 def test_heterogeneous_bn_fit_and_default_types(pbn):

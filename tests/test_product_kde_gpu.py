@@ -194,6 +194,6 @@ def test_pickle_and_dataset(pbn):
     assert k2.fitted() and k2.variables() == ["c", "a", "b"] and k2.num_instances() == SIZE
     assert np.array_equal(k2.bandwidth, k.bandwidth)
     assert np.array_equal(k2.logl(test), k.logl(test))
-    assert np.array_equal(k.dataset().to_numpy(), df[["c", "a", "b"]].to_numpy())
+    assert np.array_equal(k.dataset().to_pandas().to_numpy(), df[["c", "a", "b"]].to_numpy())
     u = pickle.loads(pickle.dumps(pbn.ProductKDE(["a"])))
     assert not u.fitted()
