@@ -226,11 +226,7 @@ class DiscreteFactor(Factor):
 
     def data_type(self):
         self._check_fitted()
-        t = self._arrow_type
-        # pandas >= 3 hands string categories over as large_string; the reference's environments (pandas 1-2) as string
-        if pa.types.is_dictionary(t) and pa.types.is_large_string(t.value_type):
-            t = pa.dictionary(t.index_type, pa.string(), t.ordered)
-        return t
+        return self._arrow_type
 
     def fit(self, df):
         frame = DataFrame.wrap(df)

@@ -98,8 +98,14 @@ class Dag:
         self._roots = _IntSet()
         for i in range(len(nodes)):
             self._roots.insert(i)
+        # Dag(nodes, arcs) (graph/generic_graph.hpp: DagImpl constructor): arcs go in unchecked, then one topological sort
+        # validates the whole graph ("Graph must be a DAG to obtain a topological sort.")
         for s, t in (arcs or []):
-            self.add_arc(s, t)
+            si, ti = self.index(s), self.index(t)
+            if (si, ti) not in self._arcs:
+                self._add_arc_unsafe(si, ti)
+        if arcs:
+            self.topological_sort()
 
     # -- nodes ---------------------------------------------------------------------------
     def nodes(self):

@@ -60,7 +60,7 @@ def test_check_compatible_cpd_errors():
     with pytest.raises(ValueError, match="parent set as evidence"):
         m.add_cpds([pbn.LinearGaussianCPD("b", [], [0.0], 1.0)])
     s = pbn.SemiparametricBN(["a", "b"], [("a", "b")], [("b", pbn.CKDEType())])
-    with pytest.raises(ValueError, match="different node type"):
+    with pytest.raises(ValueError, match="Bayesian network expects type"):
         s.add_cpds([pbn.LinearGaussianCPD("b", ["a"], [0.0, 1.0], 1.0)])
     s.add_cpds([pbn.LinearGaussianCPD("a", [], [0.0], 1.0)])  # unknown type: adopts the CPD's
     assert s.node_type("a") == pbn.LinearGaussianCPDType()
