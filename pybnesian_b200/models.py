@@ -577,8 +577,9 @@ class BayesianNetwork:
         self._cpds = []
         if bn_type.is_homogeneous():
             self._node_types = []
-            if node_types:
-                raise ValueError("node types cannot be set on a homogeneous Bayesian network")
+            for name, t in (node_types or []):  # a homogeneous network only takes its own default type
+                if t != bn_type.default_node_type():
+                    raise self._wrong_type(name, t)
         else:
             self._node_types = [UnknownFactorType() for _ in range(n)]
             for name, t in (node_types or []):

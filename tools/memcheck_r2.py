@@ -41,6 +41,23 @@ for dtype, tol in (("float64", 1e-10), ("float32", 1e-4)):
         want = oracle.kde_logl(w.to_numpy().astype(np.float64), wt.to_numpy().astype(np.float64), np.asarray(k.bandwidth))[0]
         assert np.max(np.abs(got - want) / np.abs(want)) < (1e-9 if dtype == "float64" else 1e-4)
 ctx.set_skipping(True)
+# enough tiles in one and two dimensions for list B (units dropped, explicit unit list, pass B on top of pass A)
+for dtype, tol in (("float64", 1e-10), ("float32", 1e-4)):
+    big = util_data.generate_normal_data(60_011, 0).astype(dtype)
+    bt = util_data.generate_normal_data(20_003, 1).astype(dtype)
+    for kind, variables in (("kde", ["a"]), ("ckde", ["b", "a"]), ("kde", ["b", "a"])):
+        f = pbn.KDE(variables) if kind == "kde" else pbn.CKDE(variables[0], variables[1:])
+        f.fit(big)
+        got = f.logl(bt)
+        st = ctx.skip_stats()
+        assert st["last_evaluated"] < st["last_total"], st
+        rows = np.arange(0, 20_003, 97)
+        X, T = big[variables].to_numpy().astype(np.float64), bt[variables].to_numpy().astype(np.float64)[rows]
+        H = np.asarray(f.bandwidth if kind == "kde" else f.kde_joint().bandwidth, dtype=np.float64)
+        want = (oracle.kde_logl if kind == "kde" else oracle.ckde_logl)(X, T, H)[0]
+        err = np.max(np.abs(got[rows] - want) / np.maximum(np.abs(want), 1.0))
+        print(dtype, kind, variables, "list B: units", st["last_evaluated"], "/", st["last_total"], "err %.2e" % err, flush=True)
+        assert err < tol, err
 # batched scores (job lists) and UCV
 data = util_data.generate_normal_data(3000, 0)
 cv = pbn.CVLikelihood(data, 5, 0)
