@@ -1461,10 +1461,18 @@ int pbn_ctx_set_skipping(pbn_ctx* ctx, int on) {
 }
 int pbn_ctx_skip_stats(pbn_ctx* ctx, int64_t* last_total, int64_t* last_done, int64_t* timed_total, int64_t* timed_done, int reset) {
     if (!ctx) return set_error(PBN_ERR_ARG, "null context");
-    if (last_total) *last_total = ctx->last_units_total;
-    if (last_done) *last_done = ctx->last_units_done;
-    if (timed_total) *timed_total = ctx->units_total;
-    if (timed_done) *timed_done = ctx->units_done;
+    int64_t lt = ctx->last_units_total, ld = ctx->last_units_done, tt = ctx->units_total, td = ctx->units_done;
+    for (pbn_ctx* p : ctx->peers) {  // a multi-device context reports the sums over its devices
+        lt += p->last_units_total;
+        ld += p->last_units_done;
+        tt += p->units_total;
+        td += p->units_done;
+        if (reset) { p->units_total = 0; p->units_done = 0; }
+    }
+    if (last_total) *last_total = lt;
+    if (last_done) *last_done = ld;
+    if (timed_total) *timed_total = tt;
+    if (timed_done) *timed_done = td;
     if (reset) { ctx->units_total = 0; ctx->units_done = 0; }
     return PBN_OK;
 }

@@ -117,7 +117,9 @@ def test_config5_iid_1m_subsample_and_additivity(pbn, d, dtype, tol):
     assert abs(total - logl.sum()) <= 1e-12 * abs(total)
     cut = 333_337
     parts = k.slogl(pbn.DataFrame(test.iloc[:cut])) + k.slogl(pbn.DataFrame(test.iloc[cut:]))
-    assert abs(total - parts) <= 1e-12 * abs(total)
+    # float32: a different set of test rows is Morton-sorted into different tiles, which regroups the per-tile FLOAT partial
+    # sums of every row (a few float ulps per row, see tests/test_skipping_gpu.py); float64 sums only change their order
+    assert abs(total - parts) <= (1e-12 if dtype == "float64" else 2e-7) * abs(total)
     # the kernel sum is additive over a partition of the training rows
     sub = pbn.DataFrame(test.iloc[:50_000])
     full = logl[:50_000]
