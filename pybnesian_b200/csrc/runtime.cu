@@ -911,6 +911,7 @@ int pbn_logl_impl(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const i
                      double* d_out_logl, double* d_out_slogl, double* h_out_logl, double* h_out_slogl) {
     if (!ctx || !k) return set_error(PBN_ERR_ARG, "null argument");
     const int64_t m_all = (test && rows.e0 >= rows.b0 && rows.e1 >= rows.b1) ? seg_count(rows) : 0;
+    for (pbn_ctx* p : ctx->peers) p->last_units_total = p->last_units_done = 0;  // "last call" counters are per call
     if (d_out_logl || d_out_slogl || !pbn_replicated(ctx, k) || !pbn_replicated(ctx, test) || !worth_sharding(ctx, k->n, m_all))
         return logl_one(ctx, k, test, cols, rows, d_out_logl, d_out_slogl, h_out_logl, h_out_slogl);
     PBN_TRY(check_cols(test, cols, k->d));
