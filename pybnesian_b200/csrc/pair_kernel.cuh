@@ -187,8 +187,12 @@ static_assert(kExpDeg >= 2 && kExpDeg <= 4, "PBN_EXP_DEG");
 template <typename T> __host__ __device__ constexpr size_t exp_tab_smem_bytes() {
     return sizeof(T) == 8 ? static_cast<size_t>(kExpTab) * kExpRep * sizeof(double) : 0;
 }
+#ifndef PBN_F64_TILE_LE4
+#define PBN_F64_TILE_LE4 PBN_F64_TILE
+#endif
 template <typename T> __host__ __device__ constexpr int pair_tile(int D) {
-    return (sizeof(T) == 8 && (D >= 7 || (D >= 5 && exp_tab_smem_bytes<T>() > 32 * 1024))) ? PairCfg<T>::TILE / 2
+    return (sizeof(T) == 8 && D <= 4) ? PBN_F64_TILE_LE4
+         : (sizeof(T) == 8 && (D >= 7 || (D >= 5 && exp_tab_smem_bytes<T>() > 32 * 1024))) ? PairCfg<T>::TILE / 2
                                                                                             : PairCfg<T>::TILE;
 }
 // per-stage bytes of the training-row norm tile (dot-product form, f64 only)

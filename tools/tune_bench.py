@@ -10,6 +10,7 @@ from pybnesian_b200 import _lib
 
 def run(kind, d, n, dtype, reps=3):
     ctx = pbn.default_context()
+    ctx.set_skipping(os.environ.get("TUNE_SKIPPING", "0") == "1")   # kernel tuning: every pair evaluated unless asked
     tr = util_data.iid_normal(n, d, 0, dtype); te = util_data.iid_normal(n, d, 1, dtype)
     cols = list(tr.columns)
     f = pbn.KDE(cols) if kind == 'kde' else pbn.CKDE(cols[0], cols[1:])
