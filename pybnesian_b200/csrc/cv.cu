@@ -848,22 +848,55 @@ int score_ckde_jobs(pbn_ctx* ctx, pbn_cv* cv, const pbn_cv_item* items, const Cv
             ctx->launches++;
             PBN_CUDA_TRY(cudaGetLastError());
         }
-        {
-            int rgrid = ctx->sm_count * 4;
-            if (f64) row_batch_kernel<double><<<rgrid, 256, 0, st>>>(d_pj, d_fj, d, ckde ? 1 : 0, 1.0 / unit, d_flag, d_nflag, d_out);
-            else row_batch_kernel<float><<<rgrid, 256, 0, st>>>(d_pj, d_fj, d, ckde ? 1 : 0, 1.0 / unit, d_flag, d_nflag, d_out);
-            ctx->launches++;
-            PBN_CUDA_TRY(cudaGetLastError());
+        // rows whose unshifted sums underflowed (test rows of a fold far from all its training rows): the shifted second
+        // pass of runtime.cu, job by job (round 1: one CTA per row).  Rare, so the flagged (job, row) list is read back.
+        int nflag = 0;
+        PBN_CUDA_TRY(cudaMemcpyAsync(&nflag, d_nflag, sizeof(int), cudaMemcpyDeviceToHost, st));
+        PBN_CUDA_TRY(cudaStreamSynchronize(st));
+        ctx->d2h += 4;
+        Scratch sc(st);
+        if (nflag > 0) {
+            std::vector<int2> fl((size_t)nflag);
+            PBN_CUDA_TRY(cudaMemcpyAsync(fl.data(), d_flag, (size_t)nflag * sizeof(int2), cudaMemcpyDeviceToHost, st));
+            PBN_CUDA_TRY(cudaStreamSynchronize(st));
+            ctx->d2h += (int64_t)nflag * 8;
+            std::vector<std::vector<int>> by_job(J);
+            for (const int2& e : fl) by_job[e.x].push_back(e.y);
+            for (int j = 0; j < J; ++j) {
+                std::vector<int>& rows = by_job[j];
+                if (rows.empty()) continue;
+                std::sort(rows.begin(), rows.end());
+                const int cnt = (int)rows.size();
+                rows.push_back(cnt);  // the count travels behind the list
+                int* d_rows = nullptr;
+                PBN_CUDA_TRY(sc.alloc(&d_rows, rows.size() * sizeof(int)));
+                PBN_CUDA_TRY(cudaMemcpyAsync(d_rows, rows.data(), rows.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+                PBN_CUDA_TRY(cudaStreamSynchronize(st));  // `rows` is reused by the next job
+                ctx->h2d += (int64_t)rows.size() * 4;
+                ShiftPass A;
+                A.train = wj[j].y_train;
+                A.n_train = hj[j].n_train;
+                A.test = wj[j].y_test;
+                A.m_cap = cnt;
+                A.d = d;
+                A.ckde = ckde;
+                A.f64 = f64;
+                A.lognorm_joint = fj[j].lognorm_joint;
+                A.lognorm_marg = fj[j].lognorm_marg;
+                A.flagged = d_rows;
+                A.n_flagged = d_rows + cnt;
+                A.out = d_out + fj[j].out_off;
+                A.n_row_kernel = nullptr;
+                PBN_TRY(pbn_shift_pass(ctx, sc, A));
+            }
         }
         segsum_kernel<<<J, 256, 0, st>>>(d_pj, d_fj, d_out, d_sums);
         ctx->launches++;
         PBN_CUDA_TRY(cudaGetLastError());
         std::vector<double> sums(J);
-        int nflag = 0;
         PBN_CUDA_TRY(cudaMemcpyAsync(sums.data(), d_sums, (size_t)J * sizeof(double), cudaMemcpyDeviceToHost, st));
-        PBN_CUDA_TRY(cudaMemcpyAsync(&nflag, d_nflag, sizeof(int), cudaMemcpyDeviceToHost, st));
         PBN_CUDA_TRY(cudaStreamSynchronize(st));
-        ctx->d2h += (int64_t)J * 8 + 4;
+        ctx->d2h += (int64_t)J * 8;
         ctx->last_fallback_rows = nflag;
         PBN_CUDA_TRY(cudaFreeAsync(base, st));
         for (int j = 0; j < J; ++j) job_scores[hj[j].item] = sums[j];

@@ -173,6 +173,43 @@ int pbn_logl_impl(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const i
 // variable first; writes beta[p + 1], returns the variance.
 double lg_fit_from_moments(int64_t rows, int p, const double* mean, const double* Cm, double* beta);
 
+// Stream-ordered scratch of one call: everything allocated through it is returned to the pool when the call leaves,
+// on the error paths too (PBN_CUDA_TRY / PBN_TRY return early).
+struct Scratch {
+    cudaStream_t st;
+    std::vector<void*> ptrs;
+    std::vector<cudaEvent_t> events;  // destroyed on exit unless released
+    explicit Scratch(cudaStream_t s) : st(s) {}
+    ~Scratch() {
+        for (void* p : ptrs) cudaFreeAsync(p, st);
+        for (cudaEvent_t e : events) cudaEventDestroy(e);
+    }
+    template <typename T>
+    cudaError_t alloc(T** out, size_t bytes) {
+        void* p = nullptr;
+        cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 8, st);
+        if (e == cudaSuccess) ptrs.push_back(p);
+        *out = static_cast<T*>(p);
+        return e;
+    }
+};
+
+// The shifted second pass over rows whose unshifted sums underflowed (runtime.cu)
+struct ShiftPass {
+    const void* train;   // whitened training rows AoS [n_train][d]
+    int64_t n_train;
+    const void* test;    // whitened test rows the flagged ids index
+    int64_t m_cap;       // upper bound of the flagged count (sizes the scratch)
+    int d;
+    bool ckde, f64;
+    double lognorm_joint, lognorm_marg;
+    int* flagged;        // device: ascending row ids ...
+    int* n_flagged;      // ... and their count
+    double* out;         // out[row id]
+    int* n_row_kernel;   // device int, may be null: how many rows the per-row kernel had to finish
+};
+int pbn_shift_pass(pbn_ctx* ctx, Scratch& sc, const ShiftPass& A);
+
 // ---- spatial order and tile skipping (spatial.cu) ----
 int pbn_spatial_sort(pbn_ctx* ctx, int dtype, int d, int dk, const void* y, const double* nrm, int64_t n, const float* bound, void* ys,
                      double* nrm_s, int* perm);

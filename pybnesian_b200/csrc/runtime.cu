@@ -357,7 +357,7 @@ __global__ void finalize_kernel(FinalizeParams P) {
 // Replaces the reference's max-shifted logsumexp_cols_offset (opencl/opencl_config.hpp:517-536), which it runs for every row.
 // ------------------------------------------------------------------------------------
 __global__ void compact_flagged_kernel(const unsigned char* __restrict__ mask, long long m, const int* __restrict__ n_flagged,
-                                       int* __restrict__ flagged, float* __restrict__ shift_j, float* __restrict__ shift_m) {
+                                       int* __restrict__ flagged) {
     __shared__ int warp_tot[32];
     __shared__ int base_s;
     const int cnt = *n_flagged;
@@ -383,7 +383,11 @@ __global__ void compact_flagged_kernel(const unsigned char* __restrict__ mask, l
         __syncthreads();
         if (base_s == cnt) break;  // every flagged row has been listed
     }
-    for (int i = tid; i < cnt; i += blockDim.x) {
+}
+
+__global__ void shift_init_kernel(const int* __restrict__ n_flagged, float* __restrict__ shift_j, float* __restrict__ shift_m) {
+    const int cnt = *n_flagged;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
         shift_j[i] = INFINITY;
         shift_m[i] = INFINITY;
     }
@@ -875,26 +879,98 @@ static int fit_one(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, p
     return PBN_OK;
 }
 
-// Stream-ordered scratch of one call: everything allocated through it is returned to the pool when the call leaves,
-// on the error paths too (PBN_CUDA_TRY / PBN_TRY return early).
-struct Scratch {
-    cudaStream_t st;
-    std::vector<void*> ptrs;
-    std::vector<cudaEvent_t> events;  // destroyed on exit unless released
-    explicit Scratch(cudaStream_t s) : st(s) {}
-    ~Scratch() {
-        for (void* p : ptrs) cudaFreeAsync(p, st);
-        for (cudaEvent_t e : events) cudaEventDestroy(e);
-    }
-    template <typename T>
-    cudaError_t alloc(T** out, size_t bytes) {
-        void* p = nullptr;
-        cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 8, st);
-        if (e == cudaSuccess) ptrs.push_back(p);
-        *out = static_cast<T*>(p);
-        return e;
-    }
-};
+// The shifted second pass as a unit (used by pbn_logl_impl below and by the batched scores of cv.cu): the rows
+// `flagged[0 .. *n_flagged)` (ascending ids into `test`) are evaluated against all `n_train` training rows with a
+// per-row exponent shift; out[id] receives lognorm + log(sum) - shift (minus the marginal for a CKDE).  Sized and
+// scheduled on the device from the count; nothing is read back.
+int pbn_shift_pass(pbn_ctx* ctx, Scratch& sc, const ShiftPass& A) {
+    cudaStream_t st = ctx->stream;
+    const int d = A.d;
+    const bool f64 = A.f64;
+    const int TILE = f64 ? pbn::pair_tile_f64(d) : pbn::pair_tile_f32(d);
+    const int TB = f64 ? pbn::pair_tb_for_f64(d, A.ckde) : pbn::pair_tb_for_f32(d, A.ckde);
+    const int max_grid = ctx->sm_count * (f64 ? pbn::pair_ctas_per_sm_f64() : pbn::pair_ctas_per_sm_f32());
+    const int n_acc = A.ckde ? 2 : 1;
+    const int64_t m = A.m_cap;
+    const double u2ln = 1.0 / unit_scale(f64 ? PBN_F64 : PBN_F32);
+    // [PairJob][dyn: 2 x i64][counter][flagged2: m int][shift_j, shift_m: m float]
+    const size_t jsz = (sizeof(PairJob) + 15) / 16 * 16;
+    const size_t o_dyn = jsz, o_cnt = o_dyn + 16, o_fl2 = o_cnt + 16, o_sj = o_fl2 + (size_t)m * 4, o_sm = o_sj + (size_t)m * 4;
+    char* book = nullptr;
+    double* part2 = nullptr;
+    PBN_CUDA_TRY(sc.alloc(&book, o_sm + (size_t)m * 4));
+    // slots' x m_pad' <= grid x TB + 2 (m + TB) whatever the flagged count is (see shift_prep_kernel)
+    PBN_CUDA_TRY(sc.alloc(&part2, (size_t)n_acc * ((size_t)max_grid * TB + 2 * ((size_t)m + TB) + 64) * sizeof(double)));
+    PairJob* d_job2 = reinterpret_cast<PairJob*>(book);
+    long long* dyn = reinterpret_cast<long long*>(book + o_dyn);
+    int* n_flagged2 = A.n_row_kernel ? A.n_row_kernel : reinterpret_cast<int*>(book + o_cnt);
+    int* flagged2 = reinterpret_cast<int*>(book + o_fl2);
+    float* shift_j = reinterpret_cast<float*>(book + o_sj);
+    float* shift_m = reinterpret_cast<float*>(book + o_sm);
+    shift_init_kernel<<<(int)std::min<int64_t>((m + 255) / 256, 1024), 256, 0, st>>>(A.n_flagged, shift_j, shift_m);
+    ShiftPrepParams SP;
+    memset(&SP.job, 0, sizeof(SP.job));
+    SP.job.train = A.train;
+    SP.job.test = A.test;
+    SP.job.part = part2;
+    SP.job.n_train = A.n_train;
+    SP.job.n_train_tiles = (int)((A.n_train + TILE - 1) / TILE);
+    SP.job.shift_j = shift_j;   // (no bounds, norms, unit list or initial sums: the shifted tile takes the wide-range
+    SP.job.shift_m = shift_m;   //  difference form against EVERY training tile)
+    SP.job.test_rows = A.flagged;
+    SP.n_flagged = A.n_flagged;
+    SP.d_job = d_job2;
+    SP.dyn = dyn;
+    SP.tb = TB;
+    SP.grid = max_grid;
+    SP.n_flagged2 = n_flagged2;
+    shift_prep_kernel<<<1, 1, 0, st>>>(SP);
+    // few flagged rows: split the training rows so that the scan still spreads over the GPU
+    dim3 rmgrid((unsigned)std::max<int64_t>(1, std::min<int64_t>((m + 255) / 256, (int64_t)ctx->sm_count * 2)), 8);
+    cudaError_t e2 = f64 ? launch_rowmin<double>(d, A.ckde, rmgrid, st, A.train, A.n_train, A.test, A.flagged, A.n_flagged, shift_j, shift_m)
+                         : launch_rowmin<float>(d, A.ckde, rmgrid, st, A.train, A.n_train, A.test, A.flagged, A.n_flagged, shift_j, shift_m);
+    PBN_CUDA_TRY(e2);
+    e2 = f64 ? pbn::launch_pair_shift_f64(d, A.ckde, d_job2, dyn, max_grid, ctx->d_exp_tab, st)
+             : pbn::launch_pair_shift_f32(d, A.ckde, d_job2, dyn, max_grid, ctx->d_exp_tab, st);
+    PBN_CUDA_TRY(e2);
+    FinalizeShiftParams FS;
+    FS.job = d_job2;
+    FS.dyn = dyn;
+    FS.tb = TB;
+    FS.ckde = A.ckde ? 1 : 0;
+    FS.f64 = f64 ? 1 : 0;
+    FS.lognorm_joint = A.lognorm_joint;
+    FS.lognorm_marg = A.lognorm_marg;
+    FS.u2ln = u2ln;
+    FS.thresh = ldexp(1.0, -40);  // the largest term of a shifted row is ~1
+    FS.out = A.out;
+    FS.flagged = A.flagged;
+    FS.flagged2 = flagged2;
+    FS.n_flagged2 = n_flagged2;
+    finalize_shift_kernel<<<(int)std::max<int64_t>(1, std::min<int64_t>((m + 255) / 256, (int64_t)ctx->sm_count * 4)), 256, 0, st>>>(FS);
+    ctx->launches += 5;
+    PBN_CUDA_TRY(cudaGetLastError());
+    // rows the shifted pass could not evaluate either: exact per-row evaluation (count read on device)
+    RowParams R;
+    R.train = A.train;
+    R.test = A.test;
+    R.n = A.n_train;
+    R.d = d;
+    R.ckde = A.ckde ? 1 : 0;
+    R.lognorm_joint = A.lognorm_joint;
+    R.lognorm_marg = A.lognorm_marg;
+    R.u2ln = u2ln;
+    R.rows = flagged2;
+    R.count_ptr = n_flagged2;
+    R.count = 0;
+    R.out = A.out;
+    const int rgrid = (int)std::max<int64_t>(1, std::min<int64_t>(m, (int64_t)ctx->sm_count * 8));
+    if (f64) row_kernel<double><<<rgrid, 256, 0, st>>>(R);
+    else row_kernel<float><<<rgrid, 256, 0, st>>>(R);
+    ctx->launches++;
+    PBN_CUDA_TRY(cudaGetLastError());
+    return PBN_OK;
+}
 
 static int logl_one(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const int* cols, pbn_rows rows,
                     double* d_out_logl, double* d_out_slogl, double* h_out_logl, double* h_out_slogl);
@@ -1023,28 +1099,17 @@ static int logl_one(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const
         int slots = (int)std::min<long long>((n_train_tiles + upb - 1) / upb + 1, grid);
         int n_acc = k->ckde ? 2 : 1;
         long long m_pad = (m + 31) / 32 * 32;
-        // one carve for the bookkeeping of both passes:
-        //   [PairJob x 2][dyn: 2 x i64][counters: 2 x int][flagged: m int][flagged2: m int][shift_j, shift_m: m float][mask: m bytes]
+        // one carve for the bookkeeping: [PairJob x 2][counters: 2 x int][flagged: m int][mask: m bytes]
         const size_t jsz = (sizeof(PairJob) + 15) / 16 * 16;
-        const size_t o_dyn = 3 * jsz, o_cnt = o_dyn + 16, o_fl = o_cnt + 16;
-        const size_t o_fl2 = o_fl + (size_t)m * 4, o_sj = o_fl2 + (size_t)m * 4, o_sm = o_sj + (size_t)m * 4;
-        const size_t o_mask = o_sm + (size_t)m * 4;
+        const size_t o_cnt = 2 * jsz, o_fl = o_cnt + 16, o_mask = o_fl + (size_t)m * 4;
         char* book = nullptr;
         double* part = nullptr;
-        double* part2 = nullptr;
         PBN_CUDA_TRY(sc.alloc(&book, o_mask + (size_t)m));
-        // second pass: slots' x m_pad' <= grid x TB + 2 (m + TB) whatever the flagged count is (see shift_prep_kernel)
-        PBN_CUDA_TRY(sc.alloc(&part2, (size_t)n_acc * ((size_t)max_grid * TB + 2 * ((size_t)m + TB) + 64) * sizeof(double)));
         PairJob* d_job = reinterpret_cast<PairJob*>(book);
-        PairJob* d_job2 = reinterpret_cast<PairJob*>(book + jsz);
-        PairJob* d_jobA = reinterpret_cast<PairJob*>(book + 2 * jsz);
-        long long* dyn = reinterpret_cast<long long*>(book + o_dyn);
+        PairJob* d_jobA = reinterpret_cast<PairJob*>(book + jsz);
         int* n_flagged = reinterpret_cast<int*>(book + o_cnt);
         int* n_flagged2 = n_flagged + 1;
         int* flagged = reinterpret_cast<int*>(book + o_fl);
-        int* flagged2 = reinterpret_cast<int*>(book + o_fl2);
-        float* shift_j = reinterpret_cast<float*>(book + o_sj);
-        float* shift_m = reinterpret_cast<float*>(book + o_sm);
         unsigned char* mask = reinterpret_cast<unsigned char*>(book + o_mask);
         PBN_CUDA_TRY(cudaMemsetAsync(mask, 0, (size_t)m, st));
         PairJob job;
@@ -1180,61 +1245,23 @@ static int logl_one(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const
         PBN_CUDA_TRY(cudaGetLastError());
 
         // ---- second pass over the flagged rows, scheduled on the device from their count ----
-        compact_flagged_kernel<<<1, 1024, 0, st>>>(mask, m, n_flagged, flagged, shift_j, shift_m);
-        ShiftPrepParams SP;
-        SP.job = job;
-        SP.job.part = part2;
-        SP.job.bound_train = nullptr;  // the shifted tile takes the SAFE exponent path
-        SP.job.bound_test = nullptr;
-        SP.job.train_nrm = nullptr;
-        SP.job.test_nrm = nullptr;
-        SP.job.unit_list = nullptr;  // the second pass evaluates the flagged rows against EVERY training tile
-        SP.job.tile_first = nullptr;
-        SP.job.init_sums = nullptr;
-        SP.job.slots = 0;
-        SP.job.shift_j = shift_j;
-        SP.job.shift_m = shift_m;
-        SP.job.test_rows = flagged;
-        SP.n_flagged = n_flagged;
-        SP.d_job = d_job2;
-        SP.dyn = dyn;
-        SP.tb = TB;
-        SP.grid = max_grid;
-        SP.n_flagged2 = n_flagged2;
-        shift_prep_kernel<<<1, 1, 0, st>>>(SP);
-        // few flagged rows: split the training rows so that the scan still spreads over the GPU
-        dim3 rmgrid((unsigned)std::min<int64_t>((m + 255) / 256, (int64_t)ctx->sm_count * 2), 8);
-        cudaError_t e2 = f64 ? launch_rowmin<double>(d, k->ckde, rmgrid, st, k->y, k->n, ytest, flagged, n_flagged, shift_j, shift_m)
-                             : launch_rowmin<float>(d, k->ckde, rmgrid, st, k->y, k->n, ytest, flagged, n_flagged, shift_j, shift_m);
-        PBN_CUDA_TRY(e2);
-        e2 = f64 ? pbn::launch_pair_shift_f64(d, k->ckde, d_job2, dyn, max_grid, ctx->d_exp_tab, st)
-                 : pbn::launch_pair_shift_f32(d, k->ckde, d_job2, dyn, max_grid, ctx->d_exp_tab, st);
-        PBN_CUDA_TRY(e2);
-        FinalizeShiftParams FS;
-        FS.job = d_job2;
-        FS.dyn = dyn;
-        FS.tb = TB;
-        FS.ckde = k->ckde ? 1 : 0;
-        FS.f64 = f64 ? 1 : 0;
-        FS.lognorm_joint = k->lognorm_joint;
-        FS.lognorm_marg = k->lognorm_marg;
-        FS.u2ln = u2ln;
-        FS.thresh = ldexp(1.0, -40);  // the largest term of a shifted row is ~1
-        FS.out = out;
-        FS.flagged = flagged;
-        FS.flagged2 = flagged2;
-        FS.n_flagged2 = n_flagged2;
-        finalize_shift_kernel<<<(int)std::min<int64_t>((m + 255) / 256, (int64_t)ctx->sm_count * 4), 256, 0, st>>>(FS);
-        ctx->launches += 5;
-        PBN_CUDA_TRY(cudaGetLastError());
-        // rows the shifted pass could not evaluate either: exact per-row evaluation (count read on device)
-        R.rows = flagged2;
-        R.count_ptr = n_flagged2;
-        R.count = 0;
-        if (f64) row_kernel<double><<<rgrid, 256, 0, st>>>(R);
-        else row_kernel<float><<<rgrid, 256, 0, st>>>(R);
+        compact_flagged_kernel<<<1, 1024, 0, st>>>(mask, m, n_flagged, flagged);
         ctx->launches++;
-        PBN_CUDA_TRY(cudaGetLastError());
+        ShiftPass SPA;
+        SPA.train = train_y;
+        SPA.n_train = k->n;
+        SPA.test = ytest;
+        SPA.m_cap = m;
+        SPA.d = d;
+        SPA.ckde = k->ckde;
+        SPA.f64 = f64;
+        SPA.lognorm_joint = k->lognorm_joint;
+        SPA.lognorm_marg = k->lognorm_marg;
+        SPA.flagged = flagged;
+        SPA.n_flagged = n_flagged;
+        SPA.out = out;
+        SPA.n_row_kernel = n_flagged2;
+        PBN_TRY(pbn_shift_pass(ctx, sc, SPA));
         if (h_out_logl || h_out_slogl) {
             int nf[2] = {0, 0};
             PBN_CUDA_TRY(cudaMemcpyAsync(nf, n_flagged, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));

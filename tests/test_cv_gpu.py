@@ -304,6 +304,31 @@ def test_multi_gpu_shards_match_single_gpu():
     assert out.returncode == 0 and "MULTI_GPU_CHECK_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
 
 
+def test_cvl_folds_with_isolated_outliers_take_the_shifted_pass(pbn):
+    """Isolated outliers: in the fold that tests them they are hundreds of bandwidths from every training row, so their
+    unshifted sums underflow inside the batched launch; they are re-evaluated by the shifted second pass (runtime.cu:
+    pbn_shift_pass, job by job) and the score still equals the oracle's serial fit + slogl per fold."""
+    data = util_data.generate_normal_data(3000, 0)
+    rng = np.random.default_rng(4)
+    idx = rng.choice(3000, 60, replace=False)
+    data.loc[idx, "a"] += np.linspace(30.0, 3000.0, 60) * rng.choice([-1.0, 1.0], 60)
+    data.loc[idx[:20], "c"] -= np.linspace(50.0, 900.0, 20)
+    cvl = pbn.CVLikelihood(data, 10, seed)
+    kdn = pbn.KDENetwork(list(data.columns))
+    ctx = pbn.default_context()
+    for variable, evidence in [("a", []), ("c", ["a"]), ("c", ["a", "b"]), ("d", ["a", "b", "c"])]:
+        got = cvl.local_score(kdn, variable, evidence)
+        assert ctx.last_fallback_rows() > 0
+        want = oracle_cv(data, variable, evidence, "ckde")
+        assert np.isfinite(got) and abs(got - want) <= 1e-10 * abs(want), (variable, evidence, got, want)
+    # batch = single, outliers or not
+    reqs = [(pbn.CKDEType(), "c", ["a", "b"]), (pbn.CKDEType(), "d", ["a"]), (pbn.LinearGaussianCPDType(), "b", ["a"])]
+    spbn = pbn.SemiparametricBN(list(data.columns))
+    batch = pbn.CVLikelihood(data, 10, seed).local_score_batch(spbn, reqs)
+    single = [pbn.CVLikelihood(data, 10, seed).local_score_node_type(spbn, t, v, e) for t, v, e in reqs]
+    assert np.allclose(batch, single, rtol=1e-13, atol=0)
+
+
 def test_in_process_multi_device_context_matches_single_device():
     """Needs >= 2 GPUs: ONE process, a context over all devices (pbn_ctx_create_multi, no torchrun) - sharded logl / slogl /
     cdf, dealt CV jobs, per-device UCV slices and hill climbing against the single-device results
