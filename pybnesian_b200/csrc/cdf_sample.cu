@@ -549,7 +549,8 @@ int sample_indices_device(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* ev, c
     F.m_pad = P.m_pad;
     F.n = k->n;
     F.n_splits = P.n_splits;
-    F.thresh = f64 ? ldexp(1.0, -1000) : ldexp(1.0, -120);
+    // above n_train clamped weights (exp2_tab evaluates an out-of-range term as 2^-kExpMinK): 2^25 rows
+    F.thresh = f64 ? ldexp(1.0, -pbn::kExpMinK + 25) : ldexp(1.0, -120);
     F.u = d_u;
     F.u_f64 = f64 ? 1 : 0;
     F.target = target;

@@ -204,7 +204,32 @@ template <typename T> __host__ __device__ constexpr uint32_t pair_nrm_bytes(int 
 //   K =  512, degree 3: 1.1e-15      K = 2048, degree 3: 4.3e-18      K = 256, degree 4 (plain Taylor): 3.8e-17
 //   K = 2048, degree 2: 2.0e-13      K = 4096, degree 2: 2.5e-14 (default)      K = 8192, degree 2: 3.1e-15
 // Degree 2 saves one DFMA per exp2: +1.5% (CKDE d=4) .. +3% (KDE d=2) over K = 2048 / degree 3 on B200.
+#ifndef PBN_EXP_SQ
+#define PBN_EXP_SQ 1
+#endif
+// PBN_EXP_SQ (round 2, default): the degree-2 polynomial in COMPLETED-SQUARE form, which takes one FP64 instruction less
+// and - what decides on sm_100 - fewer 64-bit REGISTER sources.  tools/micro/fp64_mix.cu (profiles/r2_fp64_mix.txt): an
+// FP64 instruction costs its scheduler 2 clk with one or two distinct register sources and 3 clk with three, and every
+// register a neighbouring integer instruction reads competes for the same two 32-bit read ports per clock; the pair
+// kernel is bound by those ports, not by the FP64 pipe alone.
+//   e^(a g) ~ 1 + a g + c2 g^2 = c2 ((g + S)^2 + Cq),   S = a / (2 c2),   Cq = 1 / c2 - S^2.
+// S is made an INTEGER (round(K / ln 2) = 5909 for K = 4096) by giving c2 the relative error S ln2 / K - 1 = 4.7e-5 instead
+// of touching the linear coefficient: the polynomial is then off by <= 4.7e-5 (a^2 / 2) g^2 + a^3 |g|^3 / 6 <= 2.7e-13 for
+// |g| <= 1/2 - ten times the 2.5e-14 of the economised Horner form below, forty times inside the 1e-11 per-term budget
+// (2.2e-13 and zero mean with the constant term corrected, kExpSqD).
+// With S an integer, g + S comes straight out of the argument split (the second DADD subtracts MAGIC + S, still exact),
+// and c2 is folded into the table (runtime.cu).  Per exp2: DADD, DADD, DADD, DFMA (g+S)^2 + Cq, DFMA accumulate = 5
+// (was 6), with 1 + 1 + 2 + 1 + 3 = 8 register sources (was 11).
+constexpr bool kExpSq = PBN_EXP_SQ != 0;
 constexpr double kExpA = 0.693147180559945309417232121458 / kExpTab;
+constexpr double kExpS = static_cast<double>(static_cast<long long>(1.0 / kExpA + 0.5));
+constexpr double kExpSqC2 = kExpA / (2.0 * kExpS);           // the table holds c2 2^(j/K)
+// constant term 1 + kExpSqD instead of 1: takes the MEAN of the quadratic-coefficient error (c2 - a^2/2) g^2 over |g| <= 1/2
+// out, so that sums of many terms carry no bias (the error of a term stays below 2.2e-13)
+constexpr double kExpSqD = -(kExpSqC2 - 0.5 * kExpA * kExpA) / 12.0;
+constexpr double kExpSqC = (1.0 + kExpSqD) / kExpSqC2 - kExpS * kExpS;
+// smallest power of two a scaled table entry may be moved to: c2 ~ 2^-26 for K = 4096 has to stay inside the normal range
+constexpr int kExpMinK = kExpSq ? 1022 - 27 : 1022;  // a clamped term is evaluated as 2^-kExpMinK
 constexpr double kExpH2 = 0.25 * kExpA * kExpA;  // h^2
 constexpr double kExpC0 = kExpDeg == 3 ? 1.0 - kExpH2 * kExpH2 / 192.0 : 1.0;
 constexpr double kExpC1 = kExpDeg == 2 ? kExpA * (1.0 + kExpH2 / 8.0) : kExpA;
@@ -276,15 +301,17 @@ __device__ __forceinline__ float normal_tail_tg_f(float a) {
 // The table holds T'[j] = T[j] with (j << (20 - log2 K)) subtracted from its high word, so that the
 // scaled entry 2^k T[j] is obtained with ONE integer multiply-add: hi' + n * 2^(20 - log2 K).
 // `tab` is the calling lane's copy of the table (tab_base + lane % kExpRep, stride kExpRep).
-// Returns P(g); `scaled` receives 2^k T[j].  SAFE = false requires t > -2^31 (guaranteed by
+// Returns P(g); `scaled` receives 2^k T[j]  (PBN_EXP_SQ: (g + S)^2 + Cq and c2 2^k T[j] - the product is the same).  SAFE = false requires t > -2^31 (guaranteed by
 // the caller from the bounding boxes of the whitened rows); SAFE = true accepts any t.
 #ifndef PBN_DOT_TOL
 #define PBN_DOT_TOL 1e-11
 #endif
 constexpr double kDotTol = PBN_DOT_TOL;  // worst-case per-term cancellation error accepted for the dot-product form
-constexpr int kNMin = -1022 * kExpTab;
-// hi word of the double -(1022 * K): sign | (1023 + 9 + log2 K) << 20 | top mantissa bits of 1022/1024
-constexpr unsigned kHiLim = 0x80000000u | (static_cast<unsigned>(1023 + 9 + kExpTabBits) << 20) | 0xFF000u;
+constexpr int kNMin = -kExpMinK * kExpTab;
+// hi word of the double -(kExpMinK * K), 512 <= kExpMinK < 1024: sign | (1023 + 9 + log2 K) << 20 | top mantissa bits of
+// kExpMinK / 512 - 1  (1022: 0xFF000)
+static_assert(kExpMinK >= 512 && kExpMinK < 1024, "kExpMinK");
+constexpr unsigned kHiLim = 0x80000000u | (static_cast<unsigned>(1023 + 9 + kExpTabBits) << 20) | (static_cast<unsigned>(kExpMinK - 512) << 11);
 // `nshift` evaluates 2^((t + nshift)/K) instead: the shift is added to the rounded exponent (tile_f64_dot keeps the
 // integer part of -|yt|^2 there); unsigned arithmetic, so only the shifted n has to fit 32 bits.
 // `nmin` (a multiple of K, >= kNMin) is the floor of the rounded exponent: terms below 2^(nmin/K) are evaluated AS
@@ -298,10 +325,12 @@ __device__ __forceinline__ double exp2_tab(double t, const double* __restrict__ 
     const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
     double tm = t + MAGIC;
     int n = static_cast<int>(static_cast<unsigned>(__double2loint(tm)) + static_cast<unsigned>(nshift));
-    double nd = tm - MAGIC;
-    double g = t - nd;
+    double nd = tm - (kExpSq ? MAGIC + kExpS : MAGIC);  // MAGIC + S is an integer below 2^53: exact
+    double g = t - nd;                                  // kExpSq: g + S
     double p;
-    if (kExpDeg == 4) {
+    if (kExpSq) {
+        p = fma(g, g, kExpSqC);
+    } else if (kExpDeg == 4) {
         p = fma(kExpC4, g, kExpC3);
         p = fma(p, g, kExpC2);
         p = fma(p, g, kExpC1);
@@ -311,7 +340,7 @@ __device__ __forceinline__ double exp2_tab(double t, const double* __restrict__ 
     } else {
         p = fma(kExpC2, g, kExpC1);
     }
-    p = fma(p, g, kExpC0);
+    if (!kExpSq) p = fma(p, g, kExpC0);
     if (SAFE) {
         // hi word of a negative double grows (as unsigned) with its magnitude;
         // kHiLim is the hi word of -(1022 * K)

@@ -1348,7 +1348,8 @@ int pbn_ctx_create(int device, pbn_ctx** out) {
     std::vector<double> tab(pbn::kExpTab);
     for (int j = 0; j < pbn::kExpTab; ++j) {
         // T'[j]: 2^(j/K) with (j << (20 - log2 K)) subtracted from the high word (see exp2_tab)
-        double v = (double)exp2l((long double)j / pbn::kExpTab);
+        // (times c2 for the completed-square polynomial, pair_kernel.cuh: PBN_EXP_SQ)
+        double v = (double)(exp2l((long double)j / pbn::kExpTab) * (pbn::kExpSq ? (long double)pbn::kExpSqC2 : 1.0L));
         uint64_t bits;
         memcpy(&bits, &v, 8);
         uint32_t hi = (uint32_t)(bits >> 32) - ((uint32_t)j << (20 - pbn::kExpTabBits));

@@ -310,9 +310,11 @@ def test_cvl_folds_with_isolated_outliers_take_the_shifted_pass(pbn):
     pbn_shift_pass, job by job) and the score still equals the oracle's serial fit + slogl per fold."""
     data = util_data.generate_normal_data(3000, 0)
     rng = np.random.default_rng(4)
-    idx = rng.choice(3000, 60, replace=False)
-    data.loc[idx, "a"] += np.linspace(30.0, 3000.0, 60) * rng.choice([-1.0, 1.0], 60)
-    data.loc[idx[:20], "c"] -= np.linspace(50.0, 900.0, 20)
+    # geometric spacing: the bandwidth grows with the largest outlier, so evenly spaced ones would stay within a few
+    # bandwidths of each other; here the two or three largest of each column are > 40 bandwidths from any other row
+    idx = rng.choice(3000, 24, replace=False)
+    data.loc[idx[:12], "a"] += 200.0 * 3.0 ** np.arange(12) * rng.choice([-1.0, 1.0], 12)
+    data.loc[idx[12:], "c"] -= 300.0 * 3.0 ** np.arange(12)
     cvl = pbn.CVLikelihood(data, 10, seed)
     kdn = pbn.KDENetwork(list(data.columns))
     ctx = pbn.default_context()
