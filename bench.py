@@ -380,12 +380,19 @@ def main():
     f_hz = (clocks.get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0) * 1e6
     sms, lanes = ctx.sm_count, 64
     # FP64-pipe instructions this kernel issues per (train, test) row pair, which is 2 pair-evals (joint + marginal):
-    # marginal exponent in dot-product form with the test-row norm hoisted (3 DFMA), table exp2 (3 DADD + 2 DFMA,
-    # degree-2 polynomial on K = 4096) + 1 DFMA to accumulate, last coordinate in difference form (1 DADD + 1 DFMA),
-    # second exp2 + accumulate: 3 + 6 + 2 + 6 = 17 (SASS: profiles/r2_sass_pair_f64_ckde_d4.txt).  The roofline is
-    # the FP64 pipe at that count; `frac` is therefore the FP64-pipe utilisation and is cross-checked by ncu's
+    # marginal exponent in dot-product form with the test-row norm hoisted (3 DFMA), table exp2 in completed-square form
+    # (3 DADD to split the argument + 1 DFMA (g + S)^2 + Cq on K = 4096) + 1 DFMA to accumulate, last coordinate in
+    # difference form (1 DADD + 1 DFMA), second exp2 + accumulate: 3 + 5 + 2 + 5 = 15 (SASS:
+    # profiles/r2_sass_pair_f64_ckde_d4.txt; 17 until round 2's completed-square polynomial).  The roofline is the FP64
+    # pipe at that count; `frac` is therefore the FP64-pipe utilisation and is cross-checked by ncu's
     # sm__inst_executed_pipe_fp64 (profiles/r2_ncu_pair_f64_ckde_d4.txt).
-    i_own = 17 / 2.0
+    i_own = 15 / 2.0
+    i_round1 = 17 / 2.0
+    # Issue model measured with tools/micro/fp64_mix.cu (profiles/r2_fp64_mix.txt): per scheduler an FP64 instruction costs
+    # 2 clk with one or two register sources and 3 clk with three (two 32-bit register read ports per clock), any other
+    # instruction 1 clk when the FP64 stream already saturates those ports.  Inner loop of 12 row pairs (SASS): 180 FP64
+    # of which 36 with three register sources (24 accumulates, 12 first dot-product steps) + 140 others = 536 clk.
+    model_clk_per_row_pair = (2 * 180 + 36 + 140) / 12.0
     # SURVEY.md 8(d) models a two-pass kernel with a 16-instruction polynomial exp: I(d) = 2d + 18 per pair-eval,
     # (26 + 24) / 2 = 25 for joint d=4 + marginal d=3.  This kernel needs a third of that, so the ratio against the
     # SURVEY model exceeds 1; it is reported on the side, never as the utilisation.
@@ -409,9 +416,20 @@ def main():
         "unit": UNIT, "frac": (achieved / peak) if achieved else None, "traffic": traffic,
         "traffic_source": traffic_src,
         "peak_def": "SMs(%d) x 64 FP64 lanes x %.0f MHz (median SM clock sampled in the timed region) / %.1f FP64-pipe "
-                    "instructions the kernel issues per pair-eval (17 per train x test row pair, SASS-counted): frac is "
+                    "instructions the kernel issues per pair-eval (15 per train x test row pair, SASS-counted): frac is "
                     "the FP64-pipe utilisation" % (sms, f_hz / 1e6, i_own),
         "fp64_instr_per_pair_eval": i_own,
+        "frac_at_round1_instruction_count": (achieved / (sms * lanes * f_hz / i_round1)) if achieved else None,
+        "round1_note": "round 1 / early round 2 issued 8.5 FP64 instructions per pair-eval (1.52e12 pair-evals/s = 0.69 of that "
+                       "roofline); the completed-square exp2 needs 7.5, so the same hardware utilisation now yields more pairs - "
+                       "this key is the throughput against the ROUND-1 roofline, for comparison only",
+        "issue_model": {
+            "clk_per_row_pair_model": model_clk_per_row_pair,
+            "clk_per_row_pair_measured": (sms * 4 * f_hz * 32 * 2.0 / achieved) if achieved else None,
+            "note": "per scheduler: FP64 instruction 2 clk (<= 2 register sources) or 3 clk (3 sources), others 1 clk "
+                    "(tools/micro/fp64_mix.cu, profiles/r2_fp64_mix.txt); the kernel is bound by the register read ports, "
+                    "the FP64 share of the modelled time is %.2f" % (2 * 180 / (2 * 180 + 36 + 140.0)),
+        },
         "frac_vs_survey_model": (achieved / (sms * lanes * f_hz / i_survey)) if achieved else None,
         "survey_model": "SURVEY.md 8(d) two-pass count, %.0f FP64 instr per pair-eval; a fused table-exp2 pass undercuts "
                         "it, so this ratio is > 1 and is NOT a utilisation" % i_survey,
