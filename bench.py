@@ -287,7 +287,8 @@ def main():
     value = pairs_per_step_job * steps / (total_ms * 1e-3)
 
     # ---- the same steps with the product's default, tile skipping on (spatial.cu): units the bounding boxes prove
-    # negligible (< 2^-48 of every row's sum) are dropped; the metric still counts n_train x n_test pairs per step ----
+    # negligible (< 2^-40 of every row's sum) are dropped, and inside the remaining units groups of training points whose terms
+    # are below 2^-64 of the running sums for a whole warp (pair_kernel.cuh: tile_f64_dot_gskip); the metric still counts n_train x n_test pairs per step ----
     ctx.set_skipping(True)
     step()
     barrier()
@@ -313,7 +314,8 @@ def main():
                      "slogl_sum_over_ranks": slogl_skipping,
                      "rel_diff_vs_all_pairs": abs(slogl_skipping - slogl_total) / abs(slogl_total),
                      "note": "same steps with tile skipping on (the library default): (test tile x train tile) units whose "
-                             "bounding boxes prove all their terms < 2^-48 of every row's sum are not evaluated; the metric "
+                             "bounding boxes prove all their terms < 2^-40 of every row's sum are not evaluated, nor are groups of training points inside "
+                             "the other units whose terms are < 2^-64 of the running sums for all rows of a warp; the metric "
                              "counts n_train x n_test pairs regardless, so this is NOT comparable with `value`"}
     assert with_skipping["rel_diff_vs_all_pairs"] < 1e-12, with_skipping
 

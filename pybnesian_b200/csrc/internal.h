@@ -228,6 +228,8 @@ cudaError_t launch_pair_f64(int D, bool ckde, const PairJob* jobs, int n_jobs, l
                             int grid, const double* tab, cudaStream_t stream);
 cudaError_t launch_pair_f32(int D, bool ckde, const PairJob* jobs, int n_jobs, long long total_units, long long upb,
                             int grid, const double* tab, cudaStream_t stream);
+cudaError_t launch_pair_gskip_f64(int D, bool ckde, const PairJob* jobs, int n_jobs, long long total_units, long long upb,
+                                  int grid, const double* tab, cudaStream_t stream);
 cudaError_t launch_pair_shift_f64(int D, bool ckde, const PairJob* job, const long long* dyn, int grid, const double* tab,
                                   cudaStream_t stream);
 cudaError_t launch_pair_shift_f32(int D, bool ckde, const PairJob* job, const long long* dyn, int grid, const double* tab,

@@ -625,6 +625,110 @@ __device__ __forceinline__ void tile_f64_dot(const double* __restrict__ tp, cons
     }
 }
 
+// GROUP SKIPPING (pass B of tile skipping, rows in Morton order; `pair_kernel<..., GSKIP = true>`): the bounding boxes of
+// spatial.cu decide per (768 test rows x 512 training points); inside a unit that stays, a WARP (3 x 32 neighbouring test
+// rows) still meets many groups of G = 2..4 neighbouring training points whose terms are all negligible.  Per group the
+// marginal exponents (the dot products, needed anyway) are compared with a per-row threshold before anything else is
+// computed; if no lane of the warp has a term above it, the group's exp2 (10 of the 15 FP64 instructions of a CKDE row
+// pair, all 10 integer ones) are not executed.  One warp-uniform branch per G x R row pairs, the two sides are long
+// straight-line blocks - unlike the per-term vote (PBN_F64_WARPSKIP), which was slower than no skipping at all.
+//   threshold = K (exponent(running sum) - kSkipBits) - A_row: a skipped term is below 2^-kSkipBits of the sum it would
+//   join, all skipped terms of a row below N 2^-kSkipBits of it (2^-44 for a million rows: 6e-14 on logl).  A CKDE's joint
+//   exponent never exceeds its marginal one, so the test on the marginal exponent against the LOWER of the two thresholds
+//   covers both sums.  Pass B starts from the pass-A sums, so the thresholds are in place from the first group on.
+#ifndef PBN_F64_GSKIP_BITS
+#define PBN_F64_GSKIP_BITS 64
+#endif
+#ifndef PBN_F64_GSKIP_GROUP
+#define PBN_F64_GSKIP_GROUP 0
+#endif
+constexpr int kSkipBits = PBN_F64_GSKIP_BITS;
+// training points per group: 2.  The group's R x G exponents stay live across the branch: 4 points spill next to R = 3 or 4
+// test rows, and finer groups are skipped more often (B200, 1M x 1M, profiles/r2_tuning.md section 7: CKDE d=4 2.65e12
+// plain, 3.06e12 with G = 4, 3.13e12 with G = 3, 3.25e12 with G = 2)
+__host__ __device__ constexpr int pair_gskip_group(bool ckde) {
+    return PBN_F64_GSKIP_GROUP > 0 ? PBN_F64_GSKIP_GROUP : 2;
+}
+__device__ __forceinline__ int pair_skip_level(double sum) {
+    const int e = __double2hiint(sum) >> 20;  // sum >= 0
+    const int f = (e - 1023 - kSkipBits) * kExpTab;
+    return (e <= 0 || e >= 2047) ? kNMin : max(f, kNMin);
+}
+template <int D, bool CKDE, int R>
+__device__ __forceinline__ void tile_f64_dot_gskip(const double* __restrict__ tp, const double* __restrict__ nb, int cnt,
+                                                   const double (&yt)[R][D], const int (&ati)[R],
+                                                   const double* __restrict__ tab, double (&sum_j)[R], double (&sum_m)[R]) {
+    constexpr int DN = CKDE ? D - 1 : D;
+    constexpr int G = pair_gskip_group(CKDE);
+    int fl_j[R], fl_m[R], thr[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        fl_j[r] = pair_floor(sum_j[r]);
+        fl_m[r] = CKDE ? pair_floor(sum_m[r]) : kNMin;
+        int lv = pair_skip_level(sum_j[r]);
+        if (CKDE) lv = min(lv, pair_skip_level(sum_m[r]));
+        thr[r] = lv - ati[r];  // |ati| < 2^31 - |kNMin| (the `safe` test of the caller): no overflow
+    }
+    auto finish = [&](int r, double acc, double p_last) {  // acc: marginal exponent of (row r, one training point)
+        const int ns = ati[r];
+        if (CKDE) {
+            double st;
+            double pm = exp2_tab<false>(acc, tab, st, ns, fl_m[r]);
+            sum_m[r] = fma(st, pm, sum_m[r]);
+            double dl = yt[r][D - 1] - p_last;
+            acc = fma(-dl, dl, acc);
+        }
+        double st;
+        double pj = exp2_tab<false>(acc, tab, st, ns, fl_j[r]);
+        sum_j[r] = fma(st, pj, sum_j[r]);
+    };
+    int i = 0;
+    for (; i + G <= cnt; i += G) {
+        double acc[G][R];
+        int top[R];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            double p[DN];
+#pragma unroll
+            for (int c = 0; c < DN; ++c) p[c] = tp[(i + g) * D + c];
+            const double b = nb[i + g];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                double a = b;
+#pragma unroll
+                for (int c = 0; c < DN; ++c) a = fma(yt[r][c], p[c], a);
+                acc[g][r] = a;
+                const int lo = __double2loint(a + 6755399441055744.0);  // rint(a): the same DADD opens exp2_tab
+                top[r] = g == 0 ? lo : max(top[r], lo);
+            }
+        }
+        bool live = false;
+#pragma unroll
+        for (int r = 0; r < R; ++r) live |= top[r] > thr[r];
+        if (__any_sync(0xffffffffu, live)) {
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const double p_last = CKDE ? tp[(i + g) * D + D - 1] : 0.0;
+#pragma unroll
+                for (int r = 0; r < R; ++r) finish(r, acc[g][r], p_last);
+            }
+        }
+    }
+    for (; i < cnt; ++i) {  // tail of the last training tile
+        double p[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) p[c] = tp[i * D + c];
+        const double b = nb[i];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            double a = b;
+#pragma unroll
+            for (int c = 0; c < DN; ++c) a = fma(yt[r][c], p[c], a);
+            finish(r, a, p[D - 1]);
+        }
+    }
+}
+
 // Same unit on the FP32 FMA pipe + MUFU.EX2; per-tile float sums are folded into the
 // double accumulators by the caller (summation error stays at ~sqrt(TILE) ulp).
 template <int D, bool CKDE, int R, bool CDF>
@@ -860,7 +964,8 @@ __device__ __forceinline__ void tile_f32_packed_cdf(const float* __restrict__ tp
 // (kernel-unit) coordinate difference into standard-normal units and is only read in that mode.
 // SHIFT = true: the shifted second pass (tile_f64_shift / tile_f32_shift) over ONE job whose size is only known on the
 // device: `dyn` = {total_units, upb} written by shift_prep_kernel (runtime.cu) replaces the by-value arguments.
-template <typename T, int D, bool CKDE, bool CDF = false, bool SHIFT = false>
+// GSKIP = true (f64, log-likelihood sums, jobs with a unit list): the group-skipping tile, see tile_f64_dot_gskip.
+template <typename T, int D, bool CKDE, bool CDF = false, bool SHIFT = false, bool GSKIP = false>
 __global__ void __launch_bounds__(kThreads, PairCfg<T>::MIN_CTAS)
 pair_kernel(const PairJob* __restrict__ jobs, int n_jobs, long long total_units, long long upb,
             const double* __restrict__ exp_tab_g, double inv_c, const long long* __restrict__ dyn = nullptr) {
@@ -1055,7 +1160,9 @@ pair_kernel(const PairJob* __restrict__ jobs, int n_jobs, long long total_units,
             tile_f32_shift<D, CKDE, R>(tp, cnt, yt, shj, shm, sum_j, sum_m);
         } else if constexpr (sizeof(T) == 8) {
             if (DOT && dot) {
-                if (PBN_F64_WARPSKIP && !CDF && jb.unit_list)
+                if constexpr (GSKIP && !CDF)
+                    tile_f64_dot_gskip<D, CKDE, R>(tp, nrm_buf + static_cast<size_t>(stage) * TILE, cnt, yt, ati, tab, sum_j, sum_m);
+                else if (PBN_F64_WARPSKIP && !CDF && jb.unit_list)
                     tile_f64_dot<D, CKDE, R, CDF, true>(tp, nrm_buf + static_cast<size_t>(stage) * TILE, cnt, yt, at, ati, tab, sum_j, sum_m, inv_c);
                 else
                     tile_f64_dot<D, CKDE, R, CDF>(tp, nrm_buf + static_cast<size_t>(stage) * TILE, cnt, yt, at, ati, tab, sum_j, sum_m, inv_c);

@@ -5,12 +5,12 @@
 
 namespace pbn {
 
-template <int D, bool CKDE, bool CDF = false, bool SHIFT = false>
+template <int D, bool CKDE, bool CDF = false, bool SHIFT = false, bool GSKIP = false>
 static cudaError_t launch_one(const PairJob* jobs, int n_jobs, long long total_units, long long upb, int grid,
                               const double* tab, cudaStream_t stream, double inv_c = 0.0, const long long* dyn = nullptr) {
     constexpr size_t smem = kStages * (pair_tile<PBN_T>(D) * D * sizeof(PBN_T) + pair_nrm_bytes<PBN_T>(D)) + 64 + exp_tab_smem_bytes<PBN_T>();
     static_assert(smem <= 113 * 1024 || PairCfg<PBN_T>::MIN_CTAS < 2, "two CTAs per SM must fit in shared memory");
-    auto kern = pair_kernel<PBN_T, D, CKDE, CDF, SHIFT>;
+    auto kern = pair_kernel<PBN_T, D, CKDE, CDF, SHIFT, GSKIP>;
     // set on every launch: the attribute is per device (and per context), and the call is a host-side table update
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
@@ -88,5 +88,23 @@ cudaError_t PBN_SHIFT_WARM_NAME() {
 }
 
 #endif  // PBN_SHIFT_LAUNCH_NAME
+
+#ifdef PBN_GSKIP_LAUNCH_NAME
+// Pass B of tile skipping with group skipping inside the units (f64; families of up to 5 variables - wider ones never
+// take the tile-skipping path at sizes that fit a GPU).
+cudaError_t PBN_GSKIP_LAUNCH_NAME(int D, bool ckde, const PairJob* jobs, int n_jobs, long long total_units, long long upb,
+                                  int grid, const double* tab, cudaStream_t stream) {
+#define PBN_CASE(d)                                                                                                              \
+    case d:                                                                                                                      \
+        return ckde ? launch_one<(d < 2 ? 2 : d), true, false, false, true>(jobs, n_jobs, total_units, upb, grid, tab, stream)   \
+                    : launch_one<d, false, false, false, true>(jobs, n_jobs, total_units, upb, grid, tab, stream);
+    switch (D) {
+        PBN_CASE(1) PBN_CASE(2) PBN_CASE(3) PBN_CASE(4) PBN_CASE(5)
+        default:
+            return cudaErrorInvalidValue;
+    }
+#undef PBN_CASE
+}
+#endif  // PBN_GSKIP_LAUNCH_NAME
 
 }  // namespace pbn

@@ -1213,8 +1213,14 @@ static int logl_one(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const
         ctx->launches++;
         PBN_CUDA_TRY(cudaGetLastError());
         if (U > 0) {
-            cudaError_t e = f64 ? pbn::launch_pair_f64(d, k->ckde, d_job, 1, U, upb, grid, ctx->d_exp_tab, st)
-                                : pbn::launch_pair_f32(d, k->ckde, d_job, 1, U, upb, grid, ctx->d_exp_tab, st);
+            // pass B (unit list, Morton order) in float64: the kernel that also skips groups of training points inside a
+            // unit (tile_f64_dot_gskip); PBN_GROUP_SKIP=0 keeps the plain kernel (A/B measurements)
+            static const bool group_skip = !(getenv("PBN_GROUP_SKIP") && atoi(getenv("PBN_GROUP_SKIP")) == 0);
+            // (not for one-dimensional exponents: with a single DFMA per exponent the test costs more than it saves)
+            const bool gs = f64 && have_A && group_skip && d <= 5 && d - (k->ckde ? 1 : 0) >= 2;
+            cudaError_t e = gs    ? pbn::launch_pair_gskip_f64(d, k->ckde, d_job, 1, U, upb, grid, ctx->d_exp_tab, st)
+                            : f64 ? pbn::launch_pair_f64(d, k->ckde, d_job, 1, U, upb, grid, ctx->d_exp_tab, st)
+                                  : pbn::launch_pair_f32(d, k->ckde, d_job, 1, U, upb, grid, ctx->d_exp_tab, st);
             ctx->launches++;
             PBN_CUDA_TRY(e);
         }

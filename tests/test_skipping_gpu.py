@@ -1,5 +1,8 @@
 """Tile skipping (pybnesian_b200/csrc/spatial.cu; on by default for large single-model calls): Morton-ordered rows, one
-bounding box per tile, units whose boxes prove every dropped term of a row below 2^-48 of its sum are not evaluated.
+bounding box per tile, units whose boxes prove every dropped term of a row below 2^-40 of its sum are not evaluated; in
+float64 the units that stay also skip groups of training points whose terms are below 2^-64 of the running sums for every
+row of a warp (pair_kernel.cuh: tile_f64_dot_gskip - families with two or more kernel coordinates, exercised here by KDE(b, a),
+KDE(a, b, c) and CKDE(c | a, b)).
 The reference evaluates every pair (kde/KDE.hpp:592-640); results must agree with the all-pairs evaluation far inside the
 1e-10 (float64) / 1e-4 (float32) bars, in the caller's row order, whatever the data look like."""
 import numpy as np
