@@ -811,11 +811,52 @@ __device__ __forceinline__ float ex2_neg(float s) {  // 2^(-s)
     return e;
 }
 
+// MUFU OFFLOAD.  The f32 kernels of 1-4 variables are bound by MUFU.EX2 (16 per clock and SM: 8 clk of the scheduler's SFU
+// per warp instruction) while the FP32 pipe idles, so a share of the exponentials is evaluated on the FP32 pipe instead,
+// two rows per instruction: 2^(-s) = 2^n P(f), n = rint(-s) from the mantissa of -s + 1.5 2^23, f = -s - n in [-1/2, 1/2],
+// P the degree-4 interpolant of 2^f at the Chebyshev nodes (3.5e-6 relative, zero mean; MUFU.EX2: 2e-7; the float32 bar
+// is 1e-4), the exponent added to the bit pattern.  3 FADD2/FFMA2 to split + 4 FFMA2 + 2 FMNMX + 4 integer instructions per
+// TWO exponentials.  Which of the (point, joint / marginal) slots of a 4-point step take this path is a compile-time mask
+// (PBN_F32_SOFT_MASK, bit 2 u + 1 = joint / only exponential of point u, bit 2 u = marginal of point u), so there is no
+// divergence and the MUFU and FP32 streams interleave.
+#ifndef PBN_F32_SOFT_MASK
+#define PBN_F32_SOFT_MASK -1
+#endif
+// B200, N = m = 400k, pair-evals/s (profiles/r2_tuning.md section 8): KDE d=1 4.42e12 -> 5.02e12 with one exponential in four
+// offloaded (the MUFU roof is 4.65e12); CKDE d=2 4.48e12 -> 5.43e12, d=3 4.40e12 -> 5.01e12 with the joint exponential of every
+// second point (one in four); CKDE d=4 4.28e12 -> 4.62e12 with one in eight.  KDE d >= 2 and wider CKDEs are bound by the FP32
+// pipe / issue slots already and lose (KDE d=3: -13%): mask 0.
+__host__ __device__ constexpr unsigned pair_f32_soft_mask(int D, bool ckde) {
+    return PBN_F32_SOFT_MASK >= 0 ? static_cast<unsigned>(PBN_F32_SOFT_MASK)
+         : ckde ? (D <= 3 ? 0x88u : D == 4 ? 0x80u : 0u)
+                : (D == 1 ? 0x80u : 0u);
+}
+__device__ __forceinline__ f32x2_t ex2_neg_soft2(f32x2_t s2) {
+    float lo, hi;
+    unpack_f32x2(s2, lo, hi);
+    s2 = pack_f32x2(fminf(lo, 125.f), fminf(hi, 125.f));  // 2^-125 ~ 2e-38: nothing next to a sum above the 2^-64 flag level
+    const f32x2_t MAGIC = pack_f32x2(12582912.f, 12582912.f), NMAGIC = pack_f32x2(-12582912.f, -12582912.f);
+    const f32x2_t r = ffma2(s2, pack_f32x2(-1.f, -1.f), MAGIC);   // low mantissa bits: n = rint(-s)
+    const f32x2_t g = fadd2(s2, fadd2(r, NMAGIC));                // s + n = -f
+    // P(f) = 1 + c1 f + c2 f^2 + c3 f^3 + c4 f^4 in g = -f: odd coefficients change sign
+    f32x2_t p = ffma2(g, pack_f32x2(0.009666368515f, 0.009666368515f), pack_f32x2(-0.05592197584f, -0.05592197584f));
+    p = ffma2(p, g, pack_f32x2(0.2402234904f, 0.2402234904f));
+    p = ffma2(p, g, pack_f32x2(-0.6931210452f, -0.6931210452f));
+    p = ffma2(p, g, pack_f32x2(1.f, 1.f));
+    float plo, phi, rlo, rhi;
+    unpack_f32x2(p, plo, phi);
+    unpack_f32x2(r, rlo, rhi);
+    plo = __int_as_float(__float_as_int(plo) + (__float_as_int(rlo) << 23));
+    phi = __int_as_float(__float_as_int(phi) + (__float_as_int(rhi) << 23));
+    return pack_f32x2(plo, phi);
+}
+
 template <int D, bool CKDE, int R>
 __device__ __forceinline__ void tile_f32_packed(const float* __restrict__ tp, int cnt, const float (&yt)[R][D],
                                                 double (&sum_j)[R], double (&sum_m)[R]) {
     static_assert(R % 2 == 0, "packed f32 tile needs an even number of rows per thread");
     constexpr int H = R / 2;
+    constexpr unsigned SOFT = pair_f32_soft_mask(D, CKDE);
     f32x2_t nyt[H][D];
     f32x2_t facc_j[H], facc_m[H];
 #pragma unroll
@@ -825,8 +866,7 @@ __device__ __forceinline__ void tile_f32_packed(const float* __restrict__ tp, in
         facc_j[h] = 0ull;
         facc_m[h] = 0ull;
     }
-#pragma unroll 4
-    for (int i = 0; i < cnt; ++i) {
+    auto point = [&](int i, bool soft_j, bool soft_m) {
         f32x2_t p2[D];
 #pragma unroll
         for (int c = 0; c < D; ++c) {
@@ -841,16 +881,30 @@ __device__ __forceinline__ void tile_f32_packed(const float* __restrict__ tp, in
                 f32x2_t d2 = fadd2(p2[c], nyt[h][c]);
                 s2 = ffma2(d2, d2, s2);
                 if (CKDE && c == D - 2) {
-                    float lo, hi;
-                    unpack_f32x2(s2, lo, hi);
-                    facc_m[h] = fadd2(facc_m[h], pack_f32x2(ex2_neg(lo), ex2_neg(hi)));
+                    if (soft_m) {
+                        facc_m[h] = fadd2(facc_m[h], ex2_neg_soft2(s2));
+                    } else {
+                        float lo, hi;
+                        unpack_f32x2(s2, lo, hi);
+                        facc_m[h] = fadd2(facc_m[h], pack_f32x2(ex2_neg(lo), ex2_neg(hi)));
+                    }
                 }
             }
-            float lo, hi;
-            unpack_f32x2(s2, lo, hi);
-            facc_j[h] = fadd2(facc_j[h], pack_f32x2(ex2_neg(lo), ex2_neg(hi)));
+            if (soft_j) {
+                facc_j[h] = fadd2(facc_j[h], ex2_neg_soft2(s2));
+            } else {
+                float lo, hi;
+                unpack_f32x2(s2, lo, hi);
+                facc_j[h] = fadd2(facc_j[h], pack_f32x2(ex2_neg(lo), ex2_neg(hi)));
+            }
         }
+    };
+    int i = 0;
+    for (; i + 4 <= cnt; i += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) point(i + u, (SOFT >> (2 * u + 1)) & 1u, (SOFT >> (2 * u)) & 1u);
     }
+    for (; i < cnt; ++i) point(i, false, false);
 #pragma unroll
     for (int h = 0; h < H; ++h) {
         float lo, hi;
