@@ -392,9 +392,10 @@ def main():
     i_round1 = 17 / 2.0
     # Issue model measured with tools/micro/fp64_mix.cu (profiles/r2_fp64_mix.txt): per scheduler an FP64 instruction costs
     # 2 clk with one or two register sources and 3 clk with three (two 32-bit register read ports per clock), any other
-    # instruction 1 clk when the FP64 stream already saturates those ports.  Inner loop of 12 row pairs (SASS): 180 FP64
-    # of which 36 with three register sources (24 accumulates, 12 first dot-product steps) + 140 others = 536 clk.
-    model_clk_per_row_pair = (2 * 180 + 36 + 140) / 12.0
+    # instruction 1 clk when the FP64 stream already saturates those ports.  Inner loop of 24 row pairs (SASS, 8 points x 3
+    # rows): 360 FP64 of which 72 with three register sources (48 accumulates, 24 first dot-product steps) + 270 others.
+    loop_fp64, loop_3src, loop_other, loop_pairs = 360, 72, 270, 24
+    model_clk_per_row_pair = (2 * loop_fp64 + loop_3src + loop_other) / float(loop_pairs)
     # SURVEY.md 8(d) models a two-pass kernel with a 16-instruction polynomial exp: I(d) = 2d + 18 per pair-eval,
     # (26 + 24) / 2 = 25 for joint d=4 + marginal d=3.  This kernel needs a third of that, so the ratio against the
     # SURVEY model exceeds 1; it is reported on the side, never as the utilisation.
@@ -430,7 +431,7 @@ def main():
             "clk_per_row_pair_measured": (sms * 4 * f_hz * 32 * 2.0 / achieved) if achieved else None,
             "note": "per scheduler: FP64 instruction 2 clk (<= 2 register sources) or 3 clk (3 sources), others 1 clk "
                     "(tools/micro/fp64_mix.cu, profiles/r2_fp64_mix.txt); the kernel is bound by the register read ports, "
-                    "the FP64 share of the modelled time is %.2f" % (2 * 180 / (2 * 180 + 36 + 140.0)),
+                    "the FP64 share of the modelled time is %.2f" % (2.0 * loop_fp64 / (2 * loop_fp64 + loop_3src + loop_other)),
         },
         "frac_vs_survey_model": (achieved / (sms * lanes * f_hz / i_survey)) if achieved else None,
         "survey_model": "SURVEY.md 8(d) two-pass count, %.0f FP64 instr per pair-eval; a fused table-exp2 pass undercuts "

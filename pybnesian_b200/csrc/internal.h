@@ -250,6 +250,7 @@ int pair_ctas_per_sm_f64();  // persistent CTAs per SM the kernels are register-
 int pair_ctas_per_sm_f32();
 cudaError_t warm_pair_f64();
 cudaError_t warm_pair_f32();
+cudaError_t warm_pair_gskip_f64();
 cudaError_t warm_pair_shift_f64();
 cudaError_t warm_pair_shift_f32();
 int pair_tb_cdf_f32(int D);

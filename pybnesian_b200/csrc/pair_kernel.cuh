@@ -164,8 +164,10 @@ template <typename T> __host__ __device__ constexpr int pair_rows(int D, bool ck
 template <typename T> __host__ __device__ constexpr int pair_rows_cdf(int D) {
     return (sizeof(T) == 8 && D >= 9) ? 2 : PairCfg<T>::R;
 }
-__host__ __device__ constexpr int pair_unroll_f64(int D, bool ckde) {
-    return (PBN_F64_UNROLL == 4 && !ckde && D <= 2) ? 8 : PBN_F64_UNROLL;
+// (round 2, with the completed-square exp2: 8 points per step pay up to d = 6 - CKDE d=4 +1.6%, KDE d=4 +1.3%, CKDE d=5 +1.2%,
+// KDE d=6 +3%; KDE d=8 -0.6%)
+__host__ __device__ constexpr int pair_unroll_f64(int D, bool ckde, bool cdf = false) {
+    return (PBN_F64_UNROLL == 4 && (cdf ? (!ckde && D <= 2) : D <= 6)) ? 8 : PBN_F64_UNROLL;
 }
 
 // exp2 table of the f64 path: T[j] = 2^(j/K), K = 2^PBN_EXP_BITS, held in shared memory in kExpRep
@@ -401,7 +403,7 @@ template <int D, bool CKDE, bool SAFE, int R, bool CDF>
 __device__ __forceinline__ void tile_f64(const double* __restrict__ tp, int cnt, const double (&yt)[R][D],
                                          const double* __restrict__ tab, double (&sum_j)[R], double (&sum_m)[R],
                                          double inv_c) {
-    constexpr int U = pair_unroll_f64(D, CKDE);
+    constexpr int U = pair_unroll_f64(D, CKDE, CDF);
     // exponent floors of this tile from the sums so far (log-likelihood sums only: a cdf sum may be far below its weights)
     int fl_j[R], fl_m[R];
 #pragma unroll
@@ -561,7 +563,7 @@ __device__ __forceinline__ void tile_f64_dot(const double* __restrict__ tp, cons
                                              const double* __restrict__ tab, double (&sum_j)[R], double (&sum_m)[R],
                                              double inv_c) {
     constexpr int DN = CKDE ? D - 1 : D;
-    constexpr int U = pair_unroll_f64(D, CKDE);
+    constexpr int U = pair_unroll_f64(D, CKDE, CDF);
     int fl_j[R], fl_m[R];  // see tile_f64
 #pragma unroll
     for (int r = 0; r < R; ++r) {

@@ -105,6 +105,10 @@ cudaError_t PBN_GSKIP_LAUNCH_NAME(int D, bool ckde, const PairJob* jobs, int n_j
     }
 #undef PBN_CASE
 }
+cudaError_t PBN_GSKIP_WARM_NAME() {
+    cudaFuncAttributes a;
+    return cudaFuncGetAttributes(&a, pair_kernel<PBN_T, 4, true, false, false, true>);
+}
 #endif  // PBN_GSKIP_LAUNCH_NAME
 
 }  // namespace pbn

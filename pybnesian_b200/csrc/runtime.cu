@@ -1481,6 +1481,7 @@ int pbn_ctx_warmup(pbn_ctx* ctx) {
         DevSetter ds(c->device);
         PBN_CUDA_TRY(pbn::warm_pair_f64());
         PBN_CUDA_TRY(pbn::warm_pair_f32());
+        PBN_CUDA_TRY(pbn::warm_pair_gskip_f64());
         PBN_CUDA_TRY(pbn::warm_pair_shift_f64());
         PBN_CUDA_TRY(pbn::warm_pair_shift_f32());
         cudaFuncAttributes a;
