@@ -10,10 +10,14 @@
 // Inputs are *whitened* rows (see whiten_kernel in runtime.cu):  y = c * L^-1 (x - mu)
 // with c chosen so that the exponent is already in table / log2 units:
 //   f64:  t = -sum_c (yt_c - yi_c)^2  ==  K * log2(e) * (-1/2 s)   (s = Mahalanobis^2, K = 4096)
-//         exp(-s/2) = 2^(t/K) = 2^k * T[j] * P(g),  n = rint(t), k = n>>11, j = n&2047,
-//         g = t - n in [-1/2, 1/2], P a degree-2 polynomial (max rel. err 2.5e-14 per term, four orders inside
-//         the 1e-10 parity bar).  Cost: 3 DADD + 2 DFMA + 1 DFMA (accumulate) on the FP64 pipe.
-//   f32:  t = -sum_c (..)^2 == log2(e) * (-1/2 s);  exp(-s/2) = ex2.approx(t) (1 MUFU).
+//         exp(-s/2) = 2^(t/K) = 2^k * T[j] * P(g),  n = rint(t), k = n>>12, j = n&4095,
+//         g = t - n in [-1/2, 1/2], P a degree-2 polynomial in completed-square form c2 ((g + S)^2 + Cq) (max rel. err
+//         2.2e-13 per term, zero mean; the parity bar is 1e-10).  Cost: 3 DADD + 1 DFMA + 1 DFMA (accumulate) on the FP64
+//         pipe, 5 integer / shared-memory instructions for 2^k T[j] (exp2_tab).
+//   f32:  t = -sum_c (..)^2 == log2(e) * (-1/2 s);  exp(-s/2) = ex2.approx(t) (1 MUFU), a per-shape share of them on the
+//         FP32 pipe instead (ex2_neg_soft2).
+// What bounds the f64 kernel is the scheduler's register read ports: an FP64 instruction costs 2 clk (3 with three register
+// sources), anything else 1 clk, and nothing overlaps (profiles/r2_tuning.md section 6) - instruction COUNT is the lever.
 // Sums are accumulated unshifted (every term <= 1); rows whose sum is too small for
 // that to be accurate are re-run with a per-row shift by the caller (runtime.cu).
 //
@@ -548,7 +552,7 @@ __device__ __forceinline__ void tile_f32_shift(const float* __restrict__ tp, int
 // their exponent floor skips the exp2 of that term altogether - the term would have been evaluated AS the floor, i.e. as
 // less than 2^-kFloorBits of the sum it joins (pair_floor), so dropping it changes the finished sum by less than the
 // floor mechanism itself already does.  The exponent (dot product, rounding) is still computed for every pair; what is
-// saved is 5 of the 6 FP64 instructions of the exp2 and its table gather, for the large majority of the pairs of a
+// saved is 4 of the 5 FP64 instructions of the exp2 and its table gather, for the large majority of the pairs of a
 // localised kernel sum.  Only worthwhile when neighbouring lanes hold neighbouring rows, hence tied to the Morton order.
 // MEASURED (B200, 1M x 1M, round 2, profiles/r2_tuning.md): slower than evaluating the floor terms - KDE d=2 5.03e12 ->
 // 3.58e12, d=4 1.67e12 -> 1.39e12 pair-evals/s with skipping on: the 24 warp-uniform branches per unrolled step cut the

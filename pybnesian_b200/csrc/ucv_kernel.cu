@@ -120,7 +120,7 @@ __device__ __forceinline__ void ucv_tile(const T* __restrict__ tp, int cnt, long
 
 // Dot-product form of the f64 tile (tile_f64_dot in pair_kernel.cuh): yi2 holds 2 y_i, the training norm nb is the addend
 // of the first DFMA, the integer part of the row's own norm is added to the rounded exponent (ati) and its fraction is a
-// per-row factor applied by the caller (scale on S2, scale^2 on S1).  D DFMA + 8 FP64 instructions per pair instead of 2 D + 8.
+// per-row factor applied by the caller (scale on S2, scale^2 on S1).  D DFMA + 7 FP64 instructions per pair instead of 2 D + 7.
 template <int D, bool DIAG, int R>
 __device__ __forceinline__ void ucv_tile_dot(const double* __restrict__ tp, const double* __restrict__ nb, int cnt,
                                              long long col0, const double (&yi2)[R][D], const int (&ati)[R],
