@@ -90,8 +90,8 @@ cudaError_t PBN_SHIFT_WARM_NAME() {
 #endif  // PBN_SHIFT_LAUNCH_NAME
 
 #ifdef PBN_GSKIP_LAUNCH_NAME
-// Pass B of tile skipping with group skipping inside the units (f64; families of up to 5 variables - wider ones never
-// take the tile-skipping path at sizes that fit a GPU).
+// Pass B of tile skipping with group skipping inside the units (f64; families of up to 8 variables: 9 and 10 run two rows
+// per thread and keep the plain kernel).
 cudaError_t PBN_GSKIP_LAUNCH_NAME(int D, bool ckde, const PairJob* jobs, int n_jobs, long long total_units, long long upb,
                                   int grid, const double* tab, cudaStream_t stream) {
 #define PBN_CASE(d)                                                                                                              \
@@ -99,7 +99,7 @@ cudaError_t PBN_GSKIP_LAUNCH_NAME(int D, bool ckde, const PairJob* jobs, int n_j
         return ckde ? launch_one<(d < 2 ? 2 : d), true, false, false, true>(jobs, n_jobs, total_units, upb, grid, tab, stream)   \
                     : launch_one<d, false, false, false, true>(jobs, n_jobs, total_units, upb, grid, tab, stream);
     switch (D) {
-        PBN_CASE(1) PBN_CASE(2) PBN_CASE(3) PBN_CASE(4) PBN_CASE(5)
+        PBN_CASE(1) PBN_CASE(2) PBN_CASE(3) PBN_CASE(4) PBN_CASE(5) PBN_CASE(6) PBN_CASE(7) PBN_CASE(8)
         default:
             return cudaErrorInvalidValue;
     }

@@ -983,6 +983,14 @@ static bool worth_sharding(const pbn_ctx* ctx, int64_t n_train, int64_t m) {
 
 // multi-device context, host outputs: contiguous shards of the test rows against the replicated model, one host thread
 // per device; slogl = the per-device sums added in device order (train replicated, test rows sharded)
+// Pass B of tile skipping uses the group-skipping kernel (pair_kernel<..., GSKIP>, tile_f64_dot_gskip): float64 families of up
+// to 8 variables with two or more kernel coordinates (one DFMA per exponent is too little to save: KDE d=1 lost 3%);
+// PBN_GROUP_SKIP=0 keeps the plain kernel (A/B measurements).
+static bool pair_group_skip(bool f64, int d, bool ckde) {
+    static const bool enabled = !(getenv("PBN_GROUP_SKIP") && atoi(getenv("PBN_GROUP_SKIP")) == 0);
+    return enabled && f64 && d <= 8 && d - (ckde ? 1 : 0) >= 2;
+}
+
 int pbn_logl_impl(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const int* cols, pbn_rows rows,
                      double* d_out_logl, double* d_out_slogl, double* h_out_logl, double* h_out_slogl) {
     if (!ctx || !k) return set_error(PBN_ERR_ARG, "null argument");
@@ -1176,7 +1184,12 @@ static int logl_one(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const
             long long total = 0;
             PBN_TRY(pbn_skip_count(ctx, d_jobA, upbA, TB, k->ckde ? 1 : 0, k->dtype, k->n, box_test, ntt, k->box, ntr, d, nearest, KA, thr,
                                    sumsA, count, tile_first, &total));
-            if ((double)(total + UA) > 0.92 * (double)ctx->last_units_total) {
+            // Share of the units above which the call gives up the sorted path (PBN_SKIP_KEEP_FRAC overrides, tuning).  The
+            // float64 kernels with group skipping keep it even when the boxes prove nothing: inside the units a warp's 96
+            // neighbouring rows still skip groups of training points (1M x 1M: KDE d=6 +12%, d=7 / 8 +8%, CKDE d=6 +30%).
+            static const double keep_env = getenv("PBN_SKIP_KEEP_FRAC") ? atof(getenv("PBN_SKIP_KEEP_FRAC")) : 0.0;
+            const double keep_frac = keep_env > 0.0 ? keep_env : (pair_group_skip(f64, d, k->ckde) ? 2.0 : 0.92);
+            if ((double)(total + UA) > keep_frac * (double)ctx->last_units_total) {
                 // (almost) nothing can be dropped - families of 6+ variables at these sizes: every pair is evaluated, in
                 // the caller's row order, where the exponent floor of pair_floor works best
                 use_sorted = false;
@@ -1213,11 +1226,8 @@ static int logl_one(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const
         ctx->launches++;
         PBN_CUDA_TRY(cudaGetLastError());
         if (U > 0) {
-            // pass B (unit list, Morton order) in float64: the kernel that also skips groups of training points inside a
-            // unit (tile_f64_dot_gskip); PBN_GROUP_SKIP=0 keeps the plain kernel (A/B measurements)
-            static const bool group_skip = !(getenv("PBN_GROUP_SKIP") && atoi(getenv("PBN_GROUP_SKIP")) == 0);
-            // (not for one-dimensional exponents: with a single DFMA per exponent the test costs more than it saves)
-            const bool gs = f64 && have_A && group_skip && d <= 5 && d - (k->ckde ? 1 : 0) >= 2;
+            // pass B (unit list, Morton order) in float64: the kernel that also skips groups of training points inside a unit
+            const bool gs = have_A && pair_group_skip(f64, d, k->ckde);
             cudaError_t e = gs    ? pbn::launch_pair_gskip_f64(d, k->ckde, d_job, 1, U, upb, grid, ctx->d_exp_tab, st)
                             : f64 ? pbn::launch_pair_f64(d, k->ckde, d_job, 1, U, upb, grid, ctx->d_exp_tab, st)
                                   : pbn::launch_pair_f32(d, k->ckde, d_job, 1, U, upb, grid, ctx->d_exp_tab, st);
