@@ -230,6 +230,8 @@ cudaError_t launch_pair_f32(int D, bool ckde, const PairJob* jobs, int n_jobs, l
                             int grid, const double* tab, cudaStream_t stream);
 cudaError_t launch_pair_gskip_f64(int D, bool ckde, const PairJob* jobs, int n_jobs, long long total_units, long long upb,
                                   int grid, const double* tab, cudaStream_t stream);
+cudaError_t launch_pair_gskip_f32(int D, bool ckde, const PairJob* jobs, int n_jobs, long long total_units, long long upb,
+                                  int grid, const double* tab, cudaStream_t stream);
 cudaError_t launch_pair_shift_f64(int D, bool ckde, const PairJob* job, const long long* dyn, int grid, const double* tab,
                                   cudaStream_t stream);
 cudaError_t launch_pair_shift_f32(int D, bool ckde, const PairJob* job, const long long* dyn, int grid, const double* tab,
@@ -251,6 +253,7 @@ int pair_ctas_per_sm_f32();
 cudaError_t warm_pair_f64();
 cudaError_t warm_pair_f32();
 cudaError_t warm_pair_gskip_f64();
+cudaError_t warm_pair_gskip_f32();
 cudaError_t warm_pair_shift_f64();
 cudaError_t warm_pair_shift_f32();
 int pair_tb_cdf_f32(int D);

@@ -925,6 +925,128 @@ __device__ __forceinline__ void tile_f32_packed(const float* __restrict__ tp, in
     }
 }
 
+// Group skipping for the packed f32 tile (pass B of tile skipping, `pair_kernel<float, ..., GSKIP>`; see tile_f64_dot_gskip).
+// The narrow f32 shapes are bound by MUFU.EX2, so what a skipped group saves is exactly the scarce resource: per group of 2
+// training points the squared distances over the marginal coordinates are formed as always (FP32 pipe), each row's smallest
+// one is compared with thr = kSkipBits32 - floor(log2(running sum)) and, when no lane of the warp has a term above
+// 2^-kSkipBits32 of its sum, the group's 2 (KDE) or 4 (CKDE) exponentials per row, the last-coordinate step and the
+// accumulates are not executed.  All skipped terms of a row are below N 2^-44 of its sum (6e-8 at a million rows; bar 1e-4).
+#ifndef PBN_F32_GSKIP_BITS
+#define PBN_F32_GSKIP_BITS 44
+#endif
+constexpr int kSkipBits32 = PBN_F32_GSKIP_BITS;
+__device__ __forceinline__ float pair_skip_level_f32(double sum) {
+    const int e = __double2hiint(sum) >> 20;  // sum >= 0: biased exponent
+    return (e <= 0 || e >= 2047) ? INFINITY : static_cast<float>(kSkipBits32 + 1023 - e);
+}
+template <int D, bool CKDE, int R>
+__device__ __forceinline__ void tile_f32_packed_gskip(const float* __restrict__ tp, int cnt, const float (&yt)[R][D],
+                                                      double (&sum_j)[R], double (&sum_m)[R]) {
+    static_assert(R % 2 == 0, "packed f32 tile needs an even number of rows per thread");
+    constexpr int H = R / 2;
+    constexpr int DN = CKDE ? D - 1 : D;
+    constexpr int G = 2;
+    f32x2_t nyt[H][D];
+    f32x2_t facc_j[H], facc_m[H];
+    float thr[R];
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) nyt[h][c] = pack_f32x2(-yt[2 * h][c], -yt[2 * h + 1][c]);
+        facc_j[h] = 0ull;
+        facc_m[h] = 0ull;
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        // a CKDE's joint term never exceeds its marginal one: the test on the marginal distance against the HIGHER of the
+        // two levels (the smaller sum's) covers both
+        thr[r] = pair_skip_level_f32(sum_j[r]);
+        if (CKDE) thr[r] = fmaxf(thr[r], pair_skip_level_f32(sum_m[r]));
+    }
+    auto finish = [&](int h, f32x2_t s2, f32x2_t p_last2) {
+        if (CKDE) {
+            float lo, hi;
+            unpack_f32x2(s2, lo, hi);
+            facc_m[h] = fadd2(facc_m[h], pack_f32x2(ex2_neg(lo), ex2_neg(hi)));
+            f32x2_t d2 = fadd2(p_last2, nyt[h][D - 1]);
+            s2 = ffma2(d2, d2, s2);
+        }
+        float lo, hi;
+        unpack_f32x2(s2, lo, hi);
+        facc_j[h] = fadd2(facc_j[h], pack_f32x2(ex2_neg(lo), ex2_neg(hi)));
+    };
+    int i = 0;
+    for (; i + G <= cnt; i += G) {
+        f32x2_t s2[G][H];
+        float low[R];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            f32x2_t p2[DN];
+#pragma unroll
+            for (int c = 0; c < DN; ++c) {
+                float v = tp[(i + g) * D + c];
+                p2[c] = pack_f32x2(v, v);
+            }
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                f32x2_t a = 0ull;
+#pragma unroll
+                for (int c = 0; c < DN; ++c) {
+                    f32x2_t d2 = fadd2(p2[c], nyt[h][c]);
+                    a = ffma2(d2, d2, a);
+                }
+                s2[g][h] = a;
+                float lo, hi;
+                unpack_f32x2(a, lo, hi);
+                low[2 * h] = g == 0 ? lo : fminf(low[2 * h], lo);
+                low[2 * h + 1] = g == 0 ? hi : fminf(low[2 * h + 1], hi);
+            }
+        }
+        bool live = false;
+#pragma unroll
+        for (int r = 0; r < R; ++r) live |= low[r] < thr[r];
+        if (__any_sync(0xffffffffu, live)) {
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const float v = CKDE ? tp[(i + g) * D + D - 1] : 0.f;
+                const f32x2_t p_last2 = pack_f32x2(v, v);
+#pragma unroll
+                for (int h = 0; h < H; ++h) finish(h, s2[g][h], p_last2);
+            }
+        }
+    }
+    for (; i < cnt; ++i) {  // tail of the last training tile
+        f32x2_t p2[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            float v = tp[i * D + c];
+            p2[c] = pack_f32x2(v, v);
+        }
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            f32x2_t a = 0ull;
+#pragma unroll
+            for (int c = 0; c < DN; ++c) {
+                f32x2_t d2 = fadd2(p2[c], nyt[h][c]);
+                a = ffma2(d2, d2, a);
+            }
+            finish(h, a, p2[D - 1]);
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+        float lo, hi;
+        unpack_f32x2(facc_j[h], lo, hi);
+        sum_j[2 * h] += static_cast<double>(lo);
+        sum_j[2 * h + 1] += static_cast<double>(hi);
+        if (CKDE) {
+            unpack_f32x2(facc_m[h], lo, hi);
+            sum_m[2 * h] += static_cast<double>(lo);
+            sum_m[2 * h + 1] += static_cast<double>(hi);
+        }
+    }
+}
+
 __device__ __forceinline__ f32x2_t fsub2(f32x2_t a, f32x2_t b) {
     f32x2_t r;
     asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
@@ -1240,7 +1362,9 @@ pair_kernel(const PairJob* __restrict__ jobs, int n_jobs, long long total_units,
             else
                 tile_f64<D, CKDE, false, R, CDF>(tp, cnt, yt, tab, sum_j, sum_m, inv_c);
         } else {
-            if constexpr (PBN_F32_PACKED && !CDF && R % 2 == 0 && D >= PBN_F32_PACKED_MIN_D)
+            if constexpr (GSKIP && !CDF && R % 2 == 0)
+                tile_f32_packed_gskip<D, CKDE, R>(tp, cnt, yt, sum_j, sum_m);
+            else if constexpr (PBN_F32_PACKED && !CDF && R % 2 == 0 && D >= PBN_F32_PACKED_MIN_D)
                 tile_f32_packed<D, CKDE, R>(tp, cnt, yt, sum_j, sum_m);
             else if constexpr (PBN_F32_PACKED && CDF && R % 2 == 0)
                 tile_f32_packed_cdf<D, CKDE, R>(tp, cnt, yt, sum_j, sum_m, static_cast<float>(inv_c));

@@ -986,9 +986,15 @@ static bool worth_sharding(const pbn_ctx* ctx, int64_t n_train, int64_t m) {
 // Pass B of tile skipping uses the group-skipping kernel (pair_kernel<..., GSKIP>, tile_f64_dot_gskip): float64 families of up
 // to 8 variables with two or more kernel coordinates (one DFMA per exponent is too little to save: KDE d=1 lost 3%);
 // PBN_GROUP_SKIP=0 keeps the plain kernel (A/B measurements).
+// float32 (tile_f32_packed_gskip): CKDE of 3..6 variables (1M x 1M with skipping: d=4 6.96e12 -> 8.47e12, d=5 4.65e12 ->
+// 5.61e12, d=6 3.73e12 -> 4.49e12, d=3 +4%; the KDE shapes and CKDE d=2 lose 2-17% - their plain kernel has the MUFU offload
+// and little else to save).  PBN_GROUP_SKIP_F32 overrides the shape mask (bit d: KDE of d variables, bit 8 + d: CKDE).
 static bool pair_group_skip(bool f64, int d, bool ckde) {
     static const bool enabled = !(getenv("PBN_GROUP_SKIP") && atoi(getenv("PBN_GROUP_SKIP")) == 0);
-    return enabled && f64 && d <= 8 && d - (ckde ? 1 : 0) >= 2;
+    static const unsigned f32_mask = getenv("PBN_GROUP_SKIP_F32") ? (unsigned)strtoul(getenv("PBN_GROUP_SKIP_F32"), nullptr, 0) : 0x7800u;
+    if (!enabled || d > 8) return false;
+    if (!f64) return (f32_mask >> ((ckde ? 8 : 0) + d)) & 1u;
+    return d - (ckde ? 1 : 0) >= 2;
 }
 
 int pbn_logl_impl(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const int* cols, pbn_rows rows,
@@ -1228,7 +1234,8 @@ static int logl_one(pbn_ctx* ctx, const pbn_kde* k, const pbn_table* test, const
         if (U > 0) {
             // pass B (unit list, Morton order) in float64: the kernel that also skips groups of training points inside a unit
             const bool gs = have_A && pair_group_skip(f64, d, k->ckde);
-            cudaError_t e = gs    ? pbn::launch_pair_gskip_f64(d, k->ckde, d_job, 1, U, upb, grid, ctx->d_exp_tab, st)
+            cudaError_t e = gs    ? (f64 ? pbn::launch_pair_gskip_f64(d, k->ckde, d_job, 1, U, upb, grid, ctx->d_exp_tab, st)
+                                         : pbn::launch_pair_gskip_f32(d, k->ckde, d_job, 1, U, upb, grid, ctx->d_exp_tab, st))
                             : f64 ? pbn::launch_pair_f64(d, k->ckde, d_job, 1, U, upb, grid, ctx->d_exp_tab, st)
                                   : pbn::launch_pair_f32(d, k->ckde, d_job, 1, U, upb, grid, ctx->d_exp_tab, st);
             ctx->launches++;
@@ -1492,6 +1499,7 @@ int pbn_ctx_warmup(pbn_ctx* ctx) {
         PBN_CUDA_TRY(pbn::warm_pair_f64());
         PBN_CUDA_TRY(pbn::warm_pair_f32());
         PBN_CUDA_TRY(pbn::warm_pair_gskip_f64());
+        PBN_CUDA_TRY(pbn::warm_pair_gskip_f32());
         PBN_CUDA_TRY(pbn::warm_pair_shift_f64());
         PBN_CUDA_TRY(pbn::warm_pair_shift_f32());
         cudaFuncAttributes a;
