@@ -773,8 +773,17 @@ static int64_t env_rows(const char* name, int64_t dflt) {
     const char* e = getenv(name);
     return (e && *e) ? (int64_t)atoll(e) : dflt;
 }
-static const int64_t kSkipMinTrain = env_rows("PBN_SKIP_MIN_TRAIN", 1 << 17);
+static const int64_t kSkipMinTrainEnv = env_rows("PBN_SKIP_MIN_TRAIN", 0);
 static const int64_t kSkipMinTest = env_rows("PBN_SKIP_MIN_TEST", 1 << 14);
+// Training rows from which the Morton-sorted copy is kept, by the number of kernel coordinates the sums are local in (the
+// marginal ones of a CKDE).  B200, N = m, float64, all pairs -> sorted path (profiles/r2_tuning.md section 10): one coordinate
+// 50k rows +34% (KDE d=1) / +19% (CKDE d=2), 100k rows +65% / +33%; two coordinates 50k -8%, 100k +22%; three and more lose
+// below ~130k (100k: 0% / -7%).
+static int64_t skip_min_train(int d, bool ckde) {
+    if (kSkipMinTrainEnv > 0) return kSkipMinTrainEnv;
+    const int dn = d - (ckde ? 1 : 0);
+    return dn <= 1 ? 40000 : (dn == 2 && !ckde) ? 90000 : (1 << 17);  // (CKDE d=3 at 100k: 0 .. -8%, stays at 2^17)
+}
 
 // multi-device context: the fitted model is replicated (every device whitens its own copy of the training rows)
 static int fit_impl(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, pbn_rows rows, const double* H,
@@ -851,7 +860,7 @@ static int fit_one(pbn_ctx* ctx, const pbn_table* tbl, const int* cols, int d, p
     rc = pbn_whiten_kde(ctx, k, tbl, cols, rows, k->y, k->d_bound, k->nrm);
     if (rc != PBN_OK) { cudaFreeAsync(k->y, ctx->stream); delete k; return rc; }
     // tile skipping: a second copy of the whitened rows in Morton order with one bounding box per training tile
-    if (d <= pbn::kMaxFastD && n >= kSkipMinTrain) {
+    if (d <= pbn::kMaxFastD && n >= skip_min_train(d, ckde)) {
         const int n_tiles = (int)((n + tile - 1) / tile);
         const size_t bbytes = ((size_t)n_tiles * 2 * d * sizeof(float) + 255) / 256 * 256;
         int* perm = nullptr;
