@@ -144,3 +144,27 @@ def test_f32_mufu_offload_polynomial_and_exponent_insertion():
     ok = want > 2.0 ** -124                                      # below: flushed / denormal, negligible next to any sum
     err = got[ok] / want[ok] - 1.0
     assert np.max(np.abs(err)) < 4e-6 and abs(err.mean()) < 2e-7
+
+
+def test_group_skip_levels_bound_what_is_dropped():
+    """tile_f64_dot_gskip / tile_f32_packed_gskip (pair_kernel.cuh): a group of training points is skipped when every rounded
+    exponent is at or below K (exponent(sum) - kSkipBits) (f64) / every squared distance at or above kSkipBits32 -
+    floor(log2 sum) (f32).  Restated with the constants of the header: every skipped term is then below 2^-bits of the
+    running sum, so all skipped terms of a row stay below N 2^-bits of it - 6e-14 (f64) / 6e-8 (f32) at a million rows."""
+    bits64, bits32 = _define("PBN_F64_GSKIP_BITS"), _define("PBN_F32_GSKIP_BITS")
+    assert bits64 >= 60 and bits32 >= 40            # N = 2^20 rows: 2^-40 (1e-12) of the sum in f64, 2^-20 (1e-6) in f32
+    rng = np.random.default_rng(7)
+    for s in np.exp2(rng.uniform(-900, 60, 2000)):
+        e = int(np.floor(np.log2(s)))                # exponent field of the running sum minus the bias
+        level = max((e - bits64) * K, NMIN)          # pair_skip_level
+        n = level                                    # the largest rounded exponent a skipped term can have
+        term_max = np.exp2((n + 0.5) / K)            # g <= 1/2 on top of the rounded exponent
+        if level > NMIN:
+            assert term_max <= s * 2.0 ** -(bits64 - 1)
+        thr32 = float(bits32 - e)                    # pair_skip_level_f32: bits + 1023 - biased exponent
+        assert np.exp2(-thr32) <= s * 2.0 ** -bits32
+    # a CKDE tests the marginal exponent against the LOWER of the two levels (f64) / the HIGHER threshold (f32): the joint
+    # exponent is the marginal one minus a square, so it passes whenever the marginal one does
+    sj, sm = 3.0e-7, 0.02
+    lj, lm = (int(np.floor(np.log2(sj))) - bits64) * K, (int(np.floor(np.log2(sm))) - bits64) * K
+    assert min(lj, lm) == lj and max(bits32 - np.floor(np.log2(sj)), bits32 - np.floor(np.log2(sm))) == bits32 - np.floor(np.log2(sj))
