@@ -664,6 +664,7 @@ template <int D, bool CKDE, int R>
 __device__ __forceinline__ void tile_f64_dot_gskip(const double* __restrict__ tp, const double* __restrict__ nb, int cnt,
                                                    const double (&yt)[R][D], const int (&ati)[R],
                                                    const double* __restrict__ tab, double (&sum_j)[R], double (&sum_m)[R]) {
+    static_assert(PBN_F64_HOIST, "the group-skipping tile takes the test-row norm on the integer side (ati) only");
     constexpr int DN = CKDE ? D - 1 : D;
     constexpr int G = pair_gskip_group(CKDE);
     int fl_j[R], fl_m[R], thr[R];
